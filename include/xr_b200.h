@@ -1,0 +1,132 @@
+/* xr_b200.h -- C ABI of libxr_b200.so, the B200 (sm_100a) implementation of the
+ * excitonic-renormalization Hamiltonian-build hot path of adutoi/QodeApplications.
+ *
+ * Two groups of entry points:
+ *
+ *  (A) The eleven legacy scalar symbols of the reference's general-XRCC/H_contractions.c,
+ *      with the identical C ABI the reference binds through qode.util.PyC.import_C
+ *      (general-XRCC/build_H.py:20-29, build_density_tensors.py:23-24,132):
+ *      PyInt = int64_t sizes, Double* = borrowed C-contiguous HOST buffers, PyFloat result
+ *      returned by value, no error channel.  Here each call copies its operands to the
+ *      GPU, runs one reduction kernel and returns the scalar -- a drop-in for the
+ *      per-element call pattern (and the parity surface for it), not the fast path.
+ *      On a CUDA failure they return NaN and xr_last_error() says why.
+ *
+ *  (B) Block-level entry points (xr_*): what replaces the reference's per-element Python
+ *      loops (general-XRCC/test_H.py:90-142) and per-diagram tensornet einsums
+ *      (hermitian-XRCC/diagrams/*.py via XRbase/XR_tensor.py:57).  They work on DEVICE
+ *      pointers, are asynchronous on the context's stream, and return 0 on success or a
+ *      negative xr_status (message from xr_last_error()).  One context per host thread;
+ *      a context must be created in the process that uses it (CUDA does not survive the
+ *      fork that general-XRCC/test_H.py:131 performs).
+ *
+ * All data are FP64, all offsets int64, nothing is complex.  No torch types appear here.
+ */
+#ifndef XR_B200_H
+#define XR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int64_t PyInt;      /* Qode's PyC_types.h names, as used by H_contractions.c */
+typedef double  PyFloat;
+typedef double  Double;
+
+/* ---------------------------------------------------------------- (A) legacy scalar ABI */
+/* replaces general-XRCC/H_contractions.c:22  */ PyFloat monomer(PyInt n_orb, Double* Rca, Double* Rccaa, Double* h, Double* V);
+/* replaces general-XRCC/H_contractions.c:48  */ PyFloat monomer_1e(PyInt n_orb, Double* Rca, Double* h);
+/* replaces general-XRCC/H_contractions.c:61  */ PyFloat monomer_2e(PyInt n_orb, Double* Rccaa, Double* V);
+/* replaces general-XRCC/H_contractions.c:80  */ PyFloat monomer_extPot(PyInt n_orb, Double* Rca, Double* h);
+/* replaces general-XRCC/H_contractions.c:95  */ PyFloat dimer_2min2pls(PyInt n_orb1, PyInt n_orb2, Double* Rcc1, Double* Raa2, Double* V);
+/* replaces general-XRCC/H_contractions.c:116 */ PyFloat dimer_1min1pls_1e(PyInt n_orb1, PyInt n_orb2, Double* Rc1, Double* Ra2, Double* h);
+/* replaces general-XRCC/H_contractions.c:129 */ PyFloat dimer_1min1pls_2e(PyInt n_orb1, PyInt n_orb2, Double* Rc1, Double* Rcca1, Double* Ra2, Double* Rcaa2, Double* V1112, Double* V1222);
+/* replaces general-XRCC/H_contractions.c:163 */ PyFloat dimer_ExEx(PyInt n_orb1, PyInt n_orb2, Double* Rca1, Double* Rca2, Double* V);
+/* replaces general-XRCC/H_contractions.c:184 */ PyFloat trimer_2min1pls1pls(PyInt n_orb1, PyInt n_orb2, PyInt n_orb3, Double* Rcc1, Double* Ra2, Double* Ra3, Double* V);
+/* replaces general-XRCC/H_contractions.c:208 */ PyFloat trimer_2pls1min1min(PyInt n_orb1, PyInt n_orb2, PyInt n_orb3, Double* Raa1, Double* Rc2, Double* Rc3, Double* V);
+/* replaces general-XRCC/H_contractions.c:232 */ PyFloat trimer_Ex1min1pls(PyInt n_orb1, PyInt n_orb2, PyInt n_orb3, Double* Rca1, Double* Rc2, Double* Ra3, Double* V);
+
+/* ------------------------------------------------------------------ (B) block-level ABI */
+typedef struct xr_ctx xr_ctx;
+
+enum xr_status {
+    XR_OK = 0,
+    XR_ERR_CUDA = -1,         /* a CUDA runtime call failed */
+    XR_ERR_ARG = -2,          /* bad argument (null pointer, unsupported size, misalignment) */
+    XR_ERR_NO_DEVICE = -3,    /* no usable sm_100 device: there is NO CPU fallback */
+    XR_ERR_UNSUPPORTED = -4
+};
+
+/* Thread-local message of the last failure in the calling thread. */
+const char* xr_last_error(void);
+
+/* Library identification: "xr_b200 <version> sm_100a". */
+const char* xr_version(void);
+
+/* Create a context on `device`.  With own_stream != 0 the context creates (and later destroys) its
+ * own non-blocking stream and `stream` is ignored; otherwise it borrows `stream`, a cudaStream_t
+ * (e.g. torch's current stream; NULL is the CUDA default stream). */
+int xr_ctx_create(int device, void* stream, int own_stream, xr_ctx** out);
+int xr_ctx_destroy(xr_ctx* ctx);
+int xr_ctx_set_stream(xr_ctx* ctx, void* stream);
+int xr_sync(xr_ctx* ctx);
+/* Number of xr kernels launched through this context since creation (bench.py's gpu_launches). */
+int xr_launch_count(xr_ctx* ctx, int64_t* count);
+int xr_device_info(xr_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes);
+
+/* Raw device memory for hosts that do not bring their own allocator. */
+int xr_malloc(xr_ctx* ctx, size_t bytes, void** dptr);
+int xr_free(xr_ctx* ctx, void* dptr);
+int xr_memset_zero(xr_ctx* ctx, void* dptr, size_t bytes);
+int xr_upload(xr_ctx* ctx, void* dst_device, const void* src_host, size_t bytes);      /* async on ctx stream */
+int xr_download(xr_ctx* ctx, void* dst_host, const void* src_device, size_t bytes);    /* async on ctx stream */
+
+/* The contraction engine.  Every pairwise rho x integral or factor x factor contraction of the
+ * hot path is one call of this (replaces tensornet/opt_einsum/BLAS below XRbase/XR_tensor.py:57
+ * and the n^4 loops of H_contractions.c):
+ *
+ *     C[ offM(m) + offN(n) ]  (=  or  +=)   alpha * sum_{k<K} A[m*lda + k] * B[n*ldb + k]
+ *
+ * with offM(m) = offM[m] if offM else m*ldc, offN(n) = offN[n] if offN else n.  The offset
+ * tables (device int64) let the epilogue write straight into the final Hamiltonian layout
+ * ([i0,i1,j0,j1] blocks, transposed permutations, charge-blocked or state_indices ordering)
+ * so no transpose/packing pass exists.  FP64 DMMA (mma.sync m8n8k4) with a multi-stage
+ * cp.async shared-memory pipeline; K tails are zero-filled, M/N tails predicated.
+ * Requirements: A, B, C device pointers to doubles.  Rows 16-byte aligned (even lda/ldb and
+ * 16-byte-aligned bases) take the vectorised path; anything else takes an 8-byte path. */
+int xr_gemm_scatter(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
+                    const double* A, int64_t lda, const double* B, int64_t ldb,
+                    double* C, const int64_t* offM, int64_t ldc, const int64_t* offN, int accumulate);
+
+/* dst[r*dst_ld + c] = alpha * src[r*src_ld + c]  (rows x cols, device to device).  Used to lay
+ * densities into zero-padded, sign-folded factor matrices. */
+int xr_copy2d_scaled(xr_ctx* ctx, double* dst, int64_t dst_ld, const double* src, int64_t src_ld,
+                     int64_t rows, int64_t cols, double alpha);
+
+/* C[idx[t]] (= or +=) value for t < count  (Kronecker-delta terms; idx is a device int64 table). */
+int xr_scatter_const(xr_ctx* ctx, double* C, const int64_t* idx, int64_t count, double value, int accumulate);
+
+/* Streamed three-factor contraction, the trimer classes of general-XRCC/build_H.py:103-188
+ * after the rho x V precontraction:
+ *
+ *     T[a,b,c] = alpha * sum_{r,s<n} W[a*ldw + r*n + s] * beta[b*ldbeta + r] * gamma[c*ldgamma + s]
+ *
+ * for a in [a_begin, a_end), b < Pb, c < Pc.  The Pa*Pb*Pc elements are formed tile by tile in
+ * registers by FP64 DMMA and handed to a consumer, because at the benchmark sizes they cannot
+ * be stored (1e13 elements per trimer):
+ *   XR_TRIMER_REDUCE      moments[0] += sum T, moments[1] += sum T^2   (device doubles, caller zeroes)
+ *   XR_TRIMER_MATERIALIZE C[offA[a] + offB[b] + offC[c]] = T[a,b,c]    (device int64 tables)
+ * n <= 48. */
+enum xr_trimer_mode { XR_TRIMER_REDUCE = 0, XR_TRIMER_MATERIALIZE = 1 };
+int xr_trimer_stream(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int64_t Pc, double alpha,
+                     const double* W, int64_t ldw, const double* beta, int64_t ldbeta,
+                     const double* gamma, int64_t ldgamma, int64_t a_begin, int64_t a_end, int mode,
+                     double* moments, double* C, const int64_t* offA, const int64_t* offB, const int64_t* offC);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XR_B200_H */

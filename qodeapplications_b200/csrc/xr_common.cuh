@@ -1,0 +1,100 @@
+// Shared declarations for libxr_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include "../../include/xr_b200.h"
+
+struct xr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 0;
+    int64_t launches = 0;
+    // scratch for the trimer stream (packed beta/gamma, per-CTA partial moments) and legacy scalars
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* pinned = nullptr;      // small pinned host staging (legacy scalars)
+    size_t pinned_bytes = 0;
+};
+
+void xr_set_error(const char* fmt, ...);
+int xr_ensure_scratch(xr_ctx* ctx, size_t bytes);
+
+#define XR_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t err__ = (call);                                                           \
+        if (err__ != cudaSuccess) {                                                           \
+            xr_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                 \
+                         cudaGetErrorString(err__));                                          \
+            return XR_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+#define XR_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            xr_set_error(__VA_ARGS__);                                                        \
+            return XR_ERR_ARG;                                                                \
+        }                                                                                     \
+    } while (0)
+
+// FP64 tensor instruction of sm_100a: D(8x8) += A(8x4, row) * B(4x8, col).
+// Fragment ownership (lane = 4*g + t, g = lane/4, t = lane%4):
+//   a = A[g][t],  b = B[t][g],  c0 = C[g][2t], c1 = C[g][2t+1]
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// cp.async (LDGSTS) with zero-fill of the bytes beyond src_bytes
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// mbarrier + 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) helpers
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}

@@ -1,0 +1,289 @@
+// xr_trimer_stream: streamed three-factor FP64 contraction for the trimer classes.
+//
+//   T[a,b,c] = alpha * sum_{r,s<n} W[a,r,s] * beta[b,r] * gamma[c,s]
+//
+// A persistent CTA takes a work item of TA=8 values of a times TB=16 values of b (128 "rows"),
+// forms X[(a,b),s] = sum_r W[a,r,s] beta[b,r] once in shared memory (negligible: 2*128*n^2 flop
+// against 2*128*Pc*n), keeps its DMMA A-fragments of X in registers, and then streams gamma in
+// tiles of 128 c through a two-slot shared-memory ring filled by 1-D bulk TMA (cp.async.bulk +
+// mbarrier).  Every 128x128 tile of T lives only in DMMA accumulators and is handed to the consumer
+// (moment reducer or scatter-store), so the 1e13-element trimer blocks never touch HBM.
+//
+// Roofline: FP64 tensor pipe.  Algorithmic flops 2*n per element; executed 2*4*ceil(n/4)
+// (k padded to the DMMA k=4: 18 -> 20) plus, in reduce mode, 2 FP64 ops per element on the same pipe.
+#include "xr_common.cuh"
+
+namespace {
+
+constexpr int TA = 8, TB = 16, ROWS = TA * TB, CT = 128, THREADS = 256;
+
+struct TrimerParams {
+    int n;
+    int64_t Pb, Pc;
+    double alpha;
+    const double* W;
+    int64_t ldw;
+    const double* betaP;    // [Pb][KP], zero padded in k
+    const double* gammaP;   // [c_tiles*CT][GS], zero padded in k and rows
+    int64_t a_begin, a_end;
+    int mode;
+    double* partials;       // [grid][2]
+    double* C;
+    const int64_t* offA;
+    const int64_t* offB;
+    const int64_t* offC;
+    int64_t tiles_b, n_items;
+    int c_tiles;
+};
+
+template <int KS>
+struct TrimerCfg {
+    static constexpr int KP = 4 * KS;
+    static constexpr int GS = (KP % 16 == 4 || KP % 16 == 12) ? KP : KP + 4;   // conflict-free fragment stride
+    static constexpr bool AREG = KS <= 5;
+    static constexpr size_t SMEM = (size_t)(ROWS + 2 * CT) * GS * sizeof(double) + 64;
+};
+
+template <int KS>
+__global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerParams p) {
+    using Cfg = TrimerCfg<KS>;
+    constexpr int KP = Cfg::KP, GS = Cfg::GS;
+    constexpr bool AREG = Cfg::AREG;
+    constexpr int MI = 4, NJ = 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* Gs = reinterpret_cast<double*>(smem_raw);              // [2][CT][GS]   (bulk-copy destinations first: 16B aligned)
+    double* Xs = Gs + 2 * CT * GS;                                  // [ROWS][GS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Xs + ROWS * GS);   // [2]
+    __shared__ double red[2][THREADS / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    constexpr uint32_t TILE_BYTES = CT * GS * sizeof(double);
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    uint32_t phase0 = 0, phase1 = 0;
+    uint32_t it = 0;
+    double s1 = 0.0, s2 = 0.0;
+    const int n = p.n;
+
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int64_t a0 = p.a_begin + (item / p.tiles_b) * TA;
+        const int64_t b0 = (item % p.tiles_b) * TB;
+
+        // first gamma tile of this item (slot it&1 was released by the trailing barrier of the last tile)
+        if (tid == 0) {
+            uint64_t* bar = &bars[it & 1];
+            mbar_expect_tx(bar, TILE_BYTES);
+            bulk_copy_g2s(Gs + (size_t)(it & 1) * CT * GS, p.gammaP, TILE_BYTES, bar);
+        }
+
+        // X[(a,b), s] = sum_r W[a, r*n + s] * beta[b, r]
+        for (int idx = tid; idx < ROWS * KP; idx += THREADS) {
+            const int row = idx / KP, s = idx - row * KP;
+            const int64_t a = a0 + row / TB, b = b0 + row % TB;
+            double v = 0.0;
+            if (a < p.a_end && b < p.Pb && s < n) {
+                const double* w = p.W + a * p.ldw + s;
+                const double* be = p.betaP + b * KP;
+                for (int r = 0; r < n; ++r) v = fma(__ldg(w + (int64_t)r * n), __ldg(be + r), v);
+            }
+            Xs[row * GS + s] = v;
+        }
+        __syncthreads();
+
+        double areg[AREG ? MI : 1][AREG ? KS : 1];
+        if (AREG) {
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) areg[i][ks] = Xs[(32 * wm + 8 * i + g) * GS + 4 * ks + t];
+        }
+
+        for (int ct = 0; ct < p.c_tiles; ++ct, ++it) {
+            const uint32_t buf = it & 1;
+            if (tid == 0 && ct + 1 < p.c_tiles) {
+                uint64_t* bar = &bars[buf ^ 1];
+                mbar_expect_tx(bar, TILE_BYTES);
+                bulk_copy_g2s(Gs + (size_t)(buf ^ 1) * CT * GS, p.gammaP + (size_t)(ct + 1) * CT * GS, TILE_BYTES, bar);
+            }
+            if (buf == 0) {
+                mbar_wait(&bars[0], phase0);
+                phase0 ^= 1;
+            } else {
+                mbar_wait(&bars[1], phase1);
+                phase1 ^= 1;
+            }
+
+            double acc[MI][NJ][2];
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+            const double* gs = Gs + (size_t)buf * CT * GS + (64 * wn + g) * GS + t;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                double b[NJ];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) b[j] = gs[j * 8 * GS + 4 * ks];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) {
+                    const double a = AREG ? areg[AREG ? i : 0][AREG ? ks : 0] : Xs[(32 * wm + 8 * i + g) * GS + 4 * ks + t];
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a, b[j]);
+                }
+            }
+            __syncthreads();   // every warp is done with Gs[buf] (and Xs): the slot may be refilled
+
+            if (p.mode == XR_TRIMER_REDUCE) {
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        s1 += acc[i][j][0] + acc[i][j][1];
+                        s2 = fma(acc[i][j][0], acc[i][j][0], s2);
+                        s2 = fma(acc[i][j][1], acc[i][j][1], s2);
+                    }
+            } else {
+                const int64_t c_base = (int64_t)ct * CT + 64 * wn + 2 * t;
+#pragma unroll
+                for (int i = 0; i < MI; ++i) {
+                    const int row = 32 * wm + 8 * i + g;
+                    const int64_t a = a0 + row / TB, b = b0 + row % TB;
+                    if (a >= p.a_end || b >= p.Pb) continue;
+                    const int64_t oab = p.offA[a] + p.offB[b];
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const int64_t c = c_base + 8 * j;
+                        if (c < p.Pc) p.C[oab + p.offC[c]] = p.alpha * acc[i][j][0];
+                        if (c + 1 < p.Pc) p.C[oab + p.offC[c + 1]] = p.alpha * acc[i][j][1];
+                    }
+                }
+            }
+        }
+    }
+
+    if (p.mode == XR_TRIMER_REDUCE) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            red[0][warp] = s1;
+            red[1][warp] = s2;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double t1 = 0.0, t2 = 0.0;
+            for (int w = 0; w < THREADS / 32; ++w) {
+                t1 += red[0][w];
+                t2 += red[1][w];
+            }
+            p.partials[2 * blockIdx.x] = t1;
+            p.partials[2 * blockIdx.x + 1] = t2;
+        }
+    }
+}
+
+__global__ void trimer_finalize_kernel(const double* partials, int count, double alpha, double* moments) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int i = 0; i < count; ++i) {   // fixed order: bit-reproducible
+            t1 += partials[2 * i];
+            t2 += partials[2 * i + 1];
+        }
+        moments[0] += alpha * t1;
+        moments[1] += alpha * alpha * t2;
+    }
+}
+
+template <int KS>
+int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbeta, const double* gamma, int64_t ldgamma,
+                  double* moments) {
+    using Cfg = TrimerCfg<KS>;
+    const int64_t n_a = p.a_end - p.a_begin;
+    const int64_t tiles_a = (n_a + TA - 1) / TA;
+    p.tiles_b = (p.Pb + TB - 1) / TB;
+    p.n_items = tiles_a * p.tiles_b;
+    p.c_tiles = (int)((p.Pc + CT - 1) / CT);
+    int grid = (int)(p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count);
+
+    // scratch: packed beta | packed gamma | partials
+    const size_t beta_bytes = (size_t)p.Pb * Cfg::KP * sizeof(double);
+    const size_t gamma_bytes = (size_t)p.c_tiles * CT * Cfg::GS * sizeof(double);
+    const size_t beta_off = 0, gamma_off = (beta_bytes + 255) / 256 * 256;
+    const size_t part_off = gamma_off + (gamma_bytes + 255) / 256 * 256;
+    int rc = xr_ensure_scratch(ctx, part_off + (size_t)grid * 2 * sizeof(double) + 256);
+    if (rc != XR_OK) return rc;
+    char* base = static_cast<char*>(ctx->scratch);
+    double* betaP = reinterpret_cast<double*>(base + beta_off);
+    double* gammaP = reinterpret_cast<double*>(base + gamma_off);
+    double* partials = reinterpret_cast<double*>(base + part_off);
+    XR_CUDA(cudaMemsetAsync(base, 0, part_off, ctx->stream));
+    rc = xr_copy2d_scaled(ctx, betaP, Cfg::KP, beta, ldbeta, p.Pb, p.n, 1.0);
+    if (rc != XR_OK) return rc;
+    rc = xr_copy2d_scaled(ctx, gammaP, Cfg::GS, gamma, ldgamma, p.Pc, p.n, 1.0);
+    if (rc != XR_OK) return rc;
+    p.betaP = betaP;
+    p.gammaP = gammaP;
+    p.partials = partials;
+
+    auto kernel = trimer_stream_kernel<KS>;
+    XR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    kernel<<<grid, THREADS, Cfg::SMEM, ctx->stream>>>(p);
+    XR_CUDA(cudaGetLastError());
+    ctx->launches++;
+    if (p.mode == XR_TRIMER_REDUCE) {
+        trimer_finalize_kernel<<<1, 32, 0, ctx->stream>>>(partials, grid, p.alpha, moments);
+        XR_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    return XR_OK;
+}
+
+}  // namespace
+
+extern "C" int xr_trimer_stream(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int64_t Pc, double alpha, const double* W,
+                                int64_t ldw, const double* beta, int64_t ldbeta, const double* gamma, int64_t ldgamma,
+                                int64_t a_begin, int64_t a_end, int mode, double* moments, double* C, const int64_t* offA,
+                                const int64_t* offB, const int64_t* offC) {
+    XR_REQUIRE(ctx, "xr_trimer_stream: null ctx");
+    XR_REQUIRE(n >= 1 && n <= 48, "xr_trimer_stream: n=%d unsupported (1..48)", n);
+    XR_REQUIRE(a_begin >= 0 && a_end <= Pa && a_begin <= a_end, "xr_trimer_stream: bad a range [%lld,%lld) of %lld",
+               (long long)a_begin, (long long)a_end, (long long)Pa);
+    if (a_begin == a_end || Pb <= 0 || Pc <= 0) return XR_OK;
+    XR_REQUIRE(W && beta && gamma, "xr_trimer_stream: null operand");
+    XR_REQUIRE(ldw >= (int64_t)n * n && ldbeta >= n && ldgamma >= n, "xr_trimer_stream: leading dimension too small");
+    if (mode == XR_TRIMER_REDUCE) {
+        XR_REQUIRE(moments, "xr_trimer_stream: reduce mode needs moments");
+    } else if (mode == XR_TRIMER_MATERIALIZE) {
+        XR_REQUIRE(C && offA && offB && offC, "xr_trimer_stream: materialize mode needs C and offset tables");
+    } else {
+        XR_REQUIRE(false, "xr_trimer_stream: unknown mode %d", mode);
+    }
+    TrimerParams p{};
+    p.n = n;
+    p.Pb = Pb;
+    p.Pc = Pc;
+    p.alpha = alpha;
+    p.W = W;
+    p.ldw = ldw;
+    p.a_begin = a_begin;
+    p.a_end = a_end;
+    p.mode = mode;
+    p.C = C;
+    p.offA = offA;
+    p.offB = offB;
+    p.offC = offC;
+    if (n <= 8) return launch_trimer<2>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+    if (n <= 20) return launch_trimer<5>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+    return launch_trimer<12>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+}

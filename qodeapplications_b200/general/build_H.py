@@ -1,0 +1,455 @@
+"""B200 drop-in for the reference's general-XRCC/build_H.py.
+
+``build_matrix_elements(supersystem, integrals, nuc_repulsion)`` keeps the reference's constructor
+and its ``monomer / dimer / trimer`` element accessors (general-XRCC/build_H.py:37-188), so
+general-XRCC/test_H.py:49-58 runs unchanged -- but an element is never computed on its own.  The
+first request for an element of a (fragment tuple) block builds the WHOLE block on the GPU and the
+accessor then reads the cached result.  New block-level methods (``H1``, ``H2``, ``H3``,
+``H3_moments``) return whole matrices in test_H.py's layout (test_H.py:65-107: state order =
+``fragment.state_indices``, product basis row-major) and are what a batched caller should use.
+
+How a block is built: flatten each fragment's (bra,ket) state pair
+into one index P; for every charge-transfer class the block is ``A[P1,K] . B[P2,K]^T`` with
+
+  class (d1)   K           A (fragment 1)                               B (fragment 2)
+  0            n2^2 + 2    4 ca1.V | delta1 | U.ca1 + nuc*delta1         ca2 | U.ca2 | delta2
+  -2 / +2      n^2         cc.V    (or aa raw)                           aa raw (or cc.V)
+  -1 / +1      n1 + n2     (h + 2 cca.V).c | c     (or a | 2 V.caa)      sign2 * (a | 2 V.caa)  (or ...)
+
+so each class is one ``xr_gemm_scatter`` whose offset tables write straight into H2's final
+layout; the precontractions ``rho . V`` are the same kernel with K = n^2 or n^3.  Every index
+permutation is applied to the tiny integral blocks on the host, never to a density.  Trimer
+classes are ``sum_rs W[Pk,r,s] beta[Pb,r] gamma[Pc,s]`` streamed by ``xr_trimer_stream``.
+
+All arithmetic runs in libxr_b200.so (hand-written sm_100a CUDA); there is no CPU path.
+"""
+import itertools
+import numpy
+import torch
+
+from .. import lib as _lib
+from ..device import Device
+
+
+def _parity(n_elec_ref, chg):
+    """build_H.py:68,113-114"""
+    return -1.0 if (n_elec_ref - chg) % 2 else 1.0
+
+
+class _FragInfo(object):
+    def __init__(self, fragment, n_orb):
+        self.n_orb = n_orb
+        self.n_elec_ref = fragment.n_elec_ref
+        rho = fragment.rho
+        self.n_states = {}
+        for (ci, cj), block in rho["ca"].items():
+            if ci == cj:
+                self.n_states[ci] = len(block)
+        if hasattr(fragment, "state_indices"):
+            self.state_indices = list(fragment.state_indices)
+        else:   # general-XRCC/Be631g.py:81-85 with ref_state=(0,0)
+            ref = 0 if 0 in self.n_states else sorted(self.n_states)[0]
+            self.state_indices = [(ref, i) for i in range(self.n_states[ref])]
+            for chg in self.n_states:
+                if chg != ref:
+                    self.state_indices += [(chg, i) for i in range(self.n_states[chg])]
+        self.dim = len(self.state_indices)
+        where = {state: p for p, state in enumerate(self.state_indices)}
+        self.charges = list(self.n_states)
+        self.pos = {chg: numpy.array([where.get((chg, i), -1) for i in range(n)], dtype=numpy.int64)
+                    for chg, n in self.n_states.items()}
+        for chg, p in self.pos.items():
+            if (p < 0).any():
+                raise ValueError("state_indices does not list every state of charge %r" % (chg,))
+        self.where = where
+
+    def sectors(self, delta):
+        """[(bra charge, ket charge)] with bra - ket = delta, both present"""
+        return [(ci, ci - delta) for ci in self.charges if (ci - delta) in self.n_states]
+
+
+class _PairClass(object):
+    """All (bra,ket) state pairs of one fragment with bra charge - ket charge = delta, optionally
+    restricted to bra states whose matrix position lies in [bra_lo, bra_hi)."""
+    def __init__(self, info, delta, bra_range=None):
+        self.delta = delta
+        self.sectors = []          # (ci, cj, i_lo, i_hi, row_offset)
+        rows = 0
+        for ci, cj in info.sectors(delta):
+            Ni, Nj = info.n_states[ci], info.n_states[cj]
+            i_lo, i_hi = 0, Ni
+            if bra_range is not None:
+                inside = numpy.nonzero((info.pos[ci] >= bra_range[0]) & (info.pos[ci] < bra_range[1]))[0]
+                if len(inside) == 0:
+                    continue
+                i_lo, i_hi = int(inside[0]), int(inside[-1]) + 1
+                if i_hi - i_lo != len(inside):
+                    raise NotImplementedError("bra slab is not contiguous inside charge sector %r" % (ci,))
+            if i_hi > i_lo and Nj > 0:
+                self.sectors.append((ci, cj, i_lo, i_hi, rows))
+                rows += (i_hi - i_lo) * Nj
+        self.P = rows
+
+    def offsets(self, info, bra_stride, ket_stride, bra_base=0):
+        """int64[P]: (pos[ci][i]-bra_base)*bra_stride + pos[cj][j]*ket_stride for every row"""
+        out = numpy.empty(self.P, dtype=numpy.int64)
+        for ci, cj, i_lo, i_hi, off in self.sectors:
+            Nj = info.n_states[cj]
+            block = ((info.pos[ci][i_lo:i_hi] - bra_base) * bra_stride)[:, None] + (info.pos[cj] * ket_stride)[None, :]
+            out[off:off + (i_hi - i_lo) * Nj] = block.reshape(-1)
+        return out
+
+    def diagonal_rows(self, info):
+        """rows with identical bra and ket state (only meaningful for delta == 0)"""
+        rows = []
+        for ci, cj, i_lo, i_hi, off in self.sectors:
+            if ci == cj:
+                Nj = info.n_states[cj]
+                i = numpy.arange(i_lo, i_hi, dtype=numpy.int64)
+                rows.append(off + (i - i_lo) * Nj + i)
+        return numpy.concatenate(rows) if rows else numpy.zeros(0, dtype=numpy.int64)
+
+
+def _even(k):
+    return k + (k & 1)
+
+
+class build_matrix_elements(object):
+    def __init__(self, supersystem, integrals, nuc_repulsion, device=None):
+        n_elec = [fragment.n_elec_ref for fragment in supersystem]
+        rho = [fragment.rho for fragment in supersystem]
+        self.data = rho, integrals.T, integrals.U, integrals.V, nuc_repulsion, n_elec     # as build_H.py:41
+        self._supersystem = supersystem
+        self._device_arg = device
+        self._dev = None
+        self._info = None
+        self._rho_dev = {}
+        self._int_dev = {}
+        self._idx_dev = {}
+        self._H1 = {}
+        self._H2 = {}
+        self._H3 = {}
+
+    # ------------------------------------------------------------------ reference accessors
+    def monomer(self, fragment, I, J):
+        """build_H.py:42-55"""
+        H = self._H1.get(fragment)
+        if H is None:
+            H = self._H1[fragment] = self.H1(fragment)
+        info = self._frag(fragment)
+        return float(H[info.where[tuple(I)], info.where[tuple(J)]])
+
+    def dimer(self, fragments, I, J):
+        """build_H.py:56-102"""
+        fragments = tuple(fragments)
+        H = self._H2.get(fragments)
+        if H is None:
+            H = self._H2[fragments] = self.H2(*fragments)
+        f1, f2 = (self._frag(m) for m in fragments)
+        i = f1.where[tuple(I[0])] * f2.dim + f2.where[tuple(I[1])]
+        j = f1.where[tuple(J[0])] * f2.dim + f2.where[tuple(J[1])]
+        return float(H[i, j])
+
+    def trimer(self, fragments, I, J):
+        """build_H.py:103-188"""
+        fragments = tuple(fragments)
+        H = self._H3.get(fragments)
+        if H is None:
+            H = self._H3[fragments] = self.H3(*fragments)
+        f = [self._frag(m) for m in fragments]
+        i = (f[0].where[tuple(I[0])] * f[1].dim + f[1].where[tuple(I[1])]) * f[2].dim + f[2].where[tuple(I[2])]
+        j = (f[0].where[tuple(J[0])] * f[1].dim + f[1].where[tuple(J[1])]) * f[2].dim + f[2].where[tuple(J[2])]
+        return float(H[i, j])
+
+    # ----------------------------------------------------------------------------- plumbing
+    @property
+    def dev(self):
+        if self._dev is None:
+            self._dev = self._device_arg if isinstance(self._device_arg, Device) else Device(self._device_arg)
+        return self._dev
+
+    def _frag(self, m):
+        if self._info is None:
+            T = self.data[1]
+            self._info = [_FragInfo(f, T[k, k].shape[0]) for k, f in enumerate(self._supersystem)]
+        return self._info[m]
+
+    def _rho(self, m, op, sector):
+        """device tensor [N_bra*N_ket, n^k] of rho[m][op][sector]"""
+        key = (m, op, sector)
+        if key not in self._rho_dev:
+            info = self._frag(m)
+            block = self.data[0][m][op][sector]
+            arr = numpy.asarray(block, dtype=numpy.float64)
+            Ni, Nj = info.n_states[sector[0]], info.n_states[sector[1]]
+            self._rho_dev[key] = self.dev.upload(arr.reshape(Ni * Nj, -1))
+        return self._rho_dev[key]
+
+    def _ints(self, key, make):
+        """device copy of a (permuted) integral block, cached by key"""
+        if key not in self._int_dev:
+            self._int_dev[key] = self.dev.upload(make())
+        return self._int_dev[key]
+
+    def _index(self, array):
+        return self.dev.upload(array, dtype=numpy.int64)
+
+    def drop_caches(self, densities=False):
+        self._H1.clear(); self._H2.clear(); self._H3.clear()
+        if densities:
+            self._rho_dev.clear(); self._int_dev.clear()
+
+    def preload(self, fragments=None, ops=("a", "c", "aa", "cc", "ca", "caa", "cca")):
+        """Upload every density of the given fragments now (so later builds start HBM-resident)."""
+        rho = self.data[0]
+        for m in (range(len(rho)) if fragments is None else fragments):
+            for op in ops:
+                for sector in rho[m].get(op, {}):
+                    self._rho(m, op, sector)
+
+    # ----- factor builders: fill columns [col0, col0+F) of a [P, ld] class buffer -------------
+    def _fill_raw(self, out, ld, col0, m, op, cls, sign=None):
+        ctx = self.dev.ctx
+        info = self._frag(m)
+        for ci, cj, i_lo, i_hi, off in cls.sectors:
+            Nj = info.n_states[cj]
+            src = self._rho(m, op, (ci, cj))
+            F = src.shape[1]
+            alpha = 1.0 if sign is None else sign(ci)
+            ctx.copy2d_scaled(out.data_ptr() + 8 * (off * ld + col0), ld, src.data_ptr() + 8 * (i_lo * Nj * F), F,
+                              (i_hi - i_lo) * Nj, F, alpha)
+
+    def _fill_contracted(self, out, ld, col0, m, op, cls, Wt, scale=1.0, sign=None, accumulate=False):
+        """out[:, col0:col0+F] (+)= scale*sign * rho[P,K] . Wt[F,K]^T"""
+        ctx = self.dev.ctx
+        info = self._frag(m)
+        F, K = Wt.shape
+        for ci, cj, i_lo, i_hi, off in cls.sectors:
+            Nj = info.n_states[cj]
+            src = self._rho(m, op, (ci, cj))
+            assert src.shape[1] == K, (op, src.shape, K)
+            alpha = scale * (1.0 if sign is None else sign(ci))
+            ctx.gemm_scatter((i_hi - i_lo) * Nj, F, K, alpha, src.data_ptr() + 8 * (i_lo * Nj * K), K, Wt, K,
+                             out.data_ptr() + 8 * (off * ld + col0), None, ld, None, accumulate)
+
+    # -------------------------------------------------------------------------------- blocks
+    def H1(self, m):
+        """H1[m] (dense, host ndarray) -- build_H.py:42-55 for every state pair at once."""
+        return self.dev.download(self.H1_device(m))
+
+    def H1_device(self, m):
+        rho, T, U, V, nuc, n_elec = self.data
+        info = self._frag(m)
+        ctx, n = self.dev.ctx, info.n_orb
+        H = self.dev.zeros((info.dim, info.dim))
+        cls = _PairClass(info, 0)
+        h = self._ints(("h1", m), lambda: (T[m, m] + U[m, m, m]).reshape(1, n * n))
+        off = self._index(cls.offsets(info, info.dim, 1))
+        one = self._ints(("one",), lambda: numpy.ones((1, 2)))
+        for ci, cj, i_lo, i_hi, row0 in cls.sectors:
+            N = info.n_states[ci]
+            ca = self._rho(m, "ca", (ci, cj))
+            ctx.gemm_scatter(N * N, 1, n * n, 1.0, ca, n * n, h, n * n, H, off.data_ptr() + 8 * row0, 0, None, False)
+            scal = self.dev.upload(numpy.asarray(rho[m]["ccaa"][(ci, cj)], dtype=numpy.float64).reshape(N * N, 1))
+            ctx.gemm_scatter(N * N, 1, 1, 1.0, scal, 1, one, 2, H, off.data_ptr() + 8 * row0, 0, None, True)
+        diag = self._index(numpy.arange(info.dim, dtype=numpy.int64) * (info.dim + 1))
+        ctx.scatter_const(H, diag, info.dim, float(nuc[m, m]), True)
+        return H
+
+    def H2(self, m1, m2):
+        """H2[m1][m2] (dense, host ndarray) in test_H.py:101-107 ordering."""
+        return self.dev.download(self.H2_device(m1, m2))
+
+    def H2_device(self, m1, m2, bra_range=None, out=None):
+        """Device tensor [(hi-lo)*dim2, dim1*dim2]: rows of H2[m1][m2] whose fragment-1 bra state has
+        matrix position in bra_range=[lo,hi) (default: all).  Rows outside every charge-allowed class
+        stay zero (build_H.py:65)."""
+        rho, T, U, V, nuc, n_elec = self.data
+        f1, f2 = self._frag(m1), self._frag(m2)
+        n1, n2 = f1.n_orb, f2.n_orb
+        ctx = self.dev.ctx
+        lo, hi = (0, f1.dim) if bra_range is None else bra_range
+        D = f1.dim * f2.dim
+        if out is None:
+            out = self.dev.zeros(((hi - lo) * f2.dim, D))
+        else:
+            assert out.shape == ((hi - lo) * f2.dim, D)
+            out.zero_()
+        s2 = lambda c2: _parity(f2.n_elec_ref, c2)
+
+        for d1 in (-2, -1, 0, 1, 2):
+            c1 = _PairClass(f1, d1, (lo, hi) if bra_range is not None else None)
+            c2 = _PairClass(f2, -d1)
+            if c1.P == 0 or c2.P == 0:
+                continue
+            off1 = self._index(c1.offsets(f1, f2.dim * D, f2.dim, bra_base=lo))
+            off2 = self._index(c2.offsets(f2, D, 1))
+            if d1 == 0:
+                K = n2 * n2 + 2
+                ld = _even(K)
+                A, B = self.dev.zeros((c1.P, ld)), self.dev.zeros((c2.P, ld))
+                # 4 * sum_pr ca1[p,r] V[p,q,r,s] -> columns (q,s)
+                Vt = self._ints(("ExEx", m1, m2), lambda: V[m1, m2, m1, m2].transpose(1, 3, 0, 2).reshape(n2 * n2, n1 * n1))
+                self._fill_contracted(A, ld, 0, m1, "ca", c1, Vt, scale=4.0)
+                u1 = self._ints(("extPot", m2, m1), lambda: U[m2, m1, m1].reshape(1, n1 * n1))
+                self._fill_contracted(A, ld, n2 * n2 + 1, m1, "ca", c1, u1)
+                d1rows = c1.diagonal_rows(f1)
+                if len(d1rows):
+                    ctx.scatter_const(A, self._index(d1rows * ld + n2 * n2), len(d1rows), 1.0, False)
+                    ctx.scatter_const(A, self._index(d1rows * ld + n2 * n2 + 1), len(d1rows), float(nuc[m1, m2]), True)
+                self._fill_raw(B, ld, 0, m2, "ca", c2)
+                u2 = self._ints(("extPot", m1, m2), lambda: U[m1, m2, m2].reshape(1, n2 * n2))
+                self._fill_contracted(B, ld, n2 * n2, m2, "ca", c2, u2)
+                d2rows = c2.diagonal_rows(f2)
+                if len(d2rows):
+                    ctx.scatter_const(B, self._index(d2rows * ld + n2 * n2 + 1), len(d2rows), 1.0, False)
+            elif d1 == -2:
+                K = n2 * n2
+                ld = _even(K)
+                A, B = self.dev.zeros((c1.P, ld)), self.dev.zeros((c2.P, ld))
+                # sum_pq cc1[p,q] V[p,q,r,s] -> column (s,r) to meet aa2[s,r]
+                Vt = self._ints(("2min2pls", m1, m2), lambda: V[m1, m1, m2, m2].transpose(3, 2, 0, 1).reshape(n2 * n2, n1 * n1))
+                self._fill_contracted(A, ld, 0, m1, "cc", c1, Vt)
+                self._fill_raw(B, ld, 0, m2, "aa", c2)
+            elif d1 == +2:
+                K = n1 * n1
+                ld = _even(K)
+                A, B = self.dev.zeros((c1.P, ld)), self.dev.zeros((c2.P, ld))
+                Vt = self._ints(("2min2pls", m2, m1), lambda: V[m2, m2, m1, m1].transpose(3, 2, 0, 1).reshape(n1 * n1, n2 * n2))
+                self._fill_raw(A, ld, 0, m1, "aa", c1)
+                self._fill_contracted(B, ld, 0, m2, "cc", c2, Vt)
+            else:
+                # x creates (delta_x = -1), y annihilates; A columns: [n_y | n_x] meeting B's [a_y-part | c_x-part]
+                x, y = (m1, m2) if d1 == -1 else (m2, m1)
+                fx, fy = self._frag(x), self._frag(y)
+                nx, ny = fx.n_orb, fy.n_orb
+                K = ny + nx
+                ld = _even(K)
+                A, B = self.dev.zeros((c1.P, ld)), self.dev.zeros((c2.P, ld))
+                hT = self._ints(("h1e", m1, m2, x, y), lambda: (T[x, y] + U[m1, x, y] + U[m2, x, y]).T.copy())          # [q, p]
+                V1 = self._ints(("1112", x, y), lambda: V[x, x, x, y].transpose(3, 1, 0, 2).reshape(ny, nx ** 3))      # [s,(q,p,r)]
+                V2 = self._ints(("1222", x, y), lambda: V[x, y, y, y].transpose(0, 1, 3, 2).reshape(nx, ny ** 3))      # [p,(q,s,r)]
+                sign = (lambda c: s2(c)) if d1 == -1 else (lambda c: -s2(c))
+                cx, cy = (c1, c2) if d1 == -1 else (c2, c1)
+                X, Y = (A, B) if d1 == -1 else (B, A)
+                sx = sign if x == m2 else None      # the sign rides on fragment 2's factor rows
+                sy = sign if y == m2 else None
+                # creator side: [ h^T.c + 2 V1112.cca | c ]
+                self._fill_contracted(X, ld, 0, x, "c", cx, hT, sign=sx)
+                self._fill_contracted(X, ld, 0, x, "cca", cx, V1, scale=2.0, sign=sx, accumulate=True)
+                self._fill_raw(X, ld, ny, x, "c", cx, sign=sx)
+                # annihilator side: [ a | 2 V1222.caa ]
+                self._fill_raw(Y, ld, 0, y, "a", cy, sign=sy)
+                self._fill_contracted(Y, ld, ny, y, "caa", cy, V2, scale=2.0, sign=sy)
+            ctx.gemm_scatter(c1.P, c2.P, K, 1.0, A, ld, B, ld, out, off1, 0, off2, False)
+        return out
+
+    # ------------------------------------------------------------------------------ trimers
+    def _trimer_classes(self, ms):
+        """Yields (role positions (k,b,c), W builder, beta op, gamma op, deltas, sign info) for the 12
+        charge-transfer patterns of build_H.py:116-186."""
+        for k in range(3):
+            o0, o1 = [o for o in range(3) if o != k]
+            yield dict(kind="2min", k=k, b=o0, c=o1, dk=-2, db=+1, dc=+1, flip=False)
+            yield dict(kind="2pls", k=k, b=o0, c=o1, dk=+2, db=-1, dc=-1, flip=False)
+            yield dict(kind="ex", k=k, b=o0, c=o1, dk=0, db=-1, dc=+1, flip=False)     # creator before annihilator
+            yield dict(kind="ex", k=k, b=o1, c=o0, dk=0, db=-1, dc=+1, flip=True)      # creator after annihilator
+
+    def _trimer_factors(self, ms, cl, a_range=None):
+        """Device factors of one trimer class: W [Pk, n_b*n_c], beta [Pb, n_b], gamma [Pc, n_c] with the
+        build_H.py:113-114 signs folded into the rows, and the three pair classes."""
+        rho, T, U, V, nuc, n_elec = self.data
+        f = [self._frag(m) for m in ms]
+        k, b, c = cl["k"], cl["b"], cl["c"]
+        mk, mb, mc = ms[k], ms[b], ms[c]
+        nk, nb, nc = f[k].n_orb, f[b].n_orb, f[c].n_orb
+        ck, cb, cc = _PairClass(f[k], cl["dk"]), _PairClass(f[b], cl["db"]), _PairClass(f[c], cl["dc"])
+        if ck.P == 0 or cb.P == 0 or cc.P == 0:
+            return None
+        # base = {0: s3, 1: s2*s3, 2: s2}[k]: s2 rides on the fragment at position 1, s3 on position 2
+        carries = {0: (2,), 1: (1, 2), 2: (1,)}[k]
+        def sign_of(pos):
+            if pos in carries:
+                return lambda chg: _parity(f[pos].n_elec_ref, chg)
+            return None
+        ldw = _even(nb * nc)
+        W = self.dev.zeros((ck.P, ldw))
+        if cl["kind"] == "2min":      # 2 sum V[k,k,b,c][p,q,r,s] cc_k[q,p]
+            Vt = self._ints(("t2min", mk, mb, mc), lambda: V[mk, mk, mb, mc].transpose(2, 3, 1, 0).reshape(nb * nc, nk * nk))
+            self._fill_contracted(W, ldw, 0, mk, "cc", ck, Vt, scale=2.0, sign=sign_of(k))
+            op_b = op_c = "a"
+        elif cl["kind"] == "2pls":    # 2 sum V[b,c,k,k][r,s,p,q] aa_k[q,p]
+            Vt = self._ints(("t2pls", mk, mb, mc), lambda: V[mb, mc, mk, mk].transpose(0, 1, 3, 2).reshape(nb * nc, nk * nk))
+            self._fill_contracted(W, ldw, 0, mk, "aa", ck, Vt, scale=2.0, sign=sign_of(k))
+            op_b = op_c = "c"
+        else:                         # 4 sum V[k,cre,k,ann][p,r,q,s] ca_k[p,q] + delta_k U[k,cre,ann][r,s]
+            Vt = self._ints(("tex", mk, mb, mc), lambda: V[mk, mb, mk, mc].transpose(1, 3, 0, 2).reshape(nb * nc, nk * nk))
+            self._fill_contracted(W, ldw, 0, mk, "ca", ck, Vt, scale=4.0, sign=sign_of(k))
+            # delta(i_k, j_k) * U[k,cre,ann][r,s] on the diagonal rows: rank-1 update through the same kernel
+            drows = ck.diagonal_rows(f[k])
+            if len(drows):
+                sg = sign_of(k)
+                dvec = numpy.zeros((ck.P, 2))
+                for ci, cj, i_lo, i_hi, off in ck.sectors:
+                    if ci == cj:
+                        i = numpy.arange(i_lo, i_hi)
+                        dvec[off + (i - i_lo) * f[k].n_states[cj] + i, 0] = 1.0 if sg is None else sg(ci)
+                Uv = self._ints(("tU", mk, mb, mc), lambda: numpy.stack([U[mk, mb, mc].reshape(nb * nc), numpy.zeros(nb * nc)], axis=1))
+                self.dev.ctx.gemm_scatter(ck.P, nb * nc, 1, 1.0, self.dev.upload(dvec), 2, Uv, 2, W, None, ldw, None, True)
+            op_b, op_c = "c", "a"
+        beta = self.dev.zeros((cb.P, _even(nb)))
+        gamma = self.dev.zeros((cc.P, _even(nc)))
+        self._fill_raw(beta, _even(nb), 0, mb, op_b, cb, sign=sign_of(b))
+        self._fill_raw(gamma, _even(nc), 0, mc, op_c, cc, sign=sign_of(c))
+        alpha = -1.0 if cl["flip"] else 1.0
+        return dict(W=W, ldw=ldw, beta=beta, gamma=gamma, ck=ck, cb=cb, cc=cc, alpha=alpha, n=nb, k=k, b=b, c=c)
+
+    def H3(self, m1, m2, m3):
+        """H3[m1][m2][m3] dense (host ndarray), test_H.py:113-126 ordering.  Only for sizes that fit."""
+        return self.dev.download(self.H3_device(m1, m2, m3))
+
+    def H3_device(self, m1, m2, m3):
+        ms = (m1, m2, m3)
+        f = [self._frag(m) for m in ms]
+        D = f[0].dim * f[1].dim * f[2].dim
+        if D * D * 8 > 64 * (1 << 30):
+            raise MemoryError("dense H3 would need %.1f GB; use H3_moments / the tile stream" % (D * D * 8 / 2 ** 30))
+        H = self.dev.zeros((D, D))
+        stride = (f[1].dim * f[2].dim, f[2].dim, 1)
+        ctx = self.dev.ctx
+        for cl in self._trimer_classes(ms):
+            fac = self._trimer_factors(ms, cl)
+            if fac is None:
+                continue
+            if fac["n"] != f[cl["c"]].n_orb:
+                raise NotImplementedError("fragments with different orbital counts in one trimer")
+            offs = []
+            for role, cls in ((cl["k"], fac["ck"]), (cl["b"], fac["cb"]), (cl["c"], fac["cc"])):
+                offs.append(self._index(cls.offsets(f[role], stride[role] * D, stride[role])))
+            ctx.trimer_stream(fac["n"], fac["ck"].P, fac["cb"].P, fac["cc"].P, fac["alpha"], fac["W"], fac["ldw"],
+                              fac["beta"], fac["beta"].shape[1], fac["gamma"], fac["gamma"].shape[1], 0, fac["ck"].P,
+                              _lib.TRIMER_MATERIALIZE, None, H, offs[0], offs[1], offs[2])
+        return H
+
+    def H3_moments(self, m1, m2, m3, shard=(0, 1), per_class=False):
+        """Stream every element of H3[m1][m2][m3] through the on-chip reducer and return
+        (sum, sum of squares) -- the consumer used when the block cannot be stored (1e13 elements at
+        200 states/fragment).  shard=(rank, world) restricts to this rank's slab of each class's
+        leading pair index (no communication; add the results)."""
+        ms = (m1, m2, m3)
+        ctx = self.dev.ctx
+        rank, world = shard
+        moments = self.dev.zeros((12, 2))
+        for idx, cl in enumerate(self._trimer_classes(ms)):
+            fac = self._trimer_factors(ms, cl)
+            if fac is None:
+                continue
+            Pa = fac["ck"].P
+            a_lo, a_hi = Pa * rank // world, Pa * (rank + 1) // world
+            ctx.trimer_stream(fac["n"], Pa, fac["cb"].P, fac["cc"].P, fac["alpha"], fac["W"], fac["ldw"], fac["beta"],
+                              fac["beta"].shape[1], fac["gamma"], fac["gamma"].shape[1], a_lo, a_hi, _lib.TRIMER_REDUCE,
+                              moments.data_ptr() + 16 * idx, None, None, None, None)
+        out = self.dev.download(moments)
+        if per_class:
+            return out
+        return float(out[:, 0].sum()), float(out[:, 1].sum())

@@ -1,0 +1,169 @@
+"""ctypes binding of libxr_b200.so (include/xr_b200.h) -- the only way Python reaches the GPU here.
+
+There is NO CPU fallback: if the shared library is missing, or no sm_100 device is present,
+``load()`` / ``Context()`` raise.  Importing this module does not need a GPU (the CPU test-suite
+checks that the library loads and exports every declared symbol).
+"""
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libxr_b200.so")
+HEADER_PATH = os.path.join(HERE, "..", "include", "xr_b200.h")
+
+_i64 = ctypes.c_int64
+_dbl = ctypes.c_double
+_ptr = ctypes.c_void_p
+_int = ctypes.c_int
+
+LEGACY_SYMBOLS = {      # name -> (number of PyInt args, number of Double* args); H_contractions.c ABI
+    "monomer": (1, 4), "monomer_1e": (1, 2), "monomer_2e": (1, 2), "monomer_extPot": (1, 2),
+    "dimer_2min2pls": (2, 3), "dimer_1min1pls_1e": (2, 3), "dimer_1min1pls_2e": (2, 6), "dimer_ExEx": (2, 3),
+    "trimer_2min1pls1pls": (3, 4), "trimer_2pls1min1min": (3, 4), "trimer_Ex1min1pls": (3, 4),
+}
+
+_PROTOTYPES = {
+    "xr_last_error": (ctypes.c_char_p, []),
+    "xr_version": (ctypes.c_char_p, []),
+    "xr_ctx_create": (_int, [_int, _ptr, _int, ctypes.POINTER(_ptr)]),
+    "xr_ctx_destroy": (_int, [_ptr]),
+    "xr_ctx_set_stream": (_int, [_ptr, _ptr]),
+    "xr_sync": (_int, [_ptr]),
+    "xr_launch_count": (_int, [_ptr, ctypes.POINTER(_i64)]),
+    "xr_device_info": (_int, [_ptr, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int),
+                              ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
+    "xr_malloc": (_int, [_ptr, ctypes.c_size_t, ctypes.POINTER(_ptr)]),
+    "xr_free": (_int, [_ptr, _ptr]),
+    "xr_memset_zero": (_int, [_ptr, _ptr, ctypes.c_size_t]),
+    "xr_upload": (_int, [_ptr, _ptr, _ptr, ctypes.c_size_t]),
+    "xr_download": (_int, [_ptr, _ptr, _ptr, ctypes.c_size_t]),
+    "xr_gemm_scatter": (_int, [_ptr, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _int]),
+    "xr_copy2d_scaled": (_int, [_ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _dbl]),
+    "xr_scatter_const": (_int, [_ptr, _ptr, _ptr, _i64, _dbl, _int]),
+    "xr_trimer_stream": (_int, [_ptr, _int, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _int,
+                                _ptr, _ptr, _ptr, _ptr, _ptr]),
+}
+
+_lib = None
+
+
+class XRError(RuntimeError):
+    pass
+
+
+def declared_symbols(header_path=HEADER_PATH):
+    """Every function name include/xr_b200.h declares (used by the CPU test that the ABI is complete)."""
+    text = open(header_path).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", text)
+    return sorted(set(n for n in names if n not in ("defined",)))
+
+
+def load():
+    """dlopen libxr_b200.so and attach prototypes.  Raises (loudly) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise XRError("%s not found: build it with `python -m qodeapplications_b200.build` "
+                      "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    for name, (n_int, n_ptr) in LEGACY_SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = _dbl
+        fn.argtypes = [_i64] * n_int + [_ptr] * n_ptr
+    _lib = lib
+    return lib
+
+
+def last_error():
+    msg = load().xr_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise XRError("%s failed (status %d): %s" % (what or "xr call", rc, last_error()))
+
+
+def _p(x):
+    """device/host pointer from int, None, torch tensor or numpy array"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return ctypes.c_void_p(x)
+    if hasattr(x, "data_ptr"):
+        return ctypes.c_void_p(x.data_ptr())
+    if hasattr(x, "ctypes"):
+        return ctypes.c_void_p(x.ctypes.data)
+    raise TypeError("cannot take a pointer of %r" % type(x))
+
+
+class Context(object):
+    """One xr_ctx: a device plus the CUDA stream all xr kernels of this context are launched on."""
+    def __init__(self, device=0, stream=None, own_stream=False):
+        """stream: a cudaStream_t handle (int) to borrow; None/0 is the CUDA default stream.
+        own_stream=True lets the context create its own non-blocking stream instead."""
+        self.lib = load()
+        handle = ctypes.c_void_p()
+        check(self.lib.xr_ctx_create(int(device), ctypes.c_void_p(stream) if stream else None,
+                                     1 if own_stream else 0, ctypes.byref(handle)), "xr_ctx_create")
+        self.handle = handle
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.xr_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream):
+        check(self.lib.xr_ctx_set_stream(self.handle, ctypes.c_void_p(stream) if stream else None), "xr_ctx_set_stream")
+
+    def sync(self):
+        check(self.lib.xr_sync(self.handle), "xr_sync")
+
+    def launch_count(self):
+        n = ctypes.c_int64()
+        check(self.lib.xr_launch_count(self.handle, ctypes.byref(n)), "xr_launch_count")
+        return n.value
+
+    def device_info(self):
+        sm, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        free, total = ctypes.c_size_t(), ctypes.c_size_t()
+        check(self.lib.xr_device_info(self.handle, ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor),
+                                      ctypes.byref(free), ctypes.byref(total)), "xr_device_info")
+        return dict(sm_count=sm.value, cc=(major.value, minor.value), free_bytes=free.value, total_bytes=total.value)
+
+    # ---- kernels -------------------------------------------------------------------------------
+    def gemm_scatter(self, M, N, K, alpha, A, lda, B, ldb, C, offM=None, ldc=0, offN=None, accumulate=False):
+        check(self.lib.xr_gemm_scatter(self.handle, M, N, K, float(alpha), _p(A), lda, _p(B), ldb, _p(C), _p(offM),
+                                       ldc, _p(offN), 1 if accumulate else 0), "xr_gemm_scatter")
+
+    def copy2d_scaled(self, dst, dst_ld, src, src_ld, rows, cols, alpha=1.0):
+        check(self.lib.xr_copy2d_scaled(self.handle, _p(dst), dst_ld, _p(src), src_ld, rows, cols, float(alpha)),
+              "xr_copy2d_scaled")
+
+    def scatter_const(self, C, idx, count, value, accumulate=False):
+        check(self.lib.xr_scatter_const(self.handle, _p(C), _p(idx), count, float(value), 1 if accumulate else 0),
+              "xr_scatter_const")
+
+    def trimer_stream(self, n, Pa, Pb, Pc, alpha, W, ldw, beta, ldbeta, gamma, ldgamma, a_begin, a_end, mode,
+                      moments=None, C=None, offA=None, offB=None, offC=None):
+        check(self.lib.xr_trimer_stream(self.handle, n, Pa, Pb, Pc, float(alpha), _p(W), ldw, _p(beta), ldbeta,
+                                        _p(gamma), ldgamma, a_begin, a_end, mode, _p(moments), _p(C), _p(offA),
+                                        _p(offB), _p(offC)), "xr_trimer_stream")
+
+
+TRIMER_REDUCE = 0
+TRIMER_MATERIALIZE = 1

@@ -1,0 +1,244 @@
+"""GPU parity tests for the general-XRCC path: every value computed by libxr_b200.so is compared
+with the CPU oracle (and with the golden vectors the reference itself produced).
+Tolerance (BASELINE.json north_star): |diff| <= 1e-10 * max|H_ref| per block; elements that are
+structurally zero in the reference must be exactly zero."""
+import itertools
+import os
+import numpy
+import pytest
+import torch
+
+from qodeapplications_b200 import synth
+from oracle import general_oracle as go
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-10
+
+
+def _close(a, b, tol=TOL):
+    a, b = numpy.asarray(a), numpy.asarray(b)
+    assert a.shape == b.shape
+    scale = max(numpy.abs(b).max(), 1e-300)
+    err = numpy.abs(a - b).max()
+    assert err <= tol * scale, (err, scale)
+    assert numpy.all(a[b == 0] == 0), "structural zeros must stay exactly zero"
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from qodeapplications_b200.device import Device
+    return Device(0)
+
+
+def _engine(system, dev):
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    return build_matrix_elements(system["fragments"], system["symm"], system["nuc"], device=dev)
+
+
+# ------------------------------------------------------------------------------- kernels
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (7, 5, 3), (64, 64, 16), (130, 70, 37), (257, 300, 324), (1000, 33, 18),
+                                   (129, 1, 325), (300, 520, 36)])
+@pytest.mark.parametrize("aligned", [True, False])
+def test_gemm_scatter_plain(dev, M, N, K, aligned):
+    rng = numpy.random.default_rng(M * 1000 + N * 10 + K)
+    lda = K + (K % 2 if aligned else 1 - K % 2)      # even (vector path) or odd (8-byte path)
+    ldb = lda + (2 if aligned else 0)
+    A, B = rng.standard_normal((M, lda)), rng.standard_normal((N, ldb))
+    dA, dB = dev.upload(A), dev.upload(B)
+    ldc = N + 3
+    C0 = rng.standard_normal((M, ldc))
+    dC = dev.upload(C0)
+    ref = 0.75 * A[:, :K] @ B[:, :K].T
+    dev.ctx.gemm_scatter(M, N, K, 0.75, dA, lda, dB, ldb, dC, None, ldc, None, False)
+    out = dev.download(dC)
+    _close(out[:, :N], ref, 1e-13 * max(1, K))
+    assert numpy.array_equal(out[:, N:], C0[:, N:])       # padding columns untouched
+    dev.ctx.gemm_scatter(M, N, K, -0.5, dA, lda, dB, ldb, dC, None, ldc, None, True)
+    _close(dev.download(dC)[:, :N], ref - 0.5 * A[:, :K] @ B[:, :K].T, 1e-13 * max(1, K))
+
+
+def test_gemm_scatter_offset_tables(dev):
+    """C[i0,i1,j0,j1] <- A[(i0,j0),k] B[(i1,j1),k]: the [ikjl] shuffle every dimer diagram needs."""
+    rng = numpy.random.default_rng(7)
+    n0i, n0j, n1i, n1j, K = 5, 4, 3, 6, 50
+    A, B = rng.standard_normal((n0i * n0j, K)), rng.standard_normal((n1i * n1j, K))
+    offM = (numpy.arange(n0i)[:, None] * (n1i * n0j * n1j) + numpy.arange(n0j)[None, :] * n1j).reshape(-1)
+    offN = (numpy.arange(n1i)[:, None] * (n0j * n1j) + numpy.arange(n1j)[None, :]).reshape(-1)
+    dC = dev.zeros((n0i, n1i, n0j, n1j))
+    dev.ctx.gemm_scatter(n0i * n0j, n1i * n1j, K, 1.0, dev.upload(A), K, dev.upload(B), K, dC,
+                         dev.upload(offM, numpy.int64), 0, dev.upload(offN, numpy.int64), False)
+    ref = numpy.einsum("ijx,klx->ikjl", A.reshape(n0i, n0j, K), B.reshape(n1i, n1j, K))
+    _close(dev.download(dC), ref, 1e-13)
+
+
+@pytest.mark.parametrize("n,Pa,Pb,Pc", [(5, 3, 4, 7), (6, 20, 33, 130), (18, 9, 17, 257), (18, 40, 50, 1000), (48, 5, 18, 140)])
+def test_trimer_stream(dev, n, Pa, Pb, Pc):
+    from qodeapplications_b200 import lib as xr
+    rng = numpy.random.default_rng(n + Pa + Pb + Pc)
+    W, beta, gamma = rng.standard_normal((Pa, n * n)), rng.standard_normal((Pb, n)), rng.standard_normal((Pc, n))
+    ref = -1.5 * numpy.einsum("ars,br,cs->abc", W.reshape(Pa, n, n), beta, gamma, optimize=True)
+    dW, dB, dG = dev.upload(W), dev.upload(beta), dev.upload(gamma)
+    # materialise with a permuted layout [c, a, b]
+    offA = numpy.arange(Pa, dtype=numpy.int64) * Pb
+    offB = numpy.arange(Pb, dtype=numpy.int64)
+    offC = numpy.arange(Pc, dtype=numpy.int64) * (Pa * Pb)
+    dC = dev.zeros((Pc, Pa, Pb))
+    dev.ctx.trimer_stream(n, Pa, Pb, Pc, -1.5, dW, n * n, dB, n, dG, n, 0, Pa, xr.TRIMER_MATERIALIZE, None, dC,
+                          dev.upload(offA, numpy.int64), dev.upload(offB, numpy.int64), dev.upload(offC, numpy.int64))
+    _close(dev.download(dC), ref.transpose(2, 0, 1), 1e-13 * n)
+    # reduce, in two shards
+    mom = dev.zeros((2,))
+    split = Pa // 2
+    for lo, hi in ((0, split), (split, Pa)):
+        dev.ctx.trimer_stream(n, Pa, Pb, Pc, -1.5, dW, n * n, dB, n, dG, n, lo, hi, xr.TRIMER_REDUCE, mom, None, None, None, None)
+    got = dev.download(mom)
+    assert abs(got[0] - ref.sum()) <= 1e-11 * numpy.abs(ref).sum()
+    assert abs(got[1] - (ref ** 2).sum()) <= 1e-12 * (ref ** 2).sum()
+    total, sumsq = go.trimer_class_moments(W.reshape(Pa, n, n), beta, gamma)
+    assert abs(got[1] - 2.25 * sumsq) <= 1e-11 * 2.25 * sumsq
+
+
+def test_legacy_scalar_abi(dev):
+    """The 11 H_contractions.c symbols, same ABI, against the CPU oracle's C library."""
+    from qodeapplications_b200.general.H_contractions import import_C
+    contract = import_C("H_contractions", flags="-O2")
+    ref_path = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "libH_contractions_ref.so")
+    ref = go.c_contractions("ref" if os.path.exists(ref_path) else "port")
+    rng = numpy.random.default_rng(5)
+    r = lambda *s: rng.standard_normal(s)
+    for n1, n2, n3 in ((5, 4, 3), (18, 18, 18)):
+        cases = [
+            ("monomer", (n1, r(n1, n1), r(n1, n1, n1, n1), r(n1, n1), r(n1, n1, n1, n1))),
+            ("monomer_1e", (n1, r(n1, n1), r(n1, n1))),
+            ("monomer_2e", (n1, r(n1, n1, n1, n1), r(n1, n1, n1, n1))),
+            ("monomer_extPot", (n1, r(n1, n1), r(n1, n1))),
+            ("dimer_2min2pls", (n1, n2, r(n1, n1), r(n2, n2), r(n1, n1, n2, n2))),
+            ("dimer_1min1pls_1e", (n1, n2, r(n1), r(n2), r(n1, n2))),
+            ("dimer_1min1pls_2e", (n1, n2, r(n1), r(n1, n1, n1), r(n2), r(n2, n2, n2), r(n1, n1, n1, n2), r(n1, n2, n2, n2))),
+            ("dimer_ExEx", (n1, n2, r(n1, n1), r(n2, n2), r(n1, n2, n1, n2))),
+            ("trimer_2min1pls1pls", (n1, n2, n3, r(n1, n1), r(n2), r(n3), r(n1, n1, n2, n3))),
+            ("trimer_2pls1min1min", (n1, n2, n3, r(n1, n1), r(n2), r(n3), r(n2, n3, n1, n1))),
+            ("trimer_Ex1min1pls", (n1, n2, n3, r(n1, n1), r(n2), r(n3), r(n1, n2, n1, n3))),
+        ]
+        for name, args in cases:
+            fn = getattr(contract, name)
+            fn.return_type(float)
+            a, b = fn(*args), getattr(ref, name)(*args)
+            terms = max(numpy.abs(args[-1]).sum(), 1.0)
+            assert abs(a - b) <= 1e-13 * terms, (name, a, b)
+
+
+# ------------------------------------------------------------------------------ H blocks
+
+@pytest.mark.parametrize("name", ["toy", "toy3"])
+def test_blocks_match_reference_golden(dev, name):
+    g = numpy.load(os.path.join(GOLDEN, "general_%s.npz" % name))
+    system = synth.make_system(name)
+    eng = _engine(system, dev)
+    F = system["n_frag"]
+    for m in range(F):
+        _close(eng.H1(m), g["H1_%d" % m])
+    for m1, m2 in itertools.combinations(range(F), 2):
+        _close(eng.H2(m1, m2), g["H2_%d%d" % (m1, m2)])
+    for ms in itertools.combinations(range(F), 3):
+        key = "H3_%d%d%d" % ms
+        ref = numpy.zeros(tuple(g[key + "_shape"]))
+        ref[g[key + "_rows"], g[key + "_cols"]] = g[key + "_vals"]
+        _close(eng.H3(*ms), ref)
+
+
+def test_element_accessors_keep_reference_signatures(dev):
+    """monomer/dimer/trimer(fragments, I, J) exactly as general-XRCC/test_H.py:51-58 calls them."""
+    g = numpy.load(os.path.join(GOLDEN, "general_toy3.npz"))
+    system = synth.make_system("toy3")
+    eng = _engine(system, dev)
+    st = [f.state_indices for f in system["fragments"]]
+    rng = numpy.random.default_rng(1)
+    H1 = g["H1_2"]
+    for _ in range(10):
+        i, j = rng.integers(len(st[2]), size=2)
+        assert abs(eng.monomer(2, st[2][i], st[2][j]) - H1[i, j]) <= TOL * numpy.abs(H1).max()
+    basis = [(a, b) for a in st[0] for b in st[1]]
+    H2 = g["H2_01"]
+    for _ in range(50):
+        i, j = rng.integers(len(basis), size=2)
+        assert abs(eng.dimer((0, 1), basis[i], basis[j]) - H2[i, j]) <= TOL * numpy.abs(H2).max()
+    basis3 = [(a, b, c) for a in st[0] for b in st[1] for c in st[2]]
+    ref = numpy.zeros(tuple(g["H3_012_shape"]))
+    ref[g["H3_012_rows"], g["H3_012_cols"]] = g["H3_012_vals"]
+    for _ in range(200):
+        i, j = rng.integers(len(basis3), size=2)
+        assert abs(eng.trimer((0, 1, 2), basis3[i], basis3[j]) - ref[i, j]) <= TOL * numpy.abs(ref).max()
+
+
+def test_cfg1_dimer_against_block_oracle(dev):
+    """Be2 / 6-31G shapes (n=18, N=11/4/8): full H1 and H2 against the NumPy block oracle."""
+    system = synth.make_system("cfg1")
+    eng = _engine(system, dev)
+    frags, ints, nuc = system["fragments"], system["symm"], system["nuc"]
+    for m in range(2):
+        _close(eng.H1(m), go.block_monomer(frags, ints, nuc, m))
+    _close(eng.H2(0, 1), go.block_dimer(frags, ints, nuc, 0, 1))
+
+
+def test_cfg1_sampled_against_reference_c(dev):
+    """The same H2 against the reference's own compiled C, element by element on a sample."""
+    ref_path = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "libH_contractions_ref.so")
+    system = synth.make_system("cfg1")
+    eng = _engine(system, dev)
+    frags = system["fragments"]
+    eo = go.element_oracle(frags, system["symm"], system["nuc"], go.c_contractions("ref" if os.path.exists(ref_path) else "port"))
+    H2 = eng.H2(0, 1)
+    basis = [(a, b) for a in frags[0].state_indices for b in frags[1].state_indices]
+    rng = numpy.random.default_rng(2)
+    scale = numpy.abs(H2).max()
+    for _ in range(400):
+        i, j = rng.integers(len(basis), size=2)
+        assert abs(H2[i, j] - eo.dimer((0, 1), basis[i], basis[j])) <= TOL * scale
+
+
+def test_bra_slab_sharding_reassembles_H2(dev):
+    """Rows built per bra slab (what each rank of a multi-GPU run computes) concatenate to H2."""
+    system = synth.make_system("toy")
+    eng = _engine(system, dev)
+    full = eng.H2(0, 1)
+    dim1 = len(system["fragments"][0].state_indices)
+    parts = []
+    for lo, hi in ((0, 2), (2, 3), (3, dim1)):
+        parts.append(dev.download(eng.H2_device(0, 1, bra_range=(lo, hi))))
+    assert numpy.array_equal(numpy.concatenate(parts, axis=0), full)
+
+
+def test_cfg3_trimer_moments_and_sampled_elements(dev):
+    """Be3 chain shapes: streamed moments of H3 equal those of the materialised block, the shards add
+    up, and sampled elements equal the reference C evaluated through the element oracle."""
+    ref_path = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "libH_contractions_ref.so")
+    system = synth.make_system("cfg3")
+    eng = _engine(system, dev)
+    H3 = eng.H3_device(0, 1, 2)
+    total, sumsq = float(H3.sum()), float((H3 * H3).sum())
+    s, q = eng.H3_moments(0, 1, 2)
+    assert abs(q - sumsq) <= 1e-11 * sumsq
+    assert abs(s - total) <= 1e-9 * float(H3.abs().sum())
+    parts = [eng.H3_moments(0, 1, 2, shard=(r, 3)) for r in range(3)]
+    assert abs(sum(p[1] for p in parts) - sumsq) <= 1e-11 * sumsq
+    frags = system["fragments"]
+    eo = go.element_oracle(frags, system["symm"], system["nuc"], go.c_contractions("ref" if os.path.exists(ref_path) else "port"))
+    st = [f.state_indices for f in frags]
+    dims = [len(s_) for s_ in st]
+    rng = numpy.random.default_rng(4)
+    scale = float(H3.abs().max())
+    D = dims[0] * dims[1] * dims[2]
+    nz = torch.nonzero(H3.reshape(-1))[:, 0]
+    picks = nz[torch.randint(len(nz), (300,), device=nz.device)].cpu().numpy()
+    picks = numpy.concatenate([picks, rng.integers(D * D, size=100)])
+    vals = H3.reshape(-1)[torch.from_numpy(picks).to(H3.device)].cpu().numpy()
+    for flat, val in zip(picks, vals):
+        i, j = divmod(int(flat), D)
+        I = numpy.unravel_index(i, dims)
+        J = numpy.unravel_index(j, dims)
+        ref = eo.trimer((0, 1, 2), tuple(st[k][I[k]] for k in range(3)), tuple(st[k][J[k]] for k in range(3)))
+        assert abs(val - (ref or 0.0)) <= TOL * scale
