@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the XR Hamiltonian build (BASELINE.json metric: H-build time and FP64 TFLOP/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl xr|reference] [--workload cfg4]
+
+One step = one full H build of the workload: every H1, every dimer block H2[m1][m2] materialised
+dense in HBM (assembled on every rank by an NCCL all-gather when N > 1), and every trimer block
+H3[m1][m2][m3] formed element by element and streamed into the on-chip moment reducer (1e13
+elements per trimer at cfg4: they cannot be stored anywhere).  Work is sharded over ranks by
+bra-state slabs (dimers) and by leading pair-index slabs (trimers): total work is fixed, so
+scaling is "strong".  `value` = algorithmic FP64 flops of the factored algorithm (BASELINE.md
+section 3) / device time, inputs resident in HBM; `e2e` = the same through the public Python API
+from pinned host buffers, uploads and result downloads inside the timed region.
+
+`--impl reference` times the reference's own per-element CPU path (general-XRCC/build_H.py control
+flow into its compiled H_contractions.c) on a bounded sample with all host cores.
+"""
+import argparse
+import itertools
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "xr_h_build_fp64_tflops"
+UNIT = "TFLOP/s"
+
+WORKLOADS = {
+    # name: (synth config, description)
+    "cfg4": dict(n_frag=4, n_orb=18, n_states={0: 96, +1: 34, -1: 70}, seed=4,
+                 text="synthetic 4-fragment Be chain, 200 states/fragment (96/34/70), n=18 spin orbitals: "
+                      "4 H1 + 6 dimer H2 (dense, 40000^2 each) + 4 trimer H3 (1.06e13 elements each, streamed)"),
+    "cfg4-half": dict(n_frag=4, n_orb=18, n_states={0: 48, +1: 17, -1: 35}, seed=4,
+                      text="development size: cfg4 with 100 states/fragment"),
+    "cfg3": dict(n_frag=3, n_orb=18, n_states={0: 11, +1: 4, -1: 8}, seed=3, text="Be3 chain shapes (parity-test size)"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="xr", choices=["xr", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample", type=int, default=0, help="CPU sample elements per class (0 = default)")
+    return ap.parse_args()
+
+
+def make_system(workload):
+    from qodeapplications_b200 import synth
+    w = WORKLOADS[workload]
+    return synth.make_system(n_frag=w["n_frag"], n_orb=w["n_orb"], n_states=w["n_states"], seed=w["seed"],
+                             ops=synth.OPS_GENERAL, general_ccaa="random")
+
+
+# ------------------------------------------------------------------------------------ clocks
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region"""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(s for s, p in zip(sm, power) if p > 0.5 * max(power)) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+
+def run_reference(args):
+    """CPU arm: rank 0 only; no CUDA is touched in this process."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    system = make_system(args.workload)
+    kind = cpu_baseline.prepare(system)
+    F = system["n_frag"]
+    dimers = list(itertools.combinations(range(F), 2))
+    trimers = list(itertools.combinations(range(F), 3))
+    acct = build_matrix_elements(system["fragments"], system["symm"], system["nuc"])     # accounting only (no GPU use)
+    total_flops, _ = acct.algorithmic_flops(dimers, trimers)
+    counts = acct.element_counts(dimers, trimers)
+    cores = os.cpu_count() or 1
+    per_class = args.sample or 250 * cores
+    sample = cpu_baseline.make_sample(system, per_class)
+    pool = cpu_baseline.make_pool(cores) if cores > 1 else None
+    for _ in range(args.warmup):
+        cpu_baseline.time_sample(sample, cores, pool)
+    t0 = time.perf_counter()
+    acc = None
+    for _ in range(args.steps):
+        secs = cpu_baseline.time_sample(sample, cores, pool)
+        acc = secs if acc is None else {k: acc[k] + secs[k] for k in secs}
+    wall = time.perf_counter() - t0
+    if pool is not None:
+        pool.close()
+    per_step = {k: v / args.steps for k, v in acc.items()}
+    full_seconds = cpu_baseline.extrapolate(per_step, sample, counts)
+    value = total_flops / full_seconds / 1e12
+    n_sample = sum(len(v) for v in sample.values())
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": WORKLOADS[args.workload]["text"]},
+        "build_time_s_extrapolated": full_seconds,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "%d random charge-allowed elements of each of %d classes (5 dimer, 3 trimer kinds) of "
+                                   "fragments (0,1)/(0,1,2) per step, one Python call per element into the C kernels, "
+                                   "Pool(%d); whole-workload time extrapolated with exact per-class element counts"
+                                   % (per_class, len(sample), cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sample_elements_per_step": n_sample,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- xr arm
+
+def pin_system(system):
+    """move every density / scalar array of the general-path fragments into pinned host memory"""
+    import torch
+    for frag in system["fragments"]:
+        for op, blocks in frag.rho.items():
+            for key in list(blocks):
+                t = torch.from_numpy(blocks[key]).contiguous().pin_memory()
+                blocks[key] = t.numpy()
+
+
+def run_xr(args):
+    import numpy
+    import torch
+    import torch.distributed as dist
+    from qodeapplications_b200.device import Device
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl xr needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus and rank == 0:
+        print("warning: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world), file=sys.stderr)
+
+    system = make_system(args.workload)
+    pin_system(system)
+    dev = Device(local_rank)
+    eng = build_matrix_elements(system["fragments"], system["symm"], system["nuc"], device=dev)
+    F = system["n_frag"]
+    dimers = list(itertools.combinations(range(F), 2))
+    trimers = list(itertools.combinations(range(F), 3))
+    total_flops, split = eng.algorithmic_flops(dimers, trimers)
+    counts = eng.element_counts(dimers, trimers)
+    dims = [len(f.state_indices) for f in system["fragments"]]
+
+    # bra-state slabs of fragment m1 for the dimers (equal sizes so the all-gather is one collective)
+    def slab(m1):
+        per = -(-dims[m1] // world)
+        return min(rank * per, dims[m1]), min((rank + 1) * per, dims[m1]), per
+
+    H2 = {}
+    for m1, m2 in dimers:
+        lo, hi, per = slab(m1)
+        D = dims[m1] * dims[m2]
+        H2[(m1, m2)] = dev.empty((per * world * dims[m2], D))      # padded to world*per bra states; rows >= dim1*dim2 unused
+
+    results = {}
+
+    def step(gather=True):
+        for m in range(F):
+            results[("H1", m)] = eng.H1_device(m)
+        for m1, m2 in dimers:
+            lo, hi, per = slab(m1)
+            full = H2[(m1, m2)]
+            mine = full[rank * per * dims[m2]:(rank * per + (hi - lo)) * dims[m2]]
+            eng.H2_device(m1, m2, bra_range=(lo, hi) if world > 1 else None, out=mine)
+            if world > 1 and gather:
+                chunk = full[rank * per * dims[m2]:(rank + 1) * per * dims[m2]]
+                dist.all_gather_into_tensor(full, chunk)
+        for ms in trimers:
+            results[("H3", ms)] = eng.H3_moments_device(*ms, shard=(rank, world))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.preload()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = dev.ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.profile = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = dev.ctx.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev.torch_device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    profile, eng.profile = eng.profile, None
+
+    # per-kernel-class device time from the events recorded around each launch (this rank)
+    per_label = {}
+    for label, flops, s, e in profile:
+        t, f, c = per_label.get(label, (0.0, 0.0, 0))
+        per_label[label] = (t + s.elapsed_time(e), f + flops, c + 1)
+    tri = [(t, f, c) for label, (t, f, c) in per_label.items() if label.startswith("trimer_stream")]
+    tri_ms, tri_flops, tri_count = (sum(x[i] for x in tri) for i in range(3)) if tri else (0.0, 0.0, 0)
+
+    # trimer moments summed over ranks (the only "exchange" the trimer path has: 24 doubles per trimer)
+    moments = {}
+    for ms_ in trimers:
+        t = results[("H3", ms_)].clone()
+        if world > 1:
+            dist.all_reduce(t)
+        moments[ms_] = t.sum(dim=0).tolist()
+
+    # ---- end-to-end: pinned host inputs -> upload -> build -> results read back to pinned host
+    e2e = None
+    if not args.no_e2e:
+        host_out = {}
+        for m1, m2 in dimers:
+            lo, hi, per = slab(m1)
+            key = ((hi - lo) * dims[m2], dims[m1] * dims[m2])
+            if key not in host_out:
+                host_out[key] = torch.empty(key, dtype=torch.float64, pin_memory=True)
+        def e2e_step():
+            eng.drop_caches(densities=True)
+            dev.h2d_bytes = dev.d2h_bytes = 0
+            step()
+            d2h = 0
+            for m in range(F):
+                d2h += results[("H1", m)].numel() * 8
+                results[("H1", m)].cpu()
+            for m1, m2 in dimers:
+                lo, hi, per = slab(m1)
+                mine = H2[(m1, m2)][rank * per * dims[m2]:(rank * per + (hi - lo)) * dims[m2]]
+                host_out[tuple(mine.shape)].copy_(mine, non_blocking=True)
+                d2h += mine.numel() * 8
+            for ms_ in trimers:
+                d2h += results[("H3", ms_)].numel() * 8
+                results[("H3", ms_)].cpu()
+            return dev.h2d_bytes, d2h
+        barrier()
+        e2e_steps = 1
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        wall0 = time.perf_counter()
+        t0.record()
+        for _ in range(e2e_steps):
+            h2d, d2h = e2e_step()
+        t1.record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        tms = torch.tensor([max(t0.elapsed_time(t1), 1e3 * wall)], device=dev.torch_device, dtype=torch.float64)
+        byt = torch.tensor([h2d, d2h], device=dev.torch_device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(byt)
+        e2e = {"value": total_flops * e2e_steps / (float(tms.item()) * 1e-3) / 1e12, "unit": UNIT,
+               "h2d_bytes_per_step": int(byt[0].item()), "d2h_bytes_per_step": int(byt[1].item()),
+               "seconds_per_step": float(tms.item()) * 1e-3 / e2e_steps, "steps": e2e_steps,
+               "note": "host wall clock (max over ranks) around upload + build + download of every H1, H2 slab and H3 moment"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (trimer_stream_kernel): FP64 tensor pipe
+    peaks = {}
+    for name in ("r01_fp64_peaks.json",):
+        path = os.path.join(REPO, "profiles", name)
+        if os.path.exists(path):
+            peaks = json.load(open(path))
+    peak = peaks.get("dmma_tflops_sustained", 37.2)
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "trimer_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    achieved = tri_flops / (tri_ms * 1e-3) / 1e12 if tri_ms else None
+    roofline = {
+        "bound": "tensor", "kernel": "trimer_stream_kernel<5> (FP64 DMMA.8x8x4)", "achieved": achieved, "peak": peak,
+        "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+        "peak_source": "measured on this pool's B200: DMMA.8x8x4 issue-rate microbenchmark tools/fp64_peaks.cu "
+                       "(profiles/r01_fp64_peaks.json; cuBLAS DGEMM 8192^3 reaches 35.5). MEASURED_PEAKS.json has no FP64 entry "
+                       "and tcgen05 has no f64 kind, so the bf16 figure does not apply",
+        "launches_timed": tri_count, "avg_launch_ms": tri_ms / tri_count if tri_count else None,
+        "share_of_step": tri_ms / ms_total if ms_total else None,
+        "algorithmic_flops_per_launch": tri_flops / tri_count if tri_count else None,
+    }
+
+    # ---- CPU baseline: the reference's per-element path, 1 core, bounded sample (rank 0, N=1 only)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import cpu_baseline
+        kind = cpu_baseline.prepare(system)
+        per_class = args.sample or 2500
+        sample = cpu_baseline.make_sample(system, per_class)
+        secs = cpu_baseline.time_sample(sample, 1)
+        full_seconds = cpu_baseline.extrapolate(secs, sample, counts)
+        cpu = {"value": total_flops / full_seconds / 1e12, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": "%d random charge-allowed elements of each of %d classes, one Python call per element into the "
+                         "reference's C kernels (-O2), %.1f s of CPU; whole-workload time (%.3g s) extrapolated with exact "
+                         "per-class element counts" % (per_class, len(sample), sum(secs.values()), full_seconds),
+               "us_per_element": {"%s_%s" % k: 1e6 * v / len(sample[k]) for k, v in secs.items()},
+               "host_cores_available": os.cpu_count()}
+
+    line = {
+        "metric": METRIC, "value": total_flops * args.steps / (ms_total * 1e-3) / 1e12, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": WORKLOADS[args.workload]["text"],
+                   "sharding": "dimers: bra-state slabs of fragment m1 + NCCL all-gather of H2; trimers: leading pair-index slabs, no collective",
+                   "cache": "inputs_larger_than_L2 (4 GB of densities, 77 GB of H2 written per step)"},
+        "build_time_s": ms_total * 1e-3 / args.steps,
+        "algorithmic_flops_per_step": total_flops, "flops_split": split,
+        "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+        "kernel_classes": {label: {"ms": t, "tflops": f / (t * 1e-3) / 1e12 if t else None, "launches": c}
+                           for label, (t, f, c) in sorted(per_label.items())},
+        "trimer_moments": {"".join(map(str, k)): v for k, v in moments.items()},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_xr(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,10 @@
 
 namespace {
 
-constexpr int TA = 8, TB = 16, ROWS = TA * TB, CT = 128, THREADS = 256;
+constexpr int TA = 8, TB = 16, ROWS = TA * TB, CT = 128;
+constexpr int CONSUMER_WARPS = 8, CONSUMER_THREADS = CONSUMER_WARPS * 32;
+constexpr int THREADS = CONSUMER_THREADS + 128;   // + one producer warpgroup (register allocation is per 4 warps)
+constexpr int SLOTS = 4;     // gamma ring depth
 
 struct TrimerParams {
     int n;
@@ -41,9 +44,19 @@ struct TrimerCfg {
     static constexpr int KP = 4 * KS;
     static constexpr int GS = (KP % 16 == 4 || KP % 16 == 12) ? KP : KP + 4;   // conflict-free fragment stride
     static constexpr bool AREG = KS <= 5;
-    static constexpr size_t SMEM = (size_t)(ROWS + 2 * CT) * GS * sizeof(double) + 64;
+    static constexpr size_t SMEM = (size_t)(ROWS + SLOTS * CT) * GS * sizeof(double) + 2 * SLOTS * sizeof(uint64_t) + 64;
 };
 
+__device__ __forceinline__ void consumer_barrier() {   // named barrier 1: the 8 consumer warps only
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_THREADS) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised: warp 8 is the TMA producer (one elected lane streams gamma tiles into a SLOTS-deep
+// ring, full/empty mbarriers per slot); warps 0..7 are DMMA consumers that never meet at a block-wide
+// barrier inside the tile loop, so one warp's epilogue overlaps the other warps' tensor work.
 template <int KS>
 __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerParams p) {
     using Cfg = TrimerCfg<KS>;
@@ -51,41 +64,60 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
     constexpr bool AREG = Cfg::AREG;
     constexpr int MI = 4, NJ = 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* Gs = reinterpret_cast<double*>(smem_raw);              // [2][CT][GS]   (bulk-copy destinations first: 16B aligned)
-    double* Xs = Gs + 2 * CT * GS;                                  // [ROWS][GS]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Xs + ROWS * GS);   // [2]
-    __shared__ double red[2][THREADS / 32];
+    double* Gs = reinterpret_cast<double*>(smem_raw);                  // [SLOTS][CT][GS]  (bulk-copy destinations: 16B aligned)
+    double* Xs = Gs + SLOTS * CT * GS;                                  // [ROWS][GS]
+    uint64_t* full = reinterpret_cast<uint64_t*>(Xs + ROWS * GS);       // [SLOTS]
+    uint64_t* empty = full + SLOTS;                                     // [SLOTS]
+    __shared__ double red[2][CONSUMER_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int wm = warp & 3, wn = warp >> 2;
     constexpr uint32_t TILE_BYTES = CT * GS * sizeof(double);
 
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int s = 0; s < SLOTS; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CONSUMER_WARPS);
+        }
         fence_barrier_init();
     }
     __syncthreads();
 
-    uint32_t phase0 = 0, phase1 = 0;
-    uint32_t it = 0;
+    int64_t my_items = 0;
+    if ((int64_t)blockIdx.x < p.n_items) my_items = (p.n_items - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t total_tiles = my_items * p.c_tiles;
+
+    if (warp >= CONSUMER_WARPS) {
+        // -------------------------------------------------- producer warpgroup (one lane works)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");     // hand registers to the consumers
+        if (warp == CONSUMER_WARPS && lane == 0) {
+            int ct = 0;
+            for (int64_t q = 0; q < total_tiles; ++q) {
+                const int slot = (int)(q % SLOTS);
+                const uint32_t round = (uint32_t)(q / SLOTS);
+                mbar_wait(&empty[slot], (round & 1) ^ 1);     // passes at once on the first lap
+                mbar_expect_tx(&full[slot], TILE_BYTES);
+                bulk_copy_g2s(Gs + (size_t)slot * CT * GS, p.gammaP + (size_t)ct * CT * GS, TILE_BYTES, &full[slot]);
+                if (++ct == p.c_tiles) ct = 0;
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
     double s1 = 0.0, s2 = 0.0;
     const int n = p.n;
+    int64_t q = 0;
 
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int64_t a0 = p.a_begin + (item / p.tiles_b) * TA;
         const int64_t b0 = (item % p.tiles_b) * TB;
 
-        // first gamma tile of this item (slot it&1 was released by the trailing barrier of the last tile)
-        if (tid == 0) {
-            uint64_t* bar = &bars[it & 1];
-            mbar_expect_tx(bar, TILE_BYTES);
-            bulk_copy_g2s(Gs + (size_t)(it & 1) * CT * GS, p.gammaP, TILE_BYTES, bar);
-        }
-
+        consumer_barrier();    // every consumer is done with the previous item's Xs
         // X[(a,b), s] = sum_r W[a, r*n + s] * beta[b, r]
-        for (int idx = tid; idx < ROWS * KP; idx += THREADS) {
+        for (int idx = tid; idx < ROWS * KP; idx += CONSUMER_THREADS) {
             const int row = idx / KP, s = idx - row * KP;
             const int64_t a = a0 + row / TB, b = b0 + row % TB;
             double v = 0.0;
@@ -96,7 +128,7 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
             }
             Xs[row * GS + s] = v;
         }
-        __syncthreads();
+        consumer_barrier();
 
         double areg[AREG ? MI : 1][AREG ? KS : 1];
         if (AREG) {
@@ -106,20 +138,9 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
                 for (int ks = 0; ks < KS; ++ks) areg[i][ks] = Xs[(32 * wm + 8 * i + g) * GS + 4 * ks + t];
         }
 
-        for (int ct = 0; ct < p.c_tiles; ++ct, ++it) {
-            const uint32_t buf = it & 1;
-            if (tid == 0 && ct + 1 < p.c_tiles) {
-                uint64_t* bar = &bars[buf ^ 1];
-                mbar_expect_tx(bar, TILE_BYTES);
-                bulk_copy_g2s(Gs + (size_t)(buf ^ 1) * CT * GS, p.gammaP + (size_t)(ct + 1) * CT * GS, TILE_BYTES, bar);
-            }
-            if (buf == 0) {
-                mbar_wait(&bars[0], phase0);
-                phase0 ^= 1;
-            } else {
-                mbar_wait(&bars[1], phase1);
-                phase1 ^= 1;
-            }
+        for (int ct = 0; ct < p.c_tiles; ++ct, ++q) {
+            const int slot = (int)(q % SLOTS);
+            mbar_wait(&full[slot], (uint32_t)(q / SLOTS) & 1);
 
             double acc[MI][NJ][2];
 #pragma unroll
@@ -127,7 +148,7 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-            const double* gs = Gs + (size_t)buf * CT * GS + (64 * wn + g) * GS + t;
+            const double* gs = Gs + (size_t)slot * CT * GS + (64 * wn + g) * GS + t;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 double b[NJ];
@@ -140,7 +161,8 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
                     for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a, b[j]);
                 }
             }
-            __syncthreads();   // every warp is done with Gs[buf] (and Xs): the slot may be refilled
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);      // this warp no longer reads the slot
 
             if (p.mode == XR_TRIMER_REDUCE) {
 #pragma unroll
@@ -180,10 +202,10 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
             red[0][warp] = s1;
             red[1][warp] = s2;
         }
-        __syncthreads();
+        consumer_barrier();
         if (tid == 0) {
             double t1 = 0.0, t2 = 0.0;
-            for (int w = 0; w < THREADS / 32; ++w) {
+            for (int w = 0; w < CONSUMER_WARPS; ++w) {
                 t1 += red[0][w];
                 t2 += red[1][w];
             }

@@ -126,6 +126,7 @@ class build_matrix_elements(object):
         self._rho_dev = {}
         self._int_dev = {}
         self._idx_dev = {}
+        self.profile = None        # set to a list to collect (label, algorithmic flops, start event, end event)
         self._H1 = {}
         self._H2 = {}
         self._H3 = {}
@@ -191,8 +192,29 @@ class build_matrix_elements(object):
             self._int_dev[key] = self.dev.upload(make())
         return self._int_dev[key]
 
-    def _index(self, array):
-        return self.dev.upload(array, dtype=numpy.int64)
+    def _index(self, array, key=None):
+        """device int64 table; cached when the caller names it with a key"""
+        if key is None:
+            return self.dev.upload(array() if callable(array) else array, dtype=numpy.int64)
+        if key not in self._idx_dev:
+            self._idx_dev[key] = self.dev.upload(array() if callable(array) else array, dtype=numpy.int64)
+        return self._idx_dev[key]
+
+    class _timed(object):
+        """records a pair of CUDA events on the launch stream around a kernel when profiling is on"""
+        def __init__(self, owner, label, flops):
+            self.owner, self.label, self.flops = owner, label, flops
+        def __enter__(self):
+            if self.owner.profile is not None:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+            return self
+        def __exit__(self, *exc):
+            if self.owner.profile is not None:
+                self.e1.record()
+                self.owner.profile.append((self.label, self.flops, self.e0, self.e1))
+            return False
 
     def drop_caches(self, densities=False):
         self._H1.clear(); self._H2.clear(); self._H3.clear()
@@ -282,8 +304,8 @@ class build_matrix_elements(object):
             c2 = _PairClass(f2, -d1)
             if c1.P == 0 or c2.P == 0:
                 continue
-            off1 = self._index(c1.offsets(f1, f2.dim * D, f2.dim, bra_base=lo))
-            off2 = self._index(c2.offsets(f2, D, 1))
+            off1 = self._index(lambda: c1.offsets(f1, f2.dim * D, f2.dim, bra_base=lo), ("off1", m1, m2, d1, lo, hi))
+            off2 = self._index(lambda: c2.offsets(f2, D, 1), ("off2", m1, m2, d1))
             if d1 == 0:
                 K = n2 * n2 + 2
                 ld = _even(K)
@@ -341,7 +363,8 @@ class build_matrix_elements(object):
                 # annihilator side: [ a | 2 V1222.caa ]
                 self._fill_raw(Y, ld, 0, y, "a", cy, sign=sy)
                 self._fill_contracted(Y, ld, ny, y, "caa", cy, V2, scale=2.0, sign=sy)
-            ctx.gemm_scatter(c1.P, c2.P, K, 1.0, A, ld, B, ld, out, off1, 0, off2, False)
+            with self._timed(self, "dimer_class_d%+d" % d1, 2.0 * c1.P * c2.P * K):
+                ctx.gemm_scatter(c1.P, c2.P, K, 1.0, A, ld, B, ld, out, off1, 0, off2, False)
         return out
 
     # ------------------------------------------------------------------------------ trimers
@@ -436,6 +459,13 @@ class build_matrix_elements(object):
         (sum, sum of squares) -- the consumer used when the block cannot be stored (1e13 elements at
         200 states/fragment).  shard=(rank, world) restricts to this rank's slab of each class's
         leading pair index (no communication; add the results)."""
+        out = self.dev.download(self.H3_moments_device(m1, m2, m3, shard))
+        if per_class:
+            return out
+        return float(out[:, 0].sum()), float(out[:, 1].sum())
+
+    def H3_moments_device(self, m1, m2, m3, shard=(0, 1)):
+        """device tensor [12, 2]: (sum, sum of squares) per charge-transfer class, no host sync"""
         ms = (m1, m2, m3)
         ctx = self.dev.ctx
         rank, world = shard
@@ -444,12 +474,53 @@ class build_matrix_elements(object):
             fac = self._trimer_factors(ms, cl)
             if fac is None:
                 continue
-            Pa = fac["ck"].P
+            Pa, Pb, Pc, n = fac["ck"].P, fac["cb"].P, fac["cc"].P, fac["n"]
             a_lo, a_hi = Pa * rank // world, Pa * (rank + 1) // world
-            ctx.trimer_stream(fac["n"], Pa, fac["cb"].P, fac["cc"].P, fac["alpha"], fac["W"], fac["ldw"], fac["beta"],
-                              fac["beta"].shape[1], fac["gamma"], fac["gamma"].shape[1], a_lo, a_hi, _lib.TRIMER_REDUCE,
-                              moments.data_ptr() + 16 * idx, None, None, None, None)
-        out = self.dev.download(moments)
-        if per_class:
-            return out
-        return float(out[:, 0].sum()), float(out[:, 1].sum())
+            flops = 2.0 * (a_hi - a_lo) * Pb * n * n + 2.0 * (a_hi - a_lo) * Pb * Pc * n
+            with self._timed(self, "trimer_stream_%s" % cl["kind"], flops):
+                ctx.trimer_stream(n, Pa, Pb, Pc, fac["alpha"], fac["W"], fac["ldw"], fac["beta"], fac["beta"].shape[1],
+                                  fac["gamma"], fac["gamma"].shape[1], a_lo, a_hi, _lib.TRIMER_REDUCE,
+                                  moments.data_ptr() + 16 * idx, None, None, None, None)
+        return moments
+
+    # ------------------------------------------------------------------- flop accounting
+    def algorithmic_flops(self, dimers=(), trimers=()):
+        """FP64 flops of the factored algorithm: precontractions
+        2*P*K*F, dimer classes 2*P1*P2*K with K = n^2 (d = 0, +-2) or 2n (d = +-1), trimer classes
+        2*Pk*n^4 + 2*Pk*Pb*n^2 + 2*Pk*Pb*Pc*n.  Returns (total, {"dimer": .., "trimer": ..})."""
+        tot_d = tot_t = 0.0
+        for m1, m2 in dimers:
+            f1, f2 = self._frag(m1), self._frag(m2)
+            n1, n2 = f1.n_orb, f2.n_orb
+            for d1 in (-2, -1, 0, 1, 2):
+                P1, P2 = _PairClass(f1, d1).P, _PairClass(f2, -d1).P
+                if P1 == 0 or P2 == 0:
+                    continue
+                if d1 == 0:
+                    tot_d += 2.0 * P1 * P2 * n2 * n2 + 2.0 * P1 * n1 * n1 * n2 * n2
+                elif abs(d1) == 2:
+                    tot_d += 2.0 * P1 * P2 * n2 * n2 + 2.0 * min(P1, P2) * n1 * n1 * n2 * n2
+                else:
+                    tot_d += 2.0 * P1 * P2 * (n1 + n2) + 2.0 * (P1 + P2) * (n1 ** 3) * n2
+        for ms in trimers:
+            f = [self._frag(m) for m in ms]
+            for cl in self._trimer_classes(ms):
+                Pk, Pb, Pc = (_PairClass(f[cl[r]], cl[d]).P for r, d in (("k", "dk"), ("b", "db"), ("c", "dc")))
+                n = f[cl["b"]].n_orb
+                if Pk and Pb and Pc:
+                    tot_t += 2.0 * Pk * n ** 4 + 2.0 * Pk * Pb * n * n + 2.0 * Pk * Pb * Pc * n
+        return tot_d + tot_t, {"dimer": tot_d, "trimer": tot_t}
+
+    def element_counts(self, dimers=(), trimers=()):
+        """non-zero (charge-allowed) element counts per class, for extrapolating sampled CPU timings"""
+        counts = {}
+        for m1, m2 in dimers:
+            f1, f2 = self._frag(m1), self._frag(m2)
+            for d1 in (-2, -1, 0, 1, 2):
+                counts[("dimer", d1)] = counts.get(("dimer", d1), 0) + _PairClass(f1, d1).P * _PairClass(f2, -d1).P
+        for ms in trimers:
+            f = [self._frag(m) for m in ms]
+            for cl in self._trimer_classes(ms):
+                Pk, Pb, Pc = (_PairClass(f[cl[r]], cl[d]).P for r, d in (("k", "dk"), ("b", "db"), ("c", "dc")))
+                counts[("trimer", cl["kind"])] = counts.get(("trimer", cl["kind"]), 0) + Pk * Pb * Pc
+        return counts
