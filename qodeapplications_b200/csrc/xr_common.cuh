@@ -49,6 +49,13 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
+// same with a zero accumulator input (first k-step of a tile: no register zeroing needed)
+__device__ __forceinline__ void dmma_m8n8k4_zero(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};"
+                 : "=d"(c0), "=d"(c1)
+                 : "d"(a), "d"(b), "d"(0.0));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_nt_scatter_kern
         cp_async_commit();
         const double* as = As + (size_t)(kt % STAGES) * BM * LDS + (warp_m * WM + g) * LDS + t;
         const double* bs = Bs + (size_t)(kt % STAGES) * BN * LDS + (warp_n * WN + g) * LDS + t;
+        // (k-steps fully unrolled: measured faster than a rolled k loop with prefetched fragments, 25.5 vs 24.0
+        //  TFLOP/s at K=326 on B200 -- ptxas interleaves the fragment loads with the DMMA stream by itself)
 #pragma unroll
         for (int ks = 0; ks < BK / 4; ++ks) {
             double a[MI], b[NJ];

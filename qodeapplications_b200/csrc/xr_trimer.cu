@@ -5,12 +5,18 @@
 // A persistent CTA takes a work item of TA=8 values of a times TB=16 values of b (128 "rows"),
 // forms X[(a,b),s] = sum_r W[a,r,s] beta[b,r] once in shared memory (negligible: 2*128*n^2 flop
 // against 2*128*Pc*n), keeps its DMMA A-fragments of X in registers, and then streams gamma in
-// tiles of 128 c through a two-slot shared-memory ring filled by 1-D bulk TMA (cp.async.bulk +
-// mbarrier).  Every 128x128 tile of T lives only in DMMA accumulators and is handed to the consumer
-// (moment reducer or scatter-store), so the 1e13-element trimer blocks never touch HBM.
+// tiles of 128 c through a shared-memory ring filled by 1-D bulk TMA (cp.async.bulk + mbarrier).
+// Every 128x128 tile of T lives only in DMMA accumulators and is handed to the consumer (moment
+// reducer or scatter-store), so the 1e13-element trimer blocks never touch HBM.
 //
-// Roofline: FP64 tensor pipe.  Algorithmic flops 2*n per element; executed 2*4*ceil(n/4)
-// (k padded to the DMMA k=4: 18 -> 20) plus, in reduce mode, 2 FP64 ops per element on the same pipe.
+// Warp-specialised: a producer warpgroup (one elected lane) streams gamma tiles into a SLOTS-deep
+// ring with full/empty mbarriers per slot; the 8 consumer warps never meet at a block-wide barrier
+// inside the tile loop.  setmaxnreg moves the producer warpgroup's registers to the consumers.
+//
+// Roofline: FP64 pipe (DMMA.8x8x4 and DFMA share it on sm_100: 64 FMA/clk/SM, 37.2 TFLOP/s measured).
+// Algorithmic flops are 2*n per element.  k = n is split as 4*KS (DMMA k-steps) + TAIL (0..2 leftover
+// k handled by DFMA on the accumulators), so n = 18 costs 18 FMA per element instead of the 20 a
+// zero-padded fifth DMMA step would; the moment reducer adds 2 FP64 ops per element on the same pipe.
 #include "xr_common.cuh"
 
 namespace {
@@ -18,7 +24,6 @@ namespace {
 constexpr int TA = 8, TB = 16, ROWS = TA * TB, CT = 128;
 constexpr int CONSUMER_WARPS = 8, CONSUMER_THREADS = CONSUMER_WARPS * 32;
 constexpr int THREADS = CONSUMER_THREADS + 128;   // + one producer warpgroup (register allocation is per 4 warps)
-constexpr int SLOTS = 4;     // gamma ring depth
 
 struct TrimerParams {
     int n;
@@ -39,11 +44,12 @@ struct TrimerParams {
     int c_tiles;
 };
 
-template <int KS>
+template <int KS, int TAIL>
 struct TrimerCfg {
-    static constexpr int KP = 4 * KS;
-    static constexpr int GS = (KP % 16 == 4 || KP % 16 == 12) ? KP : KP + 4;   // conflict-free fragment stride
-    static constexpr bool AREG = KS <= 5;
+    static constexpr int KP = 4 * KS + (TAIL ? 4 : 0);                            // packed row width (k, zero padded)
+    static constexpr int GS = (KP % 16 == 4 || KP % 16 == 12) ? KP : KP + 4;       // conflict-free fragment stride
+    static constexpr bool AREG = KS <= 5;                                         // A fragments live in registers
+    static constexpr int SLOTS = KS <= 5 ? 4 : 2;                                 // gamma ring depth (shared memory bound)
     static constexpr size_t SMEM = (size_t)(ROWS + SLOTS * CT) * GS * sizeof(double) + 2 * SLOTS * sizeof(uint64_t) + 64;
 };
 
@@ -54,13 +60,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Warp-specialised: warp 8 is the TMA producer (one elected lane streams gamma tiles into a SLOTS-deep
-// ring, full/empty mbarriers per slot); warps 0..7 are DMMA consumers that never meet at a block-wide
-// barrier inside the tile loop, so one warp's epilogue overlaps the other warps' tensor work.
-template <int KS>
+template <int KS, int TAIL>
 __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerParams p) {
-    using Cfg = TrimerCfg<KS>;
-    constexpr int KP = Cfg::KP, GS = Cfg::GS;
+    using Cfg = TrimerCfg<KS, TAIL>;
+    constexpr int KP = Cfg::KP, GS = Cfg::GS, SLOTS = Cfg::SLOTS;
     constexpr bool AREG = Cfg::AREG;
     constexpr int MI = 4, NJ = 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -107,7 +110,9 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
-    double s1 = 0.0, s2 = 0.0;
+    double s1p[NJ], s2p[NJ];     // NJ independent chains each: the moment epilogue must not be one serial FP64 dependency
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) s1p[j] = s2p[j] = 0.0;
     const int n = p.n;
     int64_t q = 0;
 
@@ -130,12 +135,20 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
         }
         consumer_barrier();
 
+        const double* xs = Xs + (32 * wm + g) * GS + t;
         double areg[AREG ? MI : 1][AREG ? KS : 1];
         if (AREG) {
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) areg[i][ks] = Xs[(32 * wm + 8 * i + g) * GS + 4 * ks + t];
+                for (int ks = 0; ks < KS; ++ks) areg[i][ks] = xs[i * 8 * GS + 4 * ks];
+        }
+        double atail[MI][TAIL ? TAIL : 1];     // X[row][4*KS + tt] for this lane's accumulator rows
+        if (TAIL) {
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int tt = 0; tt < TAIL; ++tt) atail[i][tt] = Xs[(32 * wm + 8 * i + g) * GS + 4 * KS + tt];
         }
 
         for (int ct = 0; ct < p.c_tiles; ++ct, ++q) {
@@ -143,12 +156,8 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
             mbar_wait(&full[slot], (uint32_t)(q / SLOTS) & 1);
 
             double acc[MI][NJ][2];
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-            const double* gs = Gs + (size_t)slot * CT * GS + (64 * wn + g) * GS + t;
+            const double* gtile = Gs + (size_t)slot * CT * GS;
+            const double* gs = gtile + (64 * wn + g) * GS + t;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 double b[NJ];
@@ -156,9 +165,38 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
                 for (int j = 0; j < NJ; ++j) b[j] = gs[j * 8 * GS + 4 * ks];
 #pragma unroll
                 for (int i = 0; i < MI; ++i) {
-                    const double a = AREG ? areg[AREG ? i : 0][AREG ? ks : 0] : Xs[(32 * wm + 8 * i + g) * GS + 4 * ks + t];
+                    const double a = AREG ? areg[AREG ? i : 0][AREG ? ks : 0] : xs[i * 8 * GS + 4 * ks];
 #pragma unroll
-                    for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a, b[j]);
+                    for (int j = 0; j < NJ; ++j) {
+                        if (ks == 0)
+                            dmma_m8n8k4_zero(acc[i][j][0], acc[i][j][1], a, b[j]);
+                        else
+                            dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a, b[j]);
+                    }
+                }
+            }
+            if (TAIL) {
+                // leftover k (n - 4*KS <= 2) on the accumulator layout: lane owns rows 8i+g, columns 8j+2t+{0,1}
+                const double* gt = gtile + (64 * wn + 2 * t) * GS + 4 * KS;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double bt[2];
+                        if (TAIL == 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(gt + (8 * j + e) * GS);
+                            bt[0] = v.x;
+                            bt[1] = v.y;
+                        } else {
+                            bt[0] = gt[(8 * j + e) * GS];
+                            bt[1] = 0.0;
+                        }
+#pragma unroll
+                        for (int i = 0; i < MI; ++i) {
+#pragma unroll
+                            for (int tt = 0; tt < TAIL; ++tt) acc[i][j][e] = fma(atail[i][tt], bt[tt], acc[i][j][e]);
+                        }
+                    }
                 }
             }
             __syncwarp();
@@ -169,10 +207,13 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
                 for (int i = 0; i < MI; ++i)
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
-                        s1 += acc[i][j][0] + acc[i][j][1];
-                        s2 = fma(acc[i][j][0], acc[i][j][0], s2);
-                        s2 = fma(acc[i][j][1], acc[i][j][1], s2);
+                        s1p[j] += acc[i][j][0] + acc[i][j][1];
+                        s2p[j] = fma(acc[i][j][0], acc[i][j][0], s2p[j]);
                     }
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) s2p[j] = fma(acc[i][j][1], acc[i][j][1], s2p[j]);
             } else {
                 const int64_t c_base = (int64_t)ct * CT + 64 * wn + 2 * t;
 #pragma unroll
@@ -193,6 +234,12 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
     }
 
     if (p.mode == XR_TRIMER_REDUCE) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            s1 += s1p[j];
+            s2 += s2p[j];
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -227,10 +274,10 @@ __global__ void trimer_finalize_kernel(const double* partials, int count, double
     }
 }
 
-template <int KS>
+template <int KS, int TAIL>
 int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbeta, const double* gamma, int64_t ldgamma,
                   double* moments) {
-    using Cfg = TrimerCfg<KS>;
+    using Cfg = TrimerCfg<KS, TAIL>;
     const int64_t n_a = p.a_end - p.a_begin;
     const int64_t tiles_a = (n_a + TA - 1) / TA;
     p.tiles_b = (p.Pb + TB - 1) / TB;
@@ -258,7 +305,7 @@ int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbet
     p.gammaP = gammaP;
     p.partials = partials;
 
-    auto kernel = trimer_stream_kernel<KS>;
+    auto kernel = trimer_stream_kernel<KS, TAIL>;
     XR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     kernel<<<grid, THREADS, Cfg::SMEM, ctx->stream>>>(p);
     XR_CUDA(cudaGetLastError());
@@ -305,7 +352,12 @@ extern "C" int xr_trimer_stream(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int6
     p.offA = offA;
     p.offB = offB;
     p.offC = offC;
-    if (n <= 8) return launch_trimer<2>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
-    if (n <= 20) return launch_trimer<5>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
-    return launch_trimer<12>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+    // k = n is covered by 4*KS DMMA k-steps + TAIL DFMA k (smallest instantiated cover)
+    if (n <= 4) return launch_trimer<1, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+    if (n == 5) return launch_trimer<1, 1>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+    if (n == 6) return launch_trimer<1, 2>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+    if (n <= 8) return launch_trimer<2, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+    if (n == 18) return launch_trimer<4, 2>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+    if (n <= 20) return launch_trimer<5, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+    return launch_trimer<12, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
 }

@@ -1,0 +1,31 @@
+"""Times xr_gemm_scatter alone at dimer-class sizes (development tool)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy, torch
+from qodeapplications_b200.device import Device
+dev = Device(0)
+rng = numpy.random.default_rng(0)
+for (M, N, K, scatter) in [(15272, 15272, 326, False), (15272, 15272, 326, True), (9984, 9984, 36, True), (8192, 8192, 2304, False),
+                           (15272, 324, 324, False), (9984, 18, 5832, False)]:
+    ld = K + (K & 1)
+    A, B = dev.upload(rng.standard_normal((M, ld))), dev.upload(rng.standard_normal((N, ld)))
+    if scatter:   # dimer-like layout: rows -> (i,j) pairs scattered in a (sqrt-ish) 4-index matrix
+        n1 = int(M ** 0.5) + 1; n2 = int(N ** 0.5) + 1
+        D = n1 * n2
+        C = dev.empty((D * D,))
+        offM = ((numpy.arange(M) // n1) * n2 * D + (numpy.arange(M) % n1) * n2).astype(numpy.int64)
+        offN = ((numpy.arange(N) // n2) * D + (numpy.arange(N) % n2)).astype(numpy.int64)
+        oM, oN = dev.upload(offM, numpy.int64), dev.upload(offN, numpy.int64)
+        run = lambda: dev.ctx.gemm_scatter(M, N, K, 1.0, A, ld, B, ld, C, oM, 0, oN, False)
+    else:
+        C = dev.empty((M, N))
+        run = lambda: dev.ctx.gemm_scatter(M, N, K, 1.0, A, ld, B, ld, C, None, N, None, False)
+    run(); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    print(json.dumps({"M": M, "N": N, "K": K, "scatter": scatter, "ms": best, "tflops": 2.0 * M * N * K / best / 1e9,
+                      "write_GBs": 8.0 * M * N / best / 1e6}))
+    del A, B, C
