@@ -194,3 +194,48 @@ extern "C" int xr_scatter_const(xr_ctx* ctx, double* C, const int64_t* idx, int6
     ctx->launches++;
     return XR_OK;
 }
+
+struct PermuteParams {
+    int nd;
+    int64_t shape[8];
+    int64_t stride[8];
+    int64_t total;
+};
+
+__global__ void permute_copy_kernel(double* __restrict__ dst, const double* __restrict__ src, const PermuteParams p, double alpha) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < p.total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t rem = t, at = 0;
+#pragma unroll
+        for (int d = 7; d >= 0; --d) {
+            if (d < p.nd) {
+                int64_t i = rem % p.shape[d];
+                rem /= p.shape[d];
+                at += i * p.stride[d];
+            }
+        }
+        dst[t] = alpha * src[at];
+    }
+}
+
+extern "C" int xr_permute_copy(xr_ctx* ctx, double* dst, const double* src, int nd, const int64_t* shape,
+                               const int64_t* src_strides, double alpha) {
+    XR_REQUIRE(ctx && dst && src && shape && src_strides, "xr_permute_copy: null argument");
+    XR_REQUIRE(nd >= 1 && nd <= 8, "xr_permute_copy: nd=%d unsupported (1..8)", nd);
+    PermuteParams p{};
+    p.nd = nd;
+    p.total = 1;
+    for (int d = 0; d < nd; ++d) {
+        XR_REQUIRE(shape[d] >= 0, "xr_permute_copy: negative extent");
+        p.shape[d] = shape[d];
+        p.stride[d] = src_strides[d];
+        p.total *= shape[d];
+    }
+    if (p.total == 0) return XR_OK;
+    int64_t blocks = (p.total + 255) / 256;
+    int64_t cap = (int64_t)ctx->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    permute_copy_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(dst, src, p, alpha);
+    XR_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return XR_OK;
+}

@@ -41,6 +41,7 @@ _PROTOTYPES = {
     "xr_gemm_scatter": (_int, [_ptr, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _int]),
     "xr_copy2d_scaled": (_int, [_ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _dbl]),
     "xr_scatter_const": (_int, [_ptr, _ptr, _ptr, _i64, _dbl, _int]),
+    "xr_permute_copy": (_int, [_ptr, _ptr, _ptr, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _dbl]),
     "xr_trimer_stream": (_int, [_ptr, _int, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _int,
                                 _ptr, _ptr, _ptr, _ptr, _ptr]),
 }
@@ -153,6 +154,12 @@ class Context(object):
     def copy2d_scaled(self, dst, dst_ld, src, src_ld, rows, cols, alpha=1.0):
         check(self.lib.xr_copy2d_scaled(self.handle, _p(dst), dst_ld, _p(src), src_ld, rows, cols, float(alpha)),
               "xr_copy2d_scaled")
+
+    def permute_copy(self, dst, src, shape, src_strides, alpha=1.0):
+        nd = len(shape)
+        arr = _i64 * nd
+        check(self.lib.xr_permute_copy(self.handle, _p(dst), _p(src), nd, arr(*[int(x) for x in shape]),
+                                       arr(*[int(x) for x in src_strides]), float(alpha)), "xr_permute_copy")
 
     def scatter_const(self, C, idx, count, value, accumulate=False):
         check(self.lib.xr_scatter_const(self.handle, _p(C), _p(idx), count, float(value), 1 if accumulate else 0),
