@@ -14,6 +14,7 @@ seed, a checksum of the inputs and the reference's outputs.
     python oracle/gen_golden.py            # writes tests/golden/
 """
 import hashlib
+import itertools
 import io
 import contextlib
 import os
@@ -166,6 +167,51 @@ def reference_hermitian(system, xr_order, frags=(0, 1)):
     return [numpy.asarray(h) for h in H1], numpy.asarray(H2)
 
 
+def reference_hermitian_blocks(system, labels_by_family):
+    """Every 2-fragment diagram block blocks[(0,1)][charges][label] of the reference, for every charge
+    combination, plus the 1-fragment blocks -- straight from the reference's diagrammatic_expansion."""
+    get_xr_result, XR_tensor = import_reference_hermitian()
+    import diagrammatic_expansion
+    from diagrams import S_diagrams, ST_diagrams, SU_diagrams, SV_diagrams
+    from precontract import precontract
+    from qode.util import struct, timer
+    init = XR_tensor.init
+    dens = []
+    for rho in system["densities"][:2]:
+        wrapped = {}
+        for key, val in rho.items():
+            wrapped[key] = val if key in ("n_elec", "n_states", "n_states_bra") else {c: init(t) for c, t in val.items()}
+        dens.append(wrapped)
+    symm = system["symm"]
+    S = _wrap_blocks(symm.S, init)
+    cache = precontract(dens, S, timer())
+    families = {
+        "S": (S, S_diagrams),
+        "ST": (struct(S=S, T=_wrap_blocks(symm.T, init)), ST_diagrams),
+        "SU": (struct(S=S, U=_wrap_blocks(symm.U, init)), SU_diagrams),
+        "SV": (struct(S=S, V=_wrap_blocks(symm.V, init)), SV_diagrams),
+    }
+    charges = system["charges"]
+    out = {}
+    for fam, labels in labels_by_family.items():
+        ints, diagrams = families[fam]
+        blk = diagrammatic_expansion.blocks(densities=dens, integrals=ints, diagrams=diagrams, contract_cache=cache,
+                                            timings=timer(), precon_timings=timer())
+        for label in labels:
+            if label in diagrams.catalog.get(1, {}):
+                for m in (0, 1):
+                    for c in charges:
+                        out["%s|%d|%d,%d" % (label, m, c, c)] = numpy.asarray(blk[(m,)][((c, c),)][label])
+                continue
+            for ci0, ci1, cj0, cj1 in itertools.product(charges, repeat=4):
+                if ci0 + ci1 != cj0 + cj1:
+                    continue
+                val = blk[(0, 1)][((ci0, cj0), (ci1, cj1))][label]
+                if val is not None:
+                    out["%s|%d,%d,%d,%d" % (label, ci0, ci1, cj0, cj1)] = numpy.asarray(val)
+    return out
+
+
 # ------------------------------------------------------------------------------------- main
 
 def main():
@@ -202,5 +248,22 @@ def main():
         print("wrote", path, H2.shape, float(numpy.abs(H2).max()))
 
 
+def main_blocks():
+    out_dir = os.path.join(REPO, "tests", "golden")
+    system = synth.make_system("toy", ops=synth.OPS_ORDER1, with_bior=True)
+    labels = {"S": ["s01"], "ST": ["t00", "t01", "s01t10", "s01t00", "s01t11", "s01t01"],
+              "SU": ["u000", "u100", "u001", "u101", "s01u010", "s01u000", "s01u011", "s01u001", "s01u110", "s01u100",
+                     "s01u111", "s01u101"],
+              "SV": ["v0000", "v0101", "v0001", "v0100", "v0011", "s01v0100", "s01v1101", "s01v0000", "s01v0101", "s01v1100",
+                     "s01v1111", "s01v0001", "s01v0111"]}
+    blocks = reference_hermitian_blocks(system, labels)
+    path = os.path.join(out_dir, "hermitian_toy_blocks.npz")
+    numpy.savez_compressed(path, input_sha256=input_checksum(system), **blocks)
+    print("wrote", path, len(blocks), "blocks")
+
+
 if __name__ == "__main__":
+    if "--blocks" in sys.argv:
+        main_blocks()
+        sys.exit(0)
     main()

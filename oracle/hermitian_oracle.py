@@ -1,0 +1,225 @@
+"""CPU oracle for the hermitian-XRCC Hamiltonian build (orders 0 and 1).  TEST INFRASTRUCTURE: only
+tests/, smoke() and bench.py's CPU legs may import this.
+
+Third-party dependency of the reference on this path: ``qode`` (github adutoi/Qode, version
+unpinned -- no requirements or lock file, README.rst:28-33) plus tensorly/opt_einsum, none of
+them under /root/reference or installed.  The arithmetic below that seam is plain tensor contraction,
+so this file restates it with numpy.einsum from the UN-precontracted definition that every reference
+diagram function carries as a comment (e.g. hermitian-XRCC/diagrams/SV_2mer_0.py:29-31), plus
+
+  * build_diagram.py:87-97   -- n_j0 parity of the unpermuted first fragment's ket electrons, permutations
+  * diagrammatic_expansion.py:27-59 -- transposition back by [perm] + [n + perm], sum over permutations
+  * XR_term.py:22-165        -- packing into charge-blocked matrices, Kronecker deltas over spectators
+  * get_xr_result.py:86-213, 300-353 -- which families enter at xr_order 0 / 1, S2inv, final reorder.
+
+Parity status: PINNED against the reference itself: tests/golden/hermitian_toy_order{0,1}.npz (H1, H2 of
+the reference's own get_xr_H, run through oracle/qode_shim by oracle/gen_golden.py) and
+tests/golden/hermitian_toy_blocks.npz (every diagram block of orders 0-1 for every charge combination).
+"""
+import itertools
+import numpy
+
+# label: (coefficient, parity shift or None, [(tensor name, index letters), ...]);  i,j = bra,ket of diagram
+# fragment 0; k,l = bra,ket of diagram fragment 1.  Tensor names: <op><frag> density, s/t<ff>, u<n>_<ff>, v<ffff>.
+TWO_FRAGMENT = {
+    "t01":      (1, 0,     [("c0", "ijp"), ("a1", "klq"), ("t01", "pq")]),                       # ST_2mer_0.py:29-31
+    "u001":     (1, 0,     [("c0", "ijp"), ("a1", "klq"), ("u0_01", "pq")]),                     # SU_2mer_0.py:102-104
+    "u101":     (1, 0,     [("c0", "ijp"), ("a1", "klq"), ("u1_01", "pq")]),                     # SU_2mer_0.py:113-115
+    "v0101":    (4, None,  [("ca0", "ijpr"), ("ca1", "klqs"), ("v0101", "pqrs")]),               # SV_2mer_0.py:29-31
+    "v0001":    (2, 1,     [("cca0", "ijpqr"), ("a1", "kls"), ("v0001", "pqrs")]),               # SV_2mer_0.py:40-42
+    "v0100":    (2, 0,     [("caa0", "ijpsr"), ("c1", "klq"), ("v0100", "pqrs")]),               # SV_2mer_0.py:51-53
+    "v0011":    (1, None,  [("cc0", "ijpq"), ("aa1", "klsr"), ("v0011", "pqrs")]),               # SV_2mer_0.py:62-64
+    "s01":      (1, 0,     [("c0", "ijp"), ("a1", "klq"), ("s01", "pq")]),                       # S_2mer_1.py:29-31
+    "s01t10":   (-1, None, [("ca0", "ijtq"), ("ca1", "klpu"), ("s01", "tu"), ("t10", "pq")]),    # ST_2mer_1.py:29-32
+    "s01t00":   (1, 1,     [("cca0", "ijptq"), ("a1", "klu"), ("s01", "tu"), ("t00", "pq")]),    # ST_2mer_1.py:42-45
+    "s01t11":   (1, 1,     [("c0", "ijt"), ("caa1", "klpuq"), ("s01", "tu"), ("t11", "pq")]),    # ST_2mer_1.py:55-58
+    "s01t01":   (1, None,  [("cc0", "ijpt"), ("aa1", "kluq"), ("s01", "tu"), ("t01", "pq")]),    # ST_2mer_1.py:68-71
+    "s01v0100": (-2, None, [("ccaa0", "ijptsr"), ("ca1", "klqu"), ("s01", "tu"), ("v0100", "pqrs")]),     # SV_2mer_1.py:29-32
+    "s01v1101": (2, None,  [("ca0", "ijtr"), ("ccaa1", "klpqus"), ("s01", "tu"), ("v1101", "pqrs")]),     # SV_2mer_1.py:42-45
+    "s01v0000": (1, 0,     [("cccaa0", "ijpqtsr"), ("a1", "klu"), ("s01", "tu"), ("v0000", "pqrs")]),     # SV_2mer_1.py:55-58
+    "s01v0101": (4, 0,     [("cca0", "ijptr"), ("caa1", "klqus"), ("s01", "tu"), ("v0101", "pqrs")]),     # SV_2mer_1.py:68-71
+    "s01v1100": (1, 0,     [("caa0", "ijtsr"), ("cca1", "klpqu"), ("s01", "tu"), ("v1100", "pqrs")]),     # SV_2mer_1.py:81-84
+    "s01v1111": (1, 0,     [("c0", "ijt"), ("ccaaa1", "klpqusr"), ("s01", "tu"), ("v1111", "pqrs")]),     # SV_2mer_1.py:94-97
+    "s01v0001": (2, None,  [("ccca0", "ijpqtr"), ("aa1", "klus"), ("s01", "tu"), ("v0001", "pqrs")]),     # SV_2mer_1.py:107-110
+    "s01v0111": (-2, None, [("cc0", "ijpt"), ("caaa1", "klqusr"), ("s01", "tu"), ("v0111", "pqrs")]),     # SV_2mer_1.py:120-123
+}
+for _n in "01":      # SU_2mer_1.py: the ST forms with t## -> u<n>_##
+    TWO_FRAGMENT["s01u%s10" % _n] = (-1, None, [("ca0", "ijtq"), ("ca1", "klpu"), ("s01", "tu"), ("u%s_10" % _n, "pq")])
+    TWO_FRAGMENT["s01u%s00" % _n] = (1, 1, [("cca0", "ijptq"), ("a1", "klu"), ("s01", "tu"), ("u%s_00" % _n, "pq")])
+    TWO_FRAGMENT["s01u%s11" % _n] = (1, 1, [("c0", "ijt"), ("caa1", "klpuq"), ("s01", "tu"), ("u%s_11" % _n, "pq")])
+    TWO_FRAGMENT["s01u%s01" % _n] = (1, None, [("cc0", "ijpt"), ("aa1", "kluq"), ("s01", "tu"), ("u%s_01" % _n, "pq")])
+
+ONE_FRAGMENT = {
+    "t00":   [("ca0", "ijpq"), ("t00", "pq")],              # ST_1mer_0.py:24-30
+    "u000":  [("ca0", "ijpq"), ("u0_00", "pq")],            # SU_1mer_0.py:24-30
+    "v0000": [("ccaa0", "ijpqsr"), ("v0000", "pqrs")],      # SV_1mer_0.py:24-31
+}
+
+_PM = [(+1, (0, 1)), (-1, (1, 0))]
+_PP = [(+1, (0, 1)), (+1, (1, 0))]
+# label: (Dchgs, permutations)   -- S_diagrams.py:33-40, ST_diagrams.py:35-40, SU_diagrams.py:35-46, SV_diagrams.py:35-48
+CATALOG2 = {
+    "t01": ((-1, 1), _PM), "u001": ((-1, 1), _PM), "u101": ((-1, 1), _PM), "u100": ((0, 0), _PP),
+    "v0101": ((0, 0), [(+1, (0, 1))]), "v0001": ((-1, 1), _PM), "v0100": ((1, -1), _PM), "v0011": ((-2, 2), _PP),
+    "s01": ((-1, 1), _PM),
+    "s01t10": ((0, 0), _PP), "s01t00": ((-1, 1), _PM), "s01t11": ((-1, 1), _PM), "s01t01": ((-2, 2), _PP),
+    "s01v0100": ((0, 0), _PP), "s01v1101": ((0, 0), _PP), "s01v0000": ((-1, 1), _PM), "s01v0101": ((-1, 1), _PM),
+    "s01v1100": ((1, -1), _PM), "s01v1111": ((-1, 1), _PM), "s01v0001": ((-2, 2), _PP), "s01v0111": ((-2, 2), _PP),
+}
+for _n in "01":
+    CATALOG2["s01u%s10" % _n] = ((0, 0), _PP)
+    CATALOG2["s01u%s00" % _n] = ((-1, 1), _PM)
+    CATALOG2["s01u%s11" % _n] = ((-1, 1), _PM)
+    CATALOG2["s01u%s01" % _n] = ((-2, 2), _PP)
+
+LISTS = {   # diagram_lists.py:10-71, orders 0 and 1
+    "S0": {0: ["identity"]}, "S2": {1: ["s01"]},
+    "ST1": {0: ["t00"]}, "ST2": {0: ["t01"], 1: ["s01t10", "s01t00", "s01t11", "s01t01"]},
+    "SU1": {0: ["u000"]}, "SU2": {0: ["u100", "u001", "u101"],
+                                  1: ["s01u010", "s01u000", "s01u011", "s01u001", "s01u110", "s01u100", "s01u111", "s01u101"]},
+    "SV1": {0: ["v0000"]}, "SV2": {0: ["v0101", "v0001", "v0100", "v0011"],
+                                   1: ["s01v0100", "s01v1101", "s01v0000", "s01v0101", "s01v1100", "s01v1111", "s01v0001", "s01v0111"]},
+}
+
+
+class integrals(object):
+    """S, T, U, V (+ V_diff) blocked containers with ndarray blocks"""
+    def __init__(self, S, T=None, U=None, V=None):
+        self.S, self.T, self.U, self.V = S, T, U, V
+
+
+def _tensor(name, dens, ints, frags, chgs):
+    """resolve a tensor name for diagram fragments -> absolute fragments `frags`, charges `chgs`"""
+    digits = [int(c) for c in name if c.isdigit()]
+    head = name.rstrip("0123456789_")
+    if name[0] in "stuv" and all(c.isdigit() or c == "_" for c in name[1:]):
+        block = tuple(frags[d] for d in digits)
+        return numpy.asarray({"s": ints.S, "t": ints.T, "u": ints.U, "v": ints.V}[name[0]][block])
+    op, d = name[:-1], int(name[-1])
+    return numpy.asarray(dens[frags[d]][op][chgs[d]])
+
+
+def _einsum(terms, dens, ints, frags, chgs, out):
+    operands = [_tensor(name, dens, ints, frags, chgs) for name, _ in terms]
+    return numpy.einsum(",".join(idx for _, idx in terms) + "->" + out, *operands, optimize=True)
+
+
+def dimer_block(label, dens, ints, subsystem, charges):
+    """block [N_i0, N_i1, N_j0, N_j1] (subsystem order) of a 2-fragment diagram, or None.
+    subsystem = (m0, m1) ascending; charges = ((chg_i0, chg_j0), (chg_i1, chg_j1))."""
+    Dchgs, permutations = CATALOG2[label]
+    n_j0 = dens[subsystem[0]]["n_elec"][charges[0][1]] % 2           # unpermuted first fragment (build_diagram.py:87-92)
+    total = None
+    for phase, perm in permutations:
+        frags = [subsystem[m] for m in perm]
+        chgs = [charges[m] for m in perm]
+        if any(chgs[m][0] - chgs[m][1] != Dchgs[m] for m in range(2)):
+            continue
+        if label == "u100":                                          # SU_2mer_0.py:37-48
+            blk = _einsum([("ca0", "ijpq"), ("u1_00", "pq")], dens, ints, frags, chgs, "ij")
+            n1 = dens[frags[1]]["n_states"][chgs[1][1]]
+            val = numpy.einsum("ij,kl->ikjl", blk, numpy.eye(n1))
+        else:
+            coef, shift, terms = TWO_FRAGMENT[label]
+            val = coef * _einsum(terms, dens, ints, frags, chgs, "ikjl")
+            if shift is not None:
+                val = val * (-1) ** (n_j0 + shift)
+        val = phase * val.transpose(list(perm) + [2 + m for m in perm])      # diagrammatic_expansion.py:32,58
+        total = val if total is None else total + val
+    return total
+
+
+def monomer_block(label, dens, ints, m, chg_i, chg_j):
+    if chg_i != chg_j:
+        return None
+    return _einsum(ONE_FRAGMENT[label], dens, ints, [m], [(chg_i, chg_j)], "ij")
+
+
+def monomer_matrix(dens, ints, labels, m, charge_blocks):
+    """XR_term.py:96-115"""
+    n = dens[m]["n_states"]
+    off = numpy.concatenate([[0], numpy.cumsum([n[c] for c in charge_blocks])])
+    M = numpy.zeros((off[-1], off[-1]))
+    for a, ci in enumerate(charge_blocks):
+        for label in labels:
+            M[off[a]:off[a + 1], off[a]:off[a + 1]] += monomer_block(label, dens, ints, m, ci, ci)
+    return M
+
+
+def dimer_matrix(dens, ints, active, charge_blocks, subsystem=(0, 1)):
+    """XR_term.py:117-165 + _evaluate_block :22-94, charge-blocked ordering; active = {frag_order: [labels]}"""
+    m0, m1 = subsystem
+    n0, n1 = dens[m0]["n_states"], dens[m1]["n_states"]
+    sizes = [n0[c0] * n1[c1] for c0, c1 in charge_blocks]
+    off = numpy.concatenate([[0], numpy.cumsum(sizes)])
+    M = numpy.zeros((off[-1], off[-1]))
+    for a, (ci0, ci1) in enumerate(charge_blocks):
+        for b, (cj0, cj1) in enumerate(charge_blocks):
+            shape = (n0[ci0], n1[ci1], n0[cj0], n1[cj1])
+            block = numpy.zeros(shape)
+            for frag_order, labels in active.items():
+                for label in labels:
+                    if frag_order == 0:
+                        if ci0 == cj0 and ci1 == cj1:
+                            block += numpy.einsum("ij,kl->ikjl", numpy.eye(shape[0]), numpy.eye(shape[1]))
+                    elif frag_order == 1:
+                        if ci0 == cj0 and ci1 == cj1:
+                            block += numpy.einsum("ij,kl->ikjl", monomer_block(label, dens, ints, m0, ci0, cj0), numpy.eye(shape[1]))
+                            block += numpy.einsum("ij,kl->ikjl", numpy.eye(shape[0]), monomer_block(label, dens, ints, m1, ci1, cj1))
+                    elif ci0 + ci1 == cj0 + cj1:
+                        val = dimer_block(label, dens, ints, subsystem, ((ci0, cj0), (ci1, cj1)))
+                        if val is not None:
+                            block += val
+            M[off[a]:off[a + 1], off[b]:off[b + 1]] += block.reshape(shape[0] * shape[1], shape[2] * shape[3])
+    return M
+
+
+def reorder(Hblocked, dens, monomer_charges):
+    """get_xr_result.py:300-353: charge-blocked -> (global i0, global i1) row-major"""
+    dims0 = [dens[0]["n_states"][c] for c in monomer_charges[0]]
+    dims1 = [dens[1]["n_states"][c] for c in monomer_charges[1]]
+    mapping = numpy.zeros((sum(dims0), sum(dims1)), dtype=int)
+    idx, beg0 = 0, 0
+    for d0 in dims0:
+        beg1 = 0
+        for d1 in dims1:
+            for a in range(d0):
+                for b in range(d1):
+                    mapping[beg0 + a, beg1 + b] = idx
+                    idx += 1
+            beg1 += d1
+        beg0 += d0
+    order = mapping.reshape(-1)
+    return Hblocked[numpy.ix_(order, order)]
+
+
+def get_xr_H(symm, bior, dens, xr_order, monomer_charges):
+    """get_xr_result.py:45-355 for xr_order 0 and 1.  symm/bior: objects with S,T,U,V (bior also V_diff)."""
+    charges = [(c0, c1) for c0 in monomer_charges[0] for c1 in monomer_charges[1]]
+    L = LISTS
+    mk = lambda T=None, U=None, V=None: integrals(symm.S, T, U, V)
+    if xr_order == 0:
+        H1 = [monomer_matrix(dens, mk(T=bior.T), L["ST1"][0], m, monomer_charges[m])
+              + monomer_matrix(dens, mk(U=bior.U), L["SU1"][0], m, monomer_charges[m])
+              + monomer_matrix(dens, mk(V=bior.V), L["SV1"][0], m, monomer_charges[m]) for m in (0, 1)]
+        H2 = (dimer_matrix(dens, mk(T=bior.T), {2: L["ST2"][0]}, charges) + dimer_matrix(dens, mk(U=bior.U), {2: L["SU2"][0]}, charges)
+              + dimer_matrix(dens, mk(V=bior.V), {2: L["SV2"][0]}, charges))
+    elif xr_order == 1:
+        H1 = [monomer_matrix(dens, mk(T=symm.T), L["ST1"][0], m, monomer_charges[m])
+              + monomer_matrix(dens, mk(U=symm.U), L["SU1"][0], m, monomer_charges[m])
+              + monomer_matrix(dens, mk(V=symm.V), L["SV1"][0], m, monomer_charges[m]) for m in (0, 1)]
+        S2 = dimer_matrix(dens, mk(), {0: L["S0"][0], 2: L["S2"][1]}, charges)
+        S2inv = numpy.linalg.inv(S2)
+        S2H2 = dimer_matrix(dens, mk(T=symm.T), {1: L["ST1"][0], 2: L["ST2"][0]}, charges)
+        S2H2 += dimer_matrix(dens, mk(U=symm.U), {1: L["SU1"][0], 2: L["SU2"][0]}, charges)
+        S2H2 += dimer_matrix(dens, mk(T=bior.T), {2: L["ST2"][1]}, charges)
+        S2H2 += dimer_matrix(dens, mk(U=bior.U), {2: L["SU2"][1]}, charges)
+        S2H2 += dimer_matrix(dens, mk(V=bior.V_diff), {1: L["SV1"][0], 2: L["SV2"][0]}, charges)
+        S2H2 += dimer_matrix(dens, mk(V=bior.V), {2: L["SV2"][1]}, charges)
+        H2 = S2inv @ S2H2
+        H2 -= dimer_matrix(dens, mk(T=symm.T), {1: L["ST1"][0]}, charges)
+        H2 -= dimer_matrix(dens, mk(U=symm.U), {1: L["SU1"][0]}, charges)
+        H2 -= dimer_matrix(dens, mk(V=symm.V), {1: L["SV1"][0]}, charges)
+    else:
+        raise NotImplementedError(xr_order)
+    return H1, reorder(H2, dens, monomer_charges)

@@ -166,7 +166,7 @@ class build_matrix_elements(object):
     @property
     def dev(self):
         if self._dev is None:
-            self._dev = self._device_arg if isinstance(self._device_arg, Device) else Device(self._device_arg)
+            self._dev = self._device_arg if hasattr(self._device_arg, "ctx") else Device(self._device_arg)
         return self._dev
 
     def _frag(self, m):

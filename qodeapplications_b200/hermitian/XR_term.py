@@ -1,0 +1,154 @@
+"""Packs diagram blocks into XR matrices -- drop-in for hermitian-XRCC/XR_term.py
+(``monomer_matrix`` :96-115, ``dimer_matrix`` :117-165, same positional signatures, ndarray result in
+the same charge-blocked ordering: rows for each (chg1, chg2) of ``charge_blocks``, (i1, i2) row-major).
+
+The reference materialises every diagram block on the host, transposes it and slice-adds it (with a
+Python loop over spectator states for the Kronecker deltas, :69-80).  Here the matrix lives in HBM and
+every diagram is accumulated in place by the epilogue of its own GEMM; the result is downloaded once.
+
+Extra keyword arguments (defaults reproduce the reference):
+  ordering="blocked" | "final" -- "final" lays rows/columns out as (global i1, global i2), i.e. what
+      get_xr_result.py:300-353 produces from the blocked matrix with a double Python loop;
+  device_result=False          -- return the device tensor instead of a host ndarray;
+  into=None, scale=1.0         -- accumulate scale * (this term) into an existing device matrix instead of a
+      fresh zero one (how get_xr_H sums and subtracts terms without any elementwise pass).
+"""
+import numpy
+
+from .tensor import DeviceTensor
+
+
+def _ascending(array):
+    return all(b > a for a, b in zip(array[:-1], array[1:]))
+
+
+def _check_no_det(bra_det, ket_det):
+    if bra_det or ket_det:
+        raise NotImplementedError("bra_det / ket_det matrices (StateSpaceOptimizer gradient variants) are not built yet")
+
+
+def _buffer(into, shape):
+    buf = into.buf if isinstance(into, DeviceTensor) else into
+    if tuple(buf.shape) != tuple(shape):
+        raise ValueError("into= has shape %r, expected %r" % (tuple(buf.shape), tuple(shape)))
+    return buf
+
+
+def _finish(dev, Matrix, device_result):
+    if device_result:
+        return DeviceTensor(Matrix, dev)
+    return dev.download(Matrix)
+
+
+def monomer_matrix(op_blocks, active_diagrams, subsys_index, charge_blocks, timings, device_result=False, into=None, scale=1.0):
+    rho = op_blocks.densities[subsys_index]
+    dev = op_blocks.dev
+    dim_bra = sum(rho["n_states_bra"][chg] for chg in charge_blocks)
+    dim_ket = sum(rho["n_states"][chg] for chg in charge_blocks)
+    Matrix = dev.zeros((dim_bra, dim_ket)) if into is None else _buffer(into, (dim_bra, dim_ket))
+    ld = dim_ket
+    Ibeg = 0
+    for chg_i in charge_blocks:
+        Jbeg = 0
+        for chg_j in charge_blocks:
+            for frag_order, labels in active_diagrams.items():
+                if frag_order != 1:
+                    raise NotImplementedError("monomer_matrix with diagrams of fragment order %r" % (frag_order,))
+                if chg_i != chg_j:
+                    continue
+                entry = op_blocks[(subsys_index,)][((chg_i, chg_j),)]
+                for label in labels:
+                    timings.start()
+                    entry.accumulate(label, Matrix, Ibeg * ld + Jbeg, {("i", 0): ld, ("j", 0): 1}, scale)
+                    timings.record("block evaluation")
+            Jbeg += rho["n_states"][chg_j]
+        Ibeg += rho["n_states_bra"][chg_i]
+    return _finish(dev, Matrix, device_result)
+
+
+def dimer_matrix(op_blocks, active_diagrams, subsys_indices, charge_blocks, timings, bra_det=False, ket_det=False,
+                 ordering="blocked", device_result=False, into=None, scale=1.0):
+    _check_no_det(bra_det, ket_det)
+    m = tuple(subsys_indices)
+    rho1, rho2 = (op_blocks.densities[x] for x in m)
+    dev = op_blocks.dev
+    dim_bra = sum(rho1["n_states_bra"][c1] * rho2["n_states_bra"][c2] for c1, c2 in charge_blocks)
+    dim_ket = sum(rho1["n_states"][c1] * rho2["n_states"][c2] for c1, c2 in charge_blocks)
+    Matrix = dev.zeros((dim_bra, dim_ket)) if into is None else _buffer(into, (dim_bra, dim_ket))
+    ld = dim_ket
+
+    # where each charge block starts and how its two state indices stride, for bras (rows) and kets (columns)
+    def layout(which):
+        n1, n2 = rho1[which], rho2[which]
+        starts = {}
+        if ordering == "blocked":                       # XR_term.py:153-164
+            beg = 0
+            for c1, c2 in charge_blocks:
+                starts[(c1, c2)] = (beg, n2[c2])        # (first index, stride of the fragment-1 state)
+                beg += n1[c1] * n2[c2]
+        elif ordering == "final":                       # get_xr_result.py:300-353
+            chgs1, chgs2 = [], []
+            for c1, c2 in charge_blocks:
+                if c1 not in chgs1:
+                    chgs1.append(c1)
+                if c2 not in chgs2:
+                    chgs2.append(c2)
+            if len(chgs1) * len(chgs2) != len(charge_blocks):
+                raise ValueError("ordering='final' needs charge_blocks to be a full product of monomer charges")
+            off1, off2, acc = {}, {}, 0
+            for c in chgs1:
+                off1[c] = acc
+                acc += n1[c]
+            tot2 = 0
+            for c in chgs2:
+                off2[c] = tot2
+                tot2 += n2[c]
+            for c1, c2 in charge_blocks:
+                starts[(c1, c2)] = (off1[c1] * tot2 + off2[c2], tot2)
+        else:
+            raise ValueError("ordering must be 'blocked' or 'final'")
+        return starts
+
+    rows, cols = layout("n_states_bra"), layout("n_states")
+    n_i = lambda x, chg: op_blocks.densities[m[x]]["n_states_bra"][chg]
+    n_j = lambda x, chg: op_blocks.densities[m[x]]["n_states"][chg]
+
+    for chg_i in charge_blocks:
+        for chg_j in charge_blocks:
+            subsys_charges = [(chg_i[0], chg_j[0]), (chg_i[1], chg_j[1])]
+            (Ibeg, Istride), (Jbeg, Jstride) = rows[tuple(chg_i)], cols[tuple(chg_j)]
+            base = Ibeg * ld + Jbeg
+            slot = {("i", 0): Istride * ld, ("i", 1): ld, ("j", 0): Jstride, ("j", 1): 1}
+            for frag_order, labels in active_diagrams.items():
+                # every ascending group of `frag_order` fragments of the dimer (XR_term.py:41-53)
+                groups = {0: [()], 1: [(0,), (1,)], 2: [(0, 1)]}.get(frag_order)
+                if groups is None:
+                    raise NotImplementedError("dimer_matrix with diagrams of fragment order %r" % (frag_order,))
+                for frags in groups:
+                    others = [x for x in (0, 1) if x not in frags]
+                    if any(subsys_charges[x][0] != subsys_charges[x][1] for x in others):
+                        continue
+                    if sum(subsys_charges[x][0] for x in frags) != sum(subsys_charges[x][1] for x in frags):
+                        continue
+                    entry = op_blocks[tuple(m[x] for x in frags)][tuple(subsys_charges[x] for x in frags)]
+                    for label in labels:
+                        timings.start()
+                        if frag_order == 0:
+                            # diagram value (1 for "identity") on the diagonal of the block (XR_term.py:69-80)
+                            value = entry[label]
+                            if value is not None:
+                                n0, n1 = n_j(0, chg_j[0]), n_j(1, chg_j[1])
+                                a = numpy.arange(n0, dtype=numpy.int64)[:, None]
+                                b = numpy.arange(n1, dtype=numpy.int64)[None, :]
+                                idx = base + a * (slot[("i", 0)] + slot[("j", 0)]) + b * (slot[("i", 1)] + slot[("j", 1)])
+                                idx = dev.upload(idx.reshape(-1), dtype=numpy.int64)
+                                dev.ctx.scatter_const(Matrix, idx, n0 * n1, scale * float(value), True)
+                        elif frag_order == 1:
+                            x, o = frags[0], others[0]
+                            strides = {("i", 0): slot[("i", x)], ("j", 0): slot[("j", x)],
+                                       "delta": slot[("i", o)] + slot[("j", o)], "n_delta": n_j(o, chg_j[o])}
+                            entry.accumulate(label, Matrix, base, strides, scale)
+                        else:
+                            entry.accumulate(label, Matrix, base, slot, scale)
+                        timings.record("block evaluation")
+    return _finish(dev, Matrix, device_result)

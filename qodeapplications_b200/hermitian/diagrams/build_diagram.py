@@ -22,9 +22,9 @@ def build_diagram(contraction, Dchgs, permutations):
                 result = phase * contraction(X, **args)
                 supersys_info.timings.record(label)
                 return result
-            def accumulate_into(out, offset, strides):
+            def accumulate_into(out, offset, strides, scale=1.0):
                 supersys_info.timings.start()
-                contraction.accumulate(X, phase, out, offset, strides)
+                contraction.accumulate(X, phase * scale, out, offset, strides)
                 supersys_info.timings.record(label)
             do_contraction.accumulate_into = accumulate_into if hasattr(contraction, "accumulate") else None
             do_contraction.phase = phase

@@ -1,0 +1,88 @@
+"""``get_xr_H`` -- drop-in for hermitian-XRCC/get_xr_result.py:45-355 (same signature and return value).
+
+    get_xr_H(ints=(symm_ints, bior_ints, nuc_rep), dens=[rho0, rho1], xr_order, monomer_charges,
+             bra_det=False, ket_det=False) -> (H1, H2)
+
+H1 = [monomer matrix of fragment 0, of fragment 1]; H2 = dimer matrix with rows/columns ordered as
+(global state of fragment 0, global state of fragment 1), states of a fragment ordered by the charges of
+``monomer_charges`` (get_xr_result.py:300-353).  Orders 0 and 1 are built (order 2 needs the 28
+second-order diagrams and rank-6 densities: NotImplementedError for now, like the reference does
+for orders it does not know, :298).
+
+All matrices are assembled in HBM directly in the final ordering, so the reference's O(dim^4)
+Python reorder loop disappears; ``S2inv @ S2H2`` runs through xr_gemm_scatter.  The inverse of the
+(dim <= ~1e3) overlap matrix itself is taken with NumPy plus one Newton-Schulz refinement step in
+extended precision, on the host, as the reference does with ``qode.math.precise_numpy_inverse`` (:165).
+"""
+import numpy
+
+from . import diagrammatic_expansion, XR_term
+from . import diagram_lists as D
+from .diagrams import S_diagrams, ST_diagrams, SU_diagrams, SV_diagrams
+from .precontract import precontract
+from .tensor import Contractor, DeviceStore, DeviceTensor, default_device
+from .util import struct, timer
+
+
+def precise_numpy_inverse(M):
+    M = numpy.asarray(M, dtype=numpy.float64)
+    X = numpy.linalg.inv(M)
+    ML, XL = M.astype(numpy.longdouble), X.astype(numpy.longdouble)
+    XL = XL + XL @ (numpy.eye(M.shape[0], dtype=numpy.longdouble) - ML @ XL)
+    return numpy.asarray(XL, dtype=numpy.float64)
+
+
+def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False, device=None):
+    if bra_det or ket_det:
+        raise NotImplementedError("bra_det / ket_det variants are not built yet (DESIGN.md 'next')")
+    diag_timer, precon_timer, matrix_timer = timer(), timer(), timer()
+    symm_ints, bior_ints, nuc_rep = ints
+    dev = device or default_device()
+    store, contractor = DeviceStore(dev), Contractor(dev)
+    contract_cache = precontract(dens, symm_ints.S, precon_timer, store=store, contractor=contractor)
+
+    def make(integrals, diagrams):
+        return diagrammatic_expansion.blocks(densities=dens, integrals=integrals, diagrams=diagrams,
+                                             contract_cache=contract_cache, timings=diag_timer, precon_timings=precon_timer)
+    S = symm_ints.S
+    S_blocks = make(S, S_diagrams)
+    ST_symm, SU_symm, SV_symm = make(struct(S=S, T=symm_ints.T), ST_diagrams), make(struct(S=S, U=symm_ints.U), SU_diagrams), make(struct(S=S, V=symm_ints.V), SV_diagrams)
+    ST_bior, SU_bior, SV_bior = make(struct(S=S, T=bior_ints.T), ST_diagrams), make(struct(S=S, U=bior_ints.U), SU_diagrams), make(struct(S=S, V=bior_ints.V), SV_diagrams)
+
+    all_dimer_charges = [(c0, c1) for c0 in monomer_charges[0] for c1 in monomer_charges[1]]
+
+    def monomers(ST, SU, SV):
+        H1 = []
+        for m in (0, 1):
+            M = None
+            for b, lst in ((ST, D.ST1), (SU, D.SU1), (SV, D.SV1)):
+                M = XR_term.monomer_matrix(b, {1: lst[0]}, m, monomer_charges[m], matrix_timer, device_result=True, into=M)
+            H1.append(M.host())
+        return H1
+
+    def dimer_sum(terms, into=None, scale=1.0):
+        """sum of dimer matrices, each term accumulated in place by its own GEMM epilogues"""
+        for op_blocks, active in terms:
+            into = XR_term.dimer_matrix(op_blocks, active, (0, 1), all_dimer_charges, matrix_timer, ordering="final",
+                                        device_result=True, into=into, scale=scale)
+        return into
+
+    if xr_order == 0:                                   # get_xr_result.py:86-132
+        H1 = monomers(ST_bior, SU_bior, SV_bior)
+        H2 = dimer_sum([(ST_bior, {2: D.ST2[0]}), (SU_bior, {2: D.SU2[0]}), (SV_bior, {2: D.SV2[0]})]).host()
+    elif xr_order == 1:                                 # get_xr_result.py:133-213
+        SV_diff = make(struct(S=S, V=bior_ints.V_diff), SV_diagrams)
+        H1 = monomers(ST_symm, SU_symm, SV_symm)
+        S2 = XR_term.dimer_matrix(S_blocks, {0: D.S0[0], 2: D.S2[1]}, (0, 1), all_dimer_charges, matrix_timer, ordering="final")
+        S2inv = precise_numpy_inverse(S2)
+        S2H2 = dimer_sum([(ST_symm, {1: D.ST1[0], 2: D.ST2[0]}), (SU_symm, {1: D.SU1[0], 2: D.SU2[0]}),
+                          (ST_bior, {2: D.ST2[1]}), (SU_bior, {2: D.SU2[1]}),
+                          (SV_diff, {1: D.SV1[0], 2: D.SV2[0]}), (SV_bior, {2: D.SV2[1]})])
+        # H2 = S2inv @ S2H2 - (monomer terms in the dimer basis): the subtraction is accumulated first, with
+        # scale -1, and the matrix product is then added on top by the GEMM epilogue
+        out = dimer_sum([(ST_symm, {1: D.ST1[0]}), (SU_symm, {1: D.SU1[0]}), (SV_symm, {1: D.SV1[0]})], scale=-1.0)
+        contractor.contract(store.get(S2inv), ["a", "k"], S2H2, ["k", "b"], ["a", "b"], out=out, accumulate=True)
+        H2 = out.host()
+    else:
+        raise NotImplementedError("xr order %r is not implemented" % (xr_order,))
+    return H1, H2

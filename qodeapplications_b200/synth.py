@@ -24,13 +24,14 @@ import numpy
 CONFIGS = {
     "toy":  dict(n_frag=2, n_orb=6,  n_states={0: 3,   +1: 2,   -1: 2}),
     "toy3": dict(n_frag=3, n_orb=5,  n_states={0: 2,   +1: 2,   -1: 2}),
+    "mid":  dict(n_frag=2, n_orb=8,  n_states={0: 5,   +1: 3,   -1: 4}),
     "cfg1": dict(n_frag=2, n_orb=18, n_states={0: 11,  +1: 4,   -1: 8}),
     "cfg2": dict(n_frag=2, n_orb=18, n_states={0: 11,  +1: 4,   -1: 8}),
     "cfg3": dict(n_frag=3, n_orb=18, n_states={0: 11,  +1: 4,   -1: 8}),
     "cfg4": dict(n_frag=4, n_orb=18, n_states={0: 96,  +1: 34,  -1: 70}),
     "cfg5": dict(n_frag=2, n_orb=48, n_states={0: 478, +1: 174, -1: 348}),
 }
-SEEDS = {"toy": 11, "toy3": 13, "cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}
+SEEDS = {"toy": 11, "toy3": 13, "mid": 17, "cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}
 N_ELEC_REF = 4
 
 OPS_ORDER0 = ("a", "c", "aa", "cc", "ca", "caa", "cca", "ccaa")

@@ -1,0 +1,127 @@
+"""TEST-ONLY stand-in for the device layer, so the HOST logic of the product (offset tables, sign
+folding, class bookkeeping, diagram planning) can be exercised by the CPU test-suite.
+
+It implements the semantics of the C ABI (include/xr_b200.h) on raw host pointers with NumPy and is
+injected by the tests in place of qodeapplications_b200.device.Device.  It lives under tests/ and is
+never imported by the product: the product has no CPU path.  The CUDA kernels themselves are checked
+against the oracle by the `-m gpu` tests.
+"""
+import ctypes
+import numpy
+import torch
+
+
+def _view(ptr, count, dtype=numpy.float64):
+    if hasattr(ptr, "data_ptr"):
+        ptr = ptr.data_ptr()
+    if count == 0:
+        return numpy.zeros(0, dtype=dtype)
+    ctype = ctypes.c_double if dtype == numpy.float64 else ctypes.c_int64
+    return numpy.ctypeslib.as_array((ctype * int(count)).from_address(int(ptr)))
+
+
+class FakeContext(object):
+    def __init__(self):
+        self.launches = 0
+
+    def launch_count(self):
+        return self.launches
+
+    def sync(self):
+        pass
+
+    def gemm_scatter(self, M, N, K, alpha, A, lda, B, ldb, C, offM=None, ldc=0, offN=None, accumulate=False):
+        self.launches += 1
+        if M <= 0 or N <= 0:
+            return
+        a = _view(A, (M - 1) * lda + K).copy() if K else numpy.zeros(0)
+        b = _view(B, (N - 1) * ldb + K).copy() if K else numpy.zeros(0)
+        Am = numpy.lib.stride_tricks.as_strided(a, (M, K), (8 * lda, 8)) if K else numpy.zeros((M, 0))
+        Bm = numpy.lib.stride_tricks.as_strided(b, (N, K), (8 * ldb, 8)) if K else numpy.zeros((N, 0))
+        om = _view(offM, M, numpy.int64) if offM is not None else numpy.arange(M, dtype=numpy.int64) * ldc
+        on = _view(offN, N, numpy.int64) if offN is not None else numpy.arange(N, dtype=numpy.int64)
+        at = (om[:, None] + on[None, :]).reshape(-1)
+        c = _view(C, int(at.max()) + 1)
+        val = (alpha * (Am @ Bm.T)).reshape(-1)
+        if accumulate:
+            numpy.add.at(c, at, val)
+        else:
+            c[at] = val
+
+    def copy2d_scaled(self, dst, dst_ld, src, src_ld, rows, cols, alpha=1.0):
+        self.launches += 1
+        if rows <= 0 or cols <= 0:
+            return
+        s = _view(src, (rows - 1) * src_ld + cols)
+        d = _view(dst, (rows - 1) * dst_ld + cols)
+        S = numpy.lib.stride_tricks.as_strided(s, (rows, cols), (8 * src_ld, 8))
+        D = numpy.lib.stride_tricks.as_strided(d, (rows, cols), (8 * dst_ld, 8))
+        D[...] = alpha * S
+
+    def scatter_const(self, C, idx, count, value, accumulate=False):
+        self.launches += 1
+        if count <= 0:
+            return
+        at = _view(idx, count, numpy.int64)
+        c = _view(C, int(at.max()) + 1)
+        if accumulate:
+            numpy.add.at(c, at, value)
+        else:
+            c[at] = value
+
+    def permute_copy(self, dst, src, shape, src_strides, alpha=1.0):
+        self.launches += 1
+        total = int(numpy.prod(shape))
+        if total == 0:
+            return
+        span = 1 + sum((e - 1) * abs(s) for e, s in zip(shape, src_strides))
+        s = _view(src, span)
+        S = numpy.lib.stride_tricks.as_strided(s, tuple(shape), tuple(8 * x for x in src_strides))
+        _view(dst, total)[...] = (alpha * S).reshape(-1)
+
+    def trimer_stream(self, n, Pa, Pb, Pc, alpha, W, ldw, beta, ldbeta, gamma, ldgamma, a_begin, a_end, mode,
+                      moments=None, C=None, offA=None, offB=None, offC=None):
+        self.launches += 1
+        if a_begin == a_end or Pb <= 0 or Pc <= 0:
+            return
+        w = numpy.lib.stride_tricks.as_strided(_view(W, (Pa - 1) * ldw + n * n), (Pa, n * n), (8 * ldw, 8))[a_begin:a_end]
+        b = numpy.lib.stride_tricks.as_strided(_view(beta, (Pb - 1) * ldbeta + n), (Pb, n), (8 * ldbeta, 8))
+        g = numpy.lib.stride_tricks.as_strided(_view(gamma, (Pc - 1) * ldgamma + n), (Pc, n), (8 * ldgamma, 8))
+        T = alpha * numpy.einsum("ars,br,cs->abc", w.reshape(-1, n, n), b, g, optimize=True)
+        if mode == 0:
+            m = _view(moments, 2)
+            m[0] += T.sum()
+            m[1] += (T * T).sum()
+        else:
+            oa = _view(offA, Pa, numpy.int64)[a_begin:a_end]
+            ob = _view(offB, Pb, numpy.int64)
+            oc = _view(offC, Pc, numpy.int64)
+            at = (oa[:, None, None] + ob[None, :, None] + oc[None, None, :]).reshape(-1)
+            _view(C, int(at.max()) + 1)[at] = T.reshape(-1)
+
+
+class FakeDevice(object):
+    """same surface as qodeapplications_b200.device.Device, on CPU torch tensors"""
+    def __init__(self, index=0):
+        self.index = index
+        self.torch_device = torch.device("cpu")
+        self.ctx = FakeContext()
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def empty(self, shape, dtype=torch.float64):
+        return torch.zeros(shape, dtype=dtype)
+
+    def zeros(self, shape, dtype=torch.float64):
+        return torch.zeros(shape, dtype=dtype)
+
+    def upload(self, array, dtype=numpy.float64):
+        array = numpy.array(array, dtype=dtype, order="C", copy=True)
+        self.h2d_bytes += array.nbytes
+        return torch.from_numpy(array)
+
+    def download(self, tensor):
+        self.d2h_bytes += tensor.numel() * tensor.element_size()
+        return tensor.numpy().copy()
+
+    def sync(self):
+        pass

@@ -1,0 +1,126 @@
+"""GPU parity tests for the hermitian-XRCC path: diagram blocks, XR_term matrices and get_xr_H computed
+by libxr_b200.so against the reference's golden vectors (toy) and the NumPy oracle (larger shapes).
+Tolerance: 1e-10 relative to the largest element of the block/matrix (BASELINE.json north_star)."""
+import os
+import numpy
+import pytest
+
+from qodeapplications_b200 import synth
+from oracle import hermitian_oracle as ho
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _close(a, b, tol=1e-10):
+    a, b = numpy.asarray(a), numpy.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(numpy.abs(b).max(), 1e-300)
+    assert numpy.abs(a - b).max() <= tol * scale, (numpy.abs(a - b).max(), scale)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from qodeapplications_b200.device import Device
+    return Device(0)
+
+
+def _blocks(system, dev, family, which="symm"):
+    from qodeapplications_b200.hermitian import diagrammatic_expansion
+    from qodeapplications_b200.hermitian.diagrams import S_diagrams, ST_diagrams, SU_diagrams, SV_diagrams
+    from qodeapplications_b200.hermitian.precontract import precontract
+    from qodeapplications_b200.hermitian.tensor import Contractor, DeviceStore
+    from qodeapplications_b200.hermitian.util import struct, timer
+    ints_set, dens = system[which], system["densities"][:2]
+    S = system["symm"].S
+    store, contractor = DeviceStore(dev), Contractor(dev)
+    cache = precontract(dens, S, timer(), store=store, contractor=contractor)
+    ints, diagrams = {"S": (S, S_diagrams), "ST": (struct(S=S, T=ints_set.T), ST_diagrams),
+                      "SU": (struct(S=S, U=ints_set.U), SU_diagrams), "SV": (struct(S=S, V=ints_set.V), SV_diagrams)}[family]
+    return diagrammatic_expansion.blocks(densities=dens, integrals=ints, diagrams=diagrams, contract_cache=cache,
+                                         timings=timer(), precon_timings=timer())
+
+
+def test_every_diagram_block_matches_reference_golden(dev):
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_blocks.npz"))
+    toy = synth.make_system("toy", ops=synth.OPS_ORDER1, with_bior=True)
+    family_of = lambda label: "S" if label == "s01" else "S" + label.replace("s01", "")[0].upper()
+    cache, count = {}, 0
+    for key in g.files:
+        if key == "input_sha256":
+            continue
+        parts = key.split("|")
+        label = parts[0]
+        fam = family_of(label)
+        if fam not in cache:
+            cache[fam] = _blocks(toy, dev, fam)
+        if len(parts) == 3:
+            ci, cj = (int(x) for x in parts[2].split(","))
+            _close(cache[fam][(int(parts[1]),)][((ci, cj),)][label], g[key])
+        else:
+            ci0, ci1, cj0, cj1 = (int(x) for x in parts[1].split(","))
+            _close(cache[fam][(0, 1)][((ci0, cj0), (ci1, cj1))][label], g[key])
+        count += 1
+    assert count == 221
+
+
+@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1)])
+def test_get_xr_H_matches_reference_golden(dev, order, ops):
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_order%d.npz" % order))
+    system = synth.make_system("toy", ops=ops, with_bior=True)
+    charges = system["charges"]
+    H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), system["densities"][:2], order, [charges, charges], device=dev)
+    _close(H1[0], g["H1_0"])
+    _close(H1[1], g["H1_1"])
+    _close(H2, g["H2"], 1e-9 if order else 1e-10)
+
+
+def test_cfg1_order0_against_oracle(dev):
+    """Be2 / 6-31G shapes (n = 18, N = 11/4/8): get_xr_H(order 0) against the NumPy oracle"""
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    system = synth.make_system("cfg1", ops=synth.OPS_ORDER0, with_bior=True)
+    charges = system["charges"]
+    args = (system["densities"][:2], 0, [charges, charges])
+    H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), *args, device=dev)
+    R1, R2 = ho.get_xr_H(system["symm"], system["bior"], *args)
+    _close(H1[0], R1[0])
+    _close(H1[1], R1[1])
+    _close(H2, R2)
+
+
+def test_mid_order1_against_oracle(dev):
+    """n = 8, N = 5/3/4: get_xr_H(order 1) (rank-5 densities, S2 inverse) against the NumPy oracle"""
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    system = synth.make_system("mid", ops=synth.OPS_ORDER1, with_bior=True)
+    charges = system["charges"]
+    args = (system["densities"][:2], 1, [charges, charges])
+    H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), *args, device=dev)
+    R1, R2 = ho.get_xr_H(system["symm"], system["bior"], *args)
+    _close(H1[0], R1[0])
+    _close(H2, R2, 1e-9)
+
+
+def test_dimer_matrix_blocked_and_final_orderings(dev):
+    from qodeapplications_b200.hermitian import XR_term
+    from qodeapplications_b200.hermitian.util import timer
+    toy = synth.make_system("toy", ops=synth.OPS_ORDER1, with_bior=True)
+    blk = _blocks(toy, dev, "SV")
+    charges = [(a, b) for a in toy["charges"] for b in toy["charges"]]
+    active = {1: ["v0000"], 2: ["v0101", "v0001", "v0100", "v0011", "s01v0101"]}
+    symm = toy["symm"]
+    ref = ho.dimer_matrix(toy["densities"], ho.integrals(symm.S, V=symm.V), active, charges)
+    _close(XR_term.dimer_matrix(blk, active, (0, 1), charges, timer()), ref)
+    final = XR_term.dimer_matrix(blk, active, (0, 1), charges, timer(), ordering="final")
+    _close(final, ho.reorder(ref, toy["densities"], [toy["charges"], toy["charges"]]))
+
+
+def test_permute_copy(dev):
+    rng = numpy.random.default_rng(0)
+    a = rng.standard_normal((3, 4, 5, 6))
+    dA = dev.upload(a)
+    out = dev.empty((6, 4, 3, 5))
+    strides = [5 * 6 * 4, 5 * 6, 6, 1]            # element strides of a's axes 0..3
+    order = [3, 1, 0, 2]
+    dev.ctx.permute_copy(out, dA, [a.shape[k] for k in order], [strides[k] for k in order], -2.0)
+    assert numpy.array_equal(dev.download(out), -2.0 * a.transpose(order))

@@ -1,0 +1,123 @@
+"""Host-side orchestration of the product (class bookkeeping, sign folding, offset tables, diagram
+planning) run on the TEST-ONLY NumPy device stand-in (tests/fake_xr.py) and compared with the vectors
+the reference produced.  The CUDA kernels are not involved here; they are checked by the -m gpu tests."""
+import itertools
+import os
+import numpy
+import pytest
+
+from qodeapplications_b200 import synth
+from fake_xr import FakeDevice
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _close(a, b, tol=1e-10):
+    a, b = numpy.asarray(a), numpy.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(numpy.abs(b).max(), 1e-300)
+    assert numpy.abs(a - b).max() <= tol * scale, (numpy.abs(a - b).max(), scale)
+
+
+@pytest.mark.parametrize("name", ["toy", "toy3"])
+def test_general_blocks_host_logic(name):
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    g = numpy.load(os.path.join(GOLDEN, "general_%s.npz" % name))
+    system = synth.make_system(name)
+    eng = build_matrix_elements(system["fragments"], system["symm"], system["nuc"], device=FakeDevice())
+    F = system["n_frag"]
+    for m in range(F):
+        _close(eng.H1(m), g["H1_%d" % m])
+    for m1, m2 in itertools.combinations(range(F), 2):
+        _close(eng.H2(m1, m2), g["H2_%d%d" % (m1, m2)])
+    for ms in itertools.combinations(range(F), 3):
+        key = "H3_%d%d%d" % ms
+        ref = numpy.zeros(tuple(g[key + "_shape"]))
+        ref[g[key + "_rows"], g[key + "_cols"]] = g[key + "_vals"]
+        _close(eng.H3(*ms), ref)
+        s, q = eng.H3_moments(*ms)
+        assert abs(q - (ref ** 2).sum()) <= 1e-10 * (ref ** 2).sum()
+        parts = [eng.H3_moments(*ms, shard=(r, 2)) for r in range(2)]
+        assert abs(parts[0][1] + parts[1][1] - q) <= 1e-10 * q
+
+
+def test_general_bra_slabs_host_logic():
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    system = synth.make_system("toy")
+    dev = FakeDevice()
+    eng = build_matrix_elements(system["fragments"], system["symm"], system["nuc"], device=dev)
+    full = eng.H2(0, 1)
+    dim1 = len(system["fragments"][0].state_indices)
+    parts = [dev.download(eng.H2_device(0, 1, bra_range=r)) for r in ((0, 3), (3, 4), (4, dim1))]
+    _close(numpy.concatenate(parts, axis=0), full, 1e-13)    # (BLAS rounding differs with the slab size; the GPU test asks for equality)
+
+
+@pytest.fixture(scope="module")
+def toy1():
+    return synth.make_system("toy", ops=synth.OPS_ORDER1, with_bior=True)
+
+
+def _hermitian_blocks(system, dev, family):
+    from qodeapplications_b200.hermitian import diagrammatic_expansion
+    from qodeapplications_b200.hermitian.diagrams import S_diagrams, ST_diagrams, SU_diagrams, SV_diagrams
+    from qodeapplications_b200.hermitian.precontract import precontract
+    from qodeapplications_b200.hermitian.tensor import Contractor, DeviceStore
+    from qodeapplications_b200.hermitian.util import struct, timer
+    symm, dens = system["symm"], system["densities"][:2]
+    store, contractor = DeviceStore(dev), Contractor(dev)
+    cache = precontract(dens, symm.S, timer(), store=store, contractor=contractor)
+    ints, diagrams = {"S": (symm.S, S_diagrams), "ST": (struct(S=symm.S, T=symm.T), ST_diagrams),
+                      "SU": (struct(S=symm.S, U=symm.U), SU_diagrams), "SV": (struct(S=symm.S, V=symm.V), SV_diagrams)}[family]
+    return diagrammatic_expansion.blocks(densities=dens, integrals=ints, diagrams=diagrams, contract_cache=cache,
+                                         timings=timer(), precon_timings=timer())
+
+
+def test_hermitian_every_diagram_block_host_logic(toy1):
+    """blocks[subsystem][charges][label] -- the reference's own access pattern -- for all 32 diagrams"""
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_blocks.npz"))
+    dev = FakeDevice()
+    family_of = lambda label: "S" if label == "s01" else "S" + label.replace("s01", "")[0].upper()
+    cache = {}
+    for key in g.files:
+        if key == "input_sha256":
+            continue
+        parts = key.split("|")
+        label = parts[0]
+        fam = family_of(label)
+        if fam not in cache:
+            cache[fam] = _hermitian_blocks(toy1, dev, fam)
+        blk = cache[fam]
+        if len(parts) == 3:
+            m = int(parts[1])
+            ci, cj = (int(x) for x in parts[2].split(","))
+            _close(blk[(m,)][((ci, cj),)][label], g[key])
+        else:
+            ci0, ci1, cj0, cj1 = (int(x) for x in parts[1].split(","))
+            _close(blk[(0, 1)][((ci0, cj0), (ci1, cj1))][label], g[key])
+
+
+@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1)])
+def test_hermitian_get_xr_H_host_logic(order, ops):
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_order%d.npz" % order))
+    system = synth.make_system("toy", ops=ops, with_bior=True)
+    charges = system["charges"]
+    H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), system["densities"][:2], order, [charges, charges],
+                      device=FakeDevice())
+    _close(H1[0], g["H1_0"])
+    _close(H1[1], g["H1_1"])
+    _close(H2, g["H2"], 1e-9 if order else 1e-10)
+
+
+def test_hermitian_dimer_matrix_blocked_ordering(toy1):
+    """XR_term.dimer_matrix keeps the reference's charge-blocked ordering by default"""
+    from qodeapplications_b200.hermitian import XR_term
+    from qodeapplications_b200.hermitian.util import timer
+    from oracle import hermitian_oracle as ho
+    dev = FakeDevice()
+    blk = _hermitian_blocks(toy1, dev, "SV")
+    charges = [(a, b) for a in toy1["charges"] for b in toy1["charges"]]
+    got = XR_term.dimer_matrix(blk, {1: ["v0000"], 2: ["v0101", "v0001", "v0100", "v0011"]}, (0, 1), charges, timer())
+    symm = toy1["symm"]
+    ref = ho.dimer_matrix(toy1["densities"], ho.integrals(symm.S, V=symm.V), {1: ["v0000"], 2: ["v0101", "v0001", "v0100", "v0011"]}, charges)
+    _close(got, ref)
