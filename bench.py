@@ -207,32 +207,12 @@ def run_xr(args):
     counts = eng.element_counts(dimers, trimers)
     dims = [len(f.state_indices) for f in system["fragments"]]
 
-    # bra-state slabs of fragment m1 for the dimers (equal sizes so the all-gather is one collective)
+    from qodeapplications_b200.general.distributed import sharded_build, slab_bounds
+    build = sharded_build(eng, dimers, trimers, rank, world)
+    results, H2, step = build.H1, build.H2, build.step
+
     def slab(m1):
-        per = -(-dims[m1] // world)
-        return min(rank * per, dims[m1]), min((rank + 1) * per, dims[m1]), per
-
-    H2 = {}
-    for m1, m2 in dimers:
-        lo, hi, per = slab(m1)
-        D = dims[m1] * dims[m2]
-        H2[(m1, m2)] = dev.empty((per * world * dims[m2], D))      # padded to world*per bra states; rows >= dim1*dim2 unused
-
-    results = {}
-
-    def step(gather=True):
-        for m in range(F):
-            results[("H1", m)] = eng.H1_device(m)
-        for m1, m2 in dimers:
-            lo, hi, per = slab(m1)
-            full = H2[(m1, m2)]
-            mine = full[rank * per * dims[m2]:(rank * per + (hi - lo)) * dims[m2]]
-            eng.H2_device(m1, m2, bra_range=(lo, hi) if world > 1 else None, out=mine)
-            if world > 1 and gather:
-                chunk = full[rank * per * dims[m2]:(rank + 1) * per * dims[m2]]
-                dist.all_gather_into_tensor(full, chunk)
-        for ms in trimers:
-            results[("H3", ms)] = eng.H3_moments_device(*ms, shard=(rank, world))
+        return slab_bounds(dims[m1], rank, world)
 
     def barrier():
         if world > 1:
@@ -271,12 +251,7 @@ def run_xr(args):
     tri_ms, tri_flops, tri_count = (sum(x[i] for x in tri) for i in range(3)) if tri else (0.0, 0.0, 0)
 
     # trimer moments summed over ranks (the only "exchange" the trimer path has: 24 doubles per trimer)
-    moments = {}
-    for ms_ in trimers:
-        t = results[("H3", ms_)].clone()
-        if world > 1:
-            dist.all_reduce(t)
-        moments[ms_] = t.sum(dim=0).tolist()
+    moments = build.reduced_moments()
 
     # ---- end-to-end: pinned host inputs -> upload -> build -> results read back to pinned host
     e2e = None
@@ -293,16 +268,15 @@ def run_xr(args):
             step()
             d2h = 0
             for m in range(F):
-                d2h += results[("H1", m)].numel() * 8
-                results[("H1", m)].cpu()
+                d2h += build.H1[m].numel() * 8
+                build.H1[m].cpu()
             for m1, m2 in dimers:
-                lo, hi, per = slab(m1)
-                mine = H2[(m1, m2)][rank * per * dims[m2]:(rank * per + (hi - lo)) * dims[m2]]
+                mine = build.my_rows(m1, m2)
                 host_out[tuple(mine.shape)].copy_(mine, non_blocking=True)
                 d2h += mine.numel() * 8
             for ms_ in trimers:
-                d2h += results[("H3", ms_)].numel() * 8
-                results[("H3", ms_)].cpu()
+                d2h += build.H3_moments[ms_].numel() * 8
+                build.H3_moments[ms_].cpu()
             return dev.h2d_bytes, d2h
         barrier()
         e2e_steps = 1

@@ -1,0 +1,67 @@
+"""One-process-per-GPU sharding of the general-XRCC H build.
+
+* dimers: rank r builds the rows of H2[m1][m2] whose fragment-m1 bra state lies in its slab (equal
+  slabs of ceil(dim1/world) states, so the assemble step is ONE all_gather_into_tensor per dimer,
+  in place: every rank writes its slab directly into its slice of the full matrix);
+* trimers: rank r streams its slab of every class's leading pair index; the only exchange is the sum
+  of 24 doubles per trimer (moments).  No data-path collective exists anywhere else.
+
+torch.distributed is plumbing here (NCCL on GPUs, gloo in the CPU tests); the arithmetic is in
+libxr_b200.so.
+"""
+import torch
+import torch.distributed as dist
+
+
+def slab_bounds(dim, rank, world):
+    """(lo, hi, per): bra states [lo, hi) of this rank, per = padded slab size shared by all ranks"""
+    per = -(-dim // world)
+    return min(rank * per, dim), min((rank + 1) * per, dim), per
+
+
+class sharded_build(object):
+    """Holds the output buffers of a (possibly multi-rank) build and runs one build step."""
+    def __init__(self, engine, dimers, trimers, rank=0, world=1, group=None):
+        self.eng, self.dimers, self.trimers = engine, list(dimers), list(trimers)
+        self.rank, self.world, self.group = rank, world, group
+        self.dims = [engine._frag(m).dim for m in range(len(engine._supersystem))]
+        self.H1, self.H2, self.H3_moments = {}, {}, {}
+        dev = engine.dev
+        for m1, m2 in self.dimers:
+            lo, hi, per = slab_bounds(self.dims[m1], rank, world)
+            # rows padded to world*per bra states so that all slabs have equal size; rows >= dim1*dim2 are unused
+            self.H2[(m1, m2)] = dev.empty((per * world * self.dims[m2], self.dims[m1] * self.dims[m2]))
+
+    def my_rows(self, m1, m2):
+        """view of this rank's slab of H2[m1][m2] (only the rows that exist)"""
+        lo, hi, per = slab_bounds(self.dims[m1], self.rank, self.world)
+        d2 = self.dims[m2]
+        return self.H2[(m1, m2)][self.rank * per * d2:(self.rank * per + (hi - lo)) * d2]
+
+    def full(self, m1, m2):
+        """the assembled H2[m1][m2] (valid on every rank after step(gather=True))"""
+        return self.H2[(m1, m2)][:self.dims[m1] * self.dims[m2]]
+
+    def step(self, gather=True):
+        eng, rank, world = self.eng, self.rank, self.world
+        for m in range(len(self.dims)):
+            self.H1[m] = eng.H1_device(m)
+        for m1, m2 in self.dimers:
+            lo, hi, per = slab_bounds(self.dims[m1], rank, world)
+            eng.H2_device(m1, m2, bra_range=(lo, hi) if world > 1 else None, out=self.my_rows(m1, m2))
+            if world > 1 and gather:
+                d2 = self.dims[m2]
+                full = self.H2[(m1, m2)]
+                dist.all_gather_into_tensor(full, full[rank * per * d2:(rank + 1) * per * d2], group=self.group)
+        for ms in self.trimers:
+            self.H3_moments[ms] = eng.H3_moments_device(*ms, shard=(rank, world))
+
+    def reduced_moments(self):
+        """{trimer: [sum, sum of squares]} summed over classes and ranks"""
+        out = {}
+        for ms in self.trimers:
+            t = self.H3_moments[ms].clone()
+            if self.world > 1:
+                dist.all_reduce(t, group=self.group)
+            out[ms] = [float(x) for x in self.eng.dev.download(t).sum(axis=0)]
+        return out

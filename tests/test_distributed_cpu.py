@@ -1,0 +1,57 @@
+"""world_size-2 run of the sharded build over gloo on CPU (host logic of the multi-GPU path: bra-state
+slabs, in-place all-gather of H2, summed trimer moments).  Uses the TEST-ONLY NumPy device stand-in."""
+import itertools
+import os
+import socket
+import sys
+import numpy
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fake_xr import FakeDevice
+    from qodeapplications_b200 import synth
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    from qodeapplications_b200.general.distributed import sharded_build
+    system = synth.make_system("toy3")
+    eng = build_matrix_elements(system["fragments"], system["symm"], system["nuc"], device=FakeDevice())
+    dimers = list(itertools.combinations(range(3), 2))
+    build = sharded_build(eng, dimers, [(0, 1, 2)], rank, world)
+    build.step(gather=True)
+    moments = build.reduced_moments()
+    payload = {"H2_%d%d" % k: build.full(*k).numpy() for k in dimers}
+    payload["moments"] = numpy.array(moments[(0, 1, 2)])
+    numpy.savez(os.path.join(out_dir, "rank%d.npz" % rank), **payload)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_build_matches_reference(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g = numpy.load(os.path.join(GOLDEN, "general_toy3.npz"))
+    ref3 = numpy.zeros(tuple(g["H3_012_shape"]))
+    ref3[g["H3_012_rows"], g["H3_012_cols"]] = g["H3_012_vals"]
+    for rank in range(world):
+        out = numpy.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        for m1, m2 in itertools.combinations(range(3), 2):          # every rank holds the assembled H2
+            ref = g["H2_%d%d" % (m1, m2)]
+            assert numpy.abs(out["H2_%d%d" % (m1, m2)] - ref).max() <= 1e-10 * numpy.abs(ref).max()
+        assert abs(out["moments"][1] - (ref3 ** 2).sum()) <= 1e-10 * (ref3 ** 2).sum()
+        assert abs(out["moments"][0] - ref3.sum()) <= 1e-9 * numpy.abs(ref3).sum()
