@@ -132,6 +132,18 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_nt_scatter_kern
         int64_t om = p.offM ? p.offM[row] : row * p.ldc;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
+            // the lane's two columns are adjacent in C more often than not (runs of ket states): one 16-byte store
+            double* dst0 = p.C + om + on[j][0];
+            if (on[j][0] >= 0 && on[j][1] == on[j][0] + 1 && (reinterpret_cast<uintptr_t>(dst0) & 15) == 0) {
+                double2 v = make_double2(p.alpha * acc[i][j][0], p.alpha * acc[i][j][1]);
+                if (p.accumulate) {
+                    const double2 old = *reinterpret_cast<double2*>(dst0);
+                    v.x += old.x;
+                    v.y += old.y;
+                }
+                *reinterpret_cast<double2*>(dst0) = v;
+                continue;
+            }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 if (on[j][e] < 0) continue;

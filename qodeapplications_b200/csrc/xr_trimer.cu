@@ -33,6 +33,7 @@ struct TrimerParams {
     int64_t ldw;
     const double* betaP;    // [Pb][KP], zero padded in k
     const double* gammaP;   // [c_tiles*CT][GS], zero padded in k and rows
+    const double* gammaT;   // [c_tiles*CT][2]: the TAIL columns gamma[c][4*KS .. 4*KS+1] again, compact (conflict-free tail loads)
     int64_t a_begin, a_end;
     int mode;
     double* partials;       // [grid][2]
@@ -50,7 +51,8 @@ struct TrimerCfg {
     static constexpr int GS = (KP % 16 == 4 || KP % 16 == 12) ? KP : KP + 4;       // conflict-free fragment stride
     static constexpr bool AREG = KS <= 5;                                         // A fragments live in registers
     static constexpr int SLOTS = KS <= 5 ? 4 : 2;                                 // gamma ring depth (shared memory bound)
-    static constexpr size_t SMEM = (size_t)(ROWS + SLOTS * CT) * GS * sizeof(double) + 2 * SLOTS * sizeof(uint64_t) + 64;
+    static constexpr size_t SMEM = (size_t)(ROWS + SLOTS * CT) * GS * sizeof(double) + (size_t)SLOTS * CT * 2 * sizeof(double) +
+                                   2 * SLOTS * sizeof(uint64_t) + 64;
 };
 
 __device__ __forceinline__ void consumer_barrier() {   // named barrier 1: the 8 consumer warps only
@@ -68,13 +70,15 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
     constexpr int MI = 4, NJ = 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* Gs = reinterpret_cast<double*>(smem_raw);                  // [SLOTS][CT][GS]  (bulk-copy destinations: 16B aligned)
-    double* Xs = Gs + SLOTS * CT * GS;                                  // [ROWS][GS]
+    double* Gt = Gs + SLOTS * CT * GS;                                  // [SLOTS][CT][2]   tail columns, compact
+    double* Xs = Gt + SLOTS * CT * 2;                                   // [ROWS][GS]
     uint64_t* full = reinterpret_cast<uint64_t*>(Xs + ROWS * GS);       // [SLOTS]
     uint64_t* empty = full + SLOTS;                                     // [SLOTS]
     __shared__ double red[2][CONSUMER_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr uint32_t TILE_BYTES = CT * GS * sizeof(double);
+    constexpr uint32_t TAIL_BYTES = TAIL ? CT * 2 * sizeof(double) : 0;
 
     if (tid == 0) {
         for (int s = 0; s < SLOTS; ++s) {
@@ -91,15 +95,16 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
 
     if (warp >= CONSUMER_WARPS) {
         // -------------------------------------------------- producer warpgroup (one lane works)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");     // hand registers to the consumers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");     // hand registers to the consumers
         if (warp == CONSUMER_WARPS && lane == 0) {
             int ct = 0;
             for (int64_t q = 0; q < total_tiles; ++q) {
                 const int slot = (int)(q % SLOTS);
                 const uint32_t round = (uint32_t)(q / SLOTS);
                 mbar_wait(&empty[slot], (round & 1) ^ 1);     // passes at once on the first lap
-                mbar_expect_tx(&full[slot], TILE_BYTES);
+                mbar_expect_tx(&full[slot], TILE_BYTES + TAIL_BYTES);
                 bulk_copy_g2s(Gs + (size_t)slot * CT * GS, p.gammaP + (size_t)ct * CT * GS, TILE_BYTES, &full[slot]);
+                if (TAIL) bulk_copy_g2s(Gt + (size_t)slot * CT * 2, p.gammaT + (size_t)ct * CT * 2, TAIL_BYTES, &full[slot]);
                 if (++ct == p.c_tiles) ct = 0;
             }
         }
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
     }
 
     // ---------------------------------------------------------------------- consumer warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
     double s1p[NJ], s2p[NJ];     // NJ independent chains each: the moment epilogue must not be one serial FP64 dependency
@@ -176,25 +181,19 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
                 }
             }
             if (TAIL) {
-                // leftover k (n - 4*KS <= 2) on the accumulator layout: lane owns rows 8i+g, columns 8j+2t+{0,1}
-                const double* gt = gtile + (64 * wn + 2 * t) * GS + 4 * KS;
+                // leftover k (n - 4*KS <= 2) on the accumulator layout: lane owns rows 8i+g, columns 8j+2t+{0,1}.
+                // The tail columns come from the compact [c][2] copy: a quad's four 32-byte reads cover 128
+                // contiguous bytes (no bank conflicts; the strided [c][GS] rows would give 2-way conflicts).
+                const double2* gt = reinterpret_cast<const double2*>(Gt + (size_t)slot * CT * 2) + 64 * wn + 2 * t;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        double bt[2];
-                        if (TAIL == 2) {
-                            const double2 v = *reinterpret_cast<const double2*>(gt + (8 * j + e) * GS);
-                            bt[0] = v.x;
-                            bt[1] = v.y;
-                        } else {
-                            bt[0] = gt[(8 * j + e) * GS];
-                            bt[1] = 0.0;
-                        }
+                        const double2 v = gt[8 * j + e];
 #pragma unroll
                         for (int i = 0; i < MI; ++i) {
-#pragma unroll
-                            for (int tt = 0; tt < TAIL; ++tt) acc[i][j][e] = fma(atail[i][tt], bt[tt], acc[i][j][e]);
+                            acc[i][j][e] = fma(atail[i][0], v.x, acc[i][j][e]);
+                            if (TAIL == 2) acc[i][j][e] = fma(atail[i][TAIL - 1], v.y, acc[i][j][e]);
                         }
                     }
                 }
@@ -289,20 +288,28 @@ int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbet
     const size_t beta_bytes = (size_t)p.Pb * Cfg::KP * sizeof(double);
     const size_t gamma_bytes = (size_t)p.c_tiles * CT * Cfg::GS * sizeof(double);
     const size_t beta_off = 0, gamma_off = (beta_bytes + 255) / 256 * 256;
-    const size_t part_off = gamma_off + (gamma_bytes + 255) / 256 * 256;
+    const size_t tail_bytes = (size_t)p.c_tiles * CT * 2 * sizeof(double);
+    const size_t tail_off = gamma_off + (gamma_bytes + 255) / 256 * 256;
+    const size_t part_off = tail_off + (tail_bytes + 255) / 256 * 256;
     int rc = xr_ensure_scratch(ctx, part_off + (size_t)grid * 2 * sizeof(double) + 256);
     if (rc != XR_OK) return rc;
     char* base = static_cast<char*>(ctx->scratch);
     double* betaP = reinterpret_cast<double*>(base + beta_off);
     double* gammaP = reinterpret_cast<double*>(base + gamma_off);
+    double* gammaT = reinterpret_cast<double*>(base + tail_off);
     double* partials = reinterpret_cast<double*>(base + part_off);
     XR_CUDA(cudaMemsetAsync(base, 0, part_off, ctx->stream));
     rc = xr_copy2d_scaled(ctx, betaP, Cfg::KP, beta, ldbeta, p.Pb, p.n, 1.0);
     if (rc != XR_OK) return rc;
     rc = xr_copy2d_scaled(ctx, gammaP, Cfg::GS, gamma, ldgamma, p.Pc, p.n, 1.0);
     if (rc != XR_OK) return rc;
+    if (TAIL) {
+        rc = xr_copy2d_scaled(ctx, gammaT, 2, gamma + 4 * KS, ldgamma, p.Pc, TAIL, 1.0);
+        if (rc != XR_OK) return rc;
+    }
     p.betaP = betaP;
     p.gammaP = gammaP;
+    p.gammaT = gammaT;
     p.partials = partials;
 
     auto kernel = trimer_stream_kernel<KS, TAIL>;
