@@ -1,4 +1,4 @@
-"""CPU oracle for the hermitian-XRCC Hamiltonian build (orders 0 and 1).  TEST INFRASTRUCTURE: only
+"""CPU oracle for the hermitian-XRCC Hamiltonian build (S-orders 0, 1 and 2).  TEST INFRASTRUCTURE: only
 tests/, smoke() and bench.py's CPU legs may import this.
 
 Third-party dependency of the reference on this path: ``qode`` (github adutoi/Qode, version
@@ -13,8 +13,8 @@ diagram function carries as a comment (e.g. hermitian-XRCC/diagrams/SV_2mer_0.py
   * get_xr_result.py:86-213, 300-353 -- which families enter at xr_order 0 / 1, S2inv, final reorder.
 
 Parity status: PINNED against the reference itself: tests/golden/hermitian_toy_order{0,1}.npz (H1, H2 of
-the reference's own get_xr_H, run through oracle/qode_shim by oracle/gen_golden.py) and
-tests/golden/hermitian_toy_blocks.npz (every diagram block of orders 0-1 for every charge combination).
+the reference's own get_xr_H, run through oracle/qode_shim by oracle/gen_golden.py; also order 2) and
+tests/golden/hermitian_toy_blocks{,2}.npz (every diagram block of orders 0-2 for every charge combination).
 """
 import itertools
 import numpy
@@ -49,6 +49,34 @@ for _n in "01":      # SU_2mer_1.py: the ST forms with t## -> u<n>_##
     TWO_FRAGMENT["s01u%s11" % _n] = (1, 1, [("c0", "ijt"), ("caa1", "klpuq"), ("s01", "tu"), ("u%s_11" % _n, "pq")])
     TWO_FRAGMENT["s01u%s01" % _n] = (1, None, [("cc0", "ijpt"), ("aa1", "kluq"), ("s01", "tu"), ("u%s_01" % _n, "pq")])
 
+# ---- S-order 2 (S_2mer_2.py, ST_2mer_2.py, SU_2mer_2.py, SV_2mer_2.py: the commented un-precontracted forms) ----
+_H = 0.5
+TWO_FRAGMENT.update({
+    "s01s10":    (-1, None, [("ca0", "ijps"), ("ca1", "klrq"), ("s01", "pq"), ("s10", "rs")]),
+    "s01s01":    (_H, None, [("cc0", "ijpr"), ("aa1", "klsq"), ("s01", "pq"), ("s01", "rs")]),
+    "s01s10t00": (-1, None, [("ccaa0", "ijptwq"), ("ca1", "klvu"), ("s01", "tu"), ("s10", "vw"), ("t00", "pq")]),
+    "s01s01t10": (_H, 1,    [("cca0", "ijtvq"), ("caa1", "klpwu"), ("s01", "tu"), ("s01", "vw"), ("t10", "pq")]),
+    "s01s10t01": (1, 1,     [("cca0", "ijptw"), ("caa1", "klvuq"), ("s01", "tu"), ("s10", "vw"), ("t01", "pq")]),
+    "s01s01t00": (_H, None, [("ccca0", "ijptvq"), ("aa1", "klwu"), ("s01", "tu"), ("s01", "vw"), ("t00", "pq")]),
+    "s01s01t11": (_H, None, [("cc0", "ijtv"), ("caaa1", "klpwuq"), ("s01", "tu"), ("s01", "vw"), ("t11", "pq")]),
+    "s01s01v1100": (_H, None, [("ccaa0", "ijtvsr"), ("ccaa1", "klpqwu"), ("s01", "tu"), ("s01", "vw"), ("v1100", "pqrs")]),
+    "s01s10v0000": (-1, None, [("cccaaa0", "ijpqtwsr"), ("ca1", "klvu"), ("s01", "tu"), ("s10", "vw"), ("v0000", "pqrs")]),
+    "s01s10v0101": (-4, None, [("ccaa0", "ijptwr"), ("ccaa1", "klqvus"), ("s01", "tu"), ("s10", "vw"), ("v0101", "pqrs")]),
+    "s01s01v0100": (1, 0,     [("cccaa0", "ijptvsr"), ("caa1", "klqwu"), ("s01", "tu"), ("s01", "vw"), ("v0100", "pqrs")]),
+    "s01s01v1101": (1, 1,     [("cca0", "ijtvr"), ("ccaaa1", "klpqwus"), ("s01", "tu"), ("s01", "vw"), ("v1101", "pqrs")]),
+    "s01s10v0001": (2, 0,     [("cccaa0", "ijpqtwr"), ("caa1", "klvus"), ("s01", "tu"), ("s10", "vw"), ("v0001", "pqrs")]),
+    "s01s10v0100": (2, 1,     [("ccaaa0", "ijptwsr"), ("cca1", "klqvu"), ("s01", "tu"), ("s10", "vw"), ("v0100", "pqrs")]),
+    "s01s01v0000": (_H, None, [("ccccaa0", "ijpqtvsr"), ("aa1", "klwu"), ("s01", "tu"), ("s01", "vw"), ("v0000", "pqrs")]),
+    "s01s01v0101": (2, None,  [("ccca0", "ijptvr"), ("caaa1", "klqwus"), ("s01", "tu"), ("s01", "vw"), ("v0101", "pqrs")]),
+    "s01s01v1111": (_H, None, [("cc0", "ijtv"), ("ccaaaa1", "klpqwusr"), ("s01", "tu"), ("s01", "vw"), ("v1111", "pqrs")]),
+    "s01s10v0011": (-1, None, [("ccca0", "ijpqtw"), ("caaa1", "klvusr"), ("s01", "tu"), ("s10", "vw"), ("v0011", "pqrs")]),
+})
+for _n in "01":      # SU_2mer_2.py: the ST forms with t## -> u<n>_##
+    for _t, _u in (("s01s10t00", "s01s10u%s00"), ("s01s01t10", "s01s01u%s10"), ("s01s10t01", "s01s10u%s01"),
+                   ("s01s01t00", "s01s01u%s00"), ("s01s01t11", "s01s01u%s11")):
+        _c, _s, _terms = TWO_FRAGMENT[_t]
+        TWO_FRAGMENT[_u % _n] = (_c, _s, [(("u%s_%s" % (_n, _nm[1:])) if _nm[0] == "t" else _nm, _ix) for _nm, _ix in _terms])
+
 ONE_FRAGMENT = {
     "t00":   [("ca0", "ijpq"), ("t00", "pq")],              # ST_1mer_0.py:24-30
     "u000":  [("ca0", "ijpq"), ("u0_00", "pq")],            # SU_1mer_0.py:24-30
@@ -66,6 +94,20 @@ CATALOG2 = {
     "s01v0100": ((0, 0), _PP), "s01v1101": ((0, 0), _PP), "s01v0000": ((-1, 1), _PM), "s01v0101": ((-1, 1), _PM),
     "s01v1100": ((1, -1), _PM), "s01v1111": ((-1, 1), _PM), "s01v0001": ((-2, 2), _PP), "s01v0111": ((-2, 2), _PP),
 }
+CATALOG2.update({
+    "s01s10": ((0, 0), [(+1, (0, 1))]), "s01s01": ((-2, 2), _PP),
+    "s01s10t00": ((0, 0), _PP), "s01s01t10": ((-1, 1), _PM), "s01s10t01": ((-1, 1), _PM), "s01s01t00": ((-2, 2), _PP),
+    "s01s01t11": ((-2, 2), _PP),
+    "s01s01v1100": ((0, 0), _PP), "s01s10v0000": ((0, 0), _PP), "s01s10v0101": ((0, 0), [(+1, (0, 1))]),
+    "s01s01v0100": ((-1, 1), _PM), "s01s01v1101": ((-1, 1), _PM), "s01s10v0001": ((-1, 1), _PM), "s01s10v0100": ((1, -1), _PM),
+    "s01s01v0000": ((-2, 2), _PP), "s01s01v0101": ((-2, 2), _PP), "s01s01v1111": ((-2, 2), _PP), "s01s10v0011": ((-2, 2), _PP),
+})
+for _n in "01":
+    CATALOG2["s01s10u%s00" % _n] = ((0, 0), _PP)
+    CATALOG2["s01s01u%s10" % _n] = ((-1, 1), _PM)
+    CATALOG2["s01s10u%s01" % _n] = ((-1, 1), _PM)
+    CATALOG2["s01s01u%s00" % _n] = ((-2, 2), _PP)
+    CATALOG2["s01s01u%s11" % _n] = ((-2, 2), _PP)
 for _n in "01":
     CATALOG2["s01u%s10" % _n] = ((0, 0), _PP)
     CATALOG2["s01u%s00" % _n] = ((-1, 1), _PM)
@@ -73,12 +115,17 @@ for _n in "01":
     CATALOG2["s01u%s01" % _n] = ((-2, 2), _PP)
 
 LISTS = {   # diagram_lists.py:10-71, orders 0 and 1
-    "S0": {0: ["identity"]}, "S2": {1: ["s01"]},
-    "ST1": {0: ["t00"]}, "ST2": {0: ["t01"], 1: ["s01t10", "s01t00", "s01t11", "s01t01"]},
+    "S0": {0: ["identity"]}, "S2": {1: ["s01"], 2: ["s01s10", "s01s01"]},
+    "ST1": {0: ["t00"]}, "ST2": {0: ["t01"], 1: ["s01t10", "s01t00", "s01t11", "s01t01"],
+                                  2: ["s01s10t00", "s01s01t10", "s01s10t01", "s01s01t00", "s01s01t11"]},
     "SU1": {0: ["u000"]}, "SU2": {0: ["u100", "u001", "u101"],
-                                  1: ["s01u010", "s01u000", "s01u011", "s01u001", "s01u110", "s01u100", "s01u111", "s01u101"]},
+                                  1: ["s01u010", "s01u000", "s01u011", "s01u001", "s01u110", "s01u100", "s01u111", "s01u101"],
+                                  2: ["s01s10u000", "s01s01u010", "s01s10u001", "s01s01u000", "s01s01u011",
+                                      "s01s10u100", "s01s01u110", "s01s10u101", "s01s01u100", "s01s01u111"]},
     "SV1": {0: ["v0000"]}, "SV2": {0: ["v0101", "v0001", "v0100", "v0011"],
-                                   1: ["s01v0100", "s01v1101", "s01v0000", "s01v0101", "s01v1100", "s01v1111", "s01v0001", "s01v0111"]},
+                                   1: ["s01v0100", "s01v1101", "s01v0000", "s01v0101", "s01v1100", "s01v1111", "s01v0001", "s01v0111"],
+                                   2: ["s01s01v1100", "s01s10v0000", "s01s10v0101", "s01s01v0100", "s01s01v1101", "s01s10v0001",
+                                       "s01s10v0100", "s01s01v0000", "s01s01v0101", "s01s01v1111", "s01s10v0011"]},
 }
 
 
@@ -216,6 +263,23 @@ def get_xr_H(symm, bior, dens, xr_order, monomer_charges):
         S2H2 += dimer_matrix(dens, mk(U=bior.U), {2: L["SU2"][1]}, charges)
         S2H2 += dimer_matrix(dens, mk(V=bior.V_diff), {1: L["SV1"][0], 2: L["SV2"][0]}, charges)
         S2H2 += dimer_matrix(dens, mk(V=bior.V), {2: L["SV2"][1]}, charges)
+        H2 = S2inv @ S2H2
+        H2 -= dimer_matrix(dens, mk(T=symm.T), {1: L["ST1"][0]}, charges)
+        H2 -= dimer_matrix(dens, mk(U=symm.U), {1: L["SU1"][0]}, charges)
+        H2 -= dimer_matrix(dens, mk(V=symm.V), {1: L["SV1"][0]}, charges)
+    elif xr_order == 2:                                  # get_xr_result.py:214-296
+        H1 = [monomer_matrix(dens, mk(T=symm.T), L["ST1"][0], m, monomer_charges[m])
+              + monomer_matrix(dens, mk(U=symm.U), L["SU1"][0], m, monomer_charges[m])
+              + monomer_matrix(dens, mk(V=symm.V), L["SV1"][0], m, monomer_charges[m]) for m in (0, 1)]
+        S2 = dimer_matrix(dens, mk(), {0: L["S0"][0], 2: L["S2"][1] + L["S2"][2]}, charges)
+        S2inv = numpy.linalg.inv(S2)
+        S2H2 = dimer_matrix(dens, mk(T=symm.T), {1: L["ST1"][0], 2: L["ST2"][0] + L["ST2"][1]}, charges)
+        S2H2 += dimer_matrix(dens, mk(U=symm.U), {1: L["SU1"][0], 2: L["SU2"][0] + L["SU2"][1]}, charges)
+        S2H2 += dimer_matrix(dens, mk(T=bior.T), {2: L["ST2"][2]}, charges)
+        S2H2 += dimer_matrix(dens, mk(U=bior.U), {2: L["SU2"][2]}, charges)
+        S2H2 += dimer_matrix(dens, mk(V=symm.V), {1: L["SV1"][0], 2: L["SV2"][0]}, charges)
+        S2H2 += dimer_matrix(dens, mk(V=bior.V_diff), {2: L["SV2"][1]}, charges)
+        S2H2 += dimer_matrix(dens, mk(V=bior.V), {2: L["SV2"][2]}, charges)
         H2 = S2inv @ S2H2
         H2 -= dimer_matrix(dens, mk(T=symm.T), {1: L["ST1"][0]}, charges)
         H2 -= dimer_matrix(dens, mk(U=symm.U), {1: L["SU1"][0]}, charges)

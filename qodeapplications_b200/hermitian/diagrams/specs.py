@@ -2,55 +2,76 @@
 
 Every two-fragment diagram of the reference (hermitian-XRCC/diagrams/S*_2mer_*.py) has the form
 
-    coefficient * (-1)**(X.n_j0 + shift) * raw( A(i0,j0, a-free...) @ B(i1,j1, b-free...) )
+    coefficient * (-1)**(X.n_j0 + shift) * raw( A(i0,j0, ...) @ B(i1,j1, ...) [@ s01(v,w) | s10(v,w)] )
 
 with A a density or rho x integral precontraction of diagram fragment 0, B the same for fragment 1,
-and equal letters in the two free-index lists contracted.  A row of the table below is
-``label: (coefficient, parity shift or None, A name, A free letters, B name, B free letters)``;
-it is turned into a function with the reference's signature ``fn(X, contract_last=False) ->
-ndarray[N_i0, N_i1, N_j0, N_j1]``, evaluated as ONE xr_gemm_scatter over K = the shared letters.
-One-fragment diagrams are a single precontraction; ``u100`` carries a Kronecker delta over the
-spectator fragment (SU_2mer_0.py:26-48); ``identity`` is the 0-mer (S_0mer_0.py:21-22).
-File:line of the reference definition is given per row.
+from S-order 2 on a bare overlap block as third factor, and equal letters contracted.  A row of the
+table is ``label: (coefficient, parity shift or None, [(operand name, free letters), ...])``; the
+operand names are exactly the attribute names the reference reads from ``X`` (build_diagram.py:116-134),
+so ``frag_resolve`` resolves them the same way.  A row becomes a function with the reference's signature
+``fn(X, contract_last=False) -> ndarray[N_i0, N_i1, N_j0, N_j1]``; the product is evaluated by
+``Contractor.multi_contract`` (pairwise xr_gemm_scatter calls, the last one writing -- or accumulating in
+place -- the [i0,i1,j0,j1] block).  One-fragment diagrams are a single precontraction; ``u100`` carries a
+Kronecker delta over the spectator fragment (SU_2mer_0.py:26-48); ``identity`` is the 0-mer
+(S_0mer_0.py:21-22).  File:line of the reference definition is given per row or group.
 """
+import re
 import numpy
 
 from ..tensor import DeviceTensor
 
-# label: (coef, parity shift (None = no n_j0 phase), A, A free, B, B free)
+H = 0.5
+# label: (coef, parity shift (None = no n_j0 phase), [(operand, free letters), ...])
 TWO_FRAGMENT = {
     # ---- order 0 --------------------------------------------------------------------------------
-    "t01":      (1, 0,    "c0p_Tp1", "q",            "a1", "q"),                    # ST_2mer_0.py:25-34
-    "u001":     (1, 0,    "c0p_U0p1", "q",           "a1", "q"),                    # SU_2mer_0.py:98-107
-    "u101":     (1, 0,    "c0p_U1p1", "q",           "a1", "q"),                    # SU_2mer_0.py:109-118
-    "v0101":    (4, None, "ca0pr_Vp1r1", "qs",       "ca1", "qs"),                  # SV_2mer_0.py:25-34
-    "v0001":    (2, 1,    "cca0pqr_Vpqr1", "s",      "a1", "s"),                    # SV_2mer_0.py:36-45
-    "v0100":    (2, 0,    "caa0psr_Vp1rs", "q",      "c1", "q"),                    # SV_2mer_0.py:47-56
-    "v0011":    (1, None, "cc0pq_Vpq11", "rs",       "aa1", "sr"),                  # SV_2mer_0.py:58-67
+    "t01":      (1, 0,     [("c0p_Tp1", "q"), ("a1", "q")]),                                  # ST_2mer_0.py:25-34
+    "u001":     (1, 0,     [("c0p_U0p1", "q"), ("a1", "q")]),                                 # SU_2mer_0.py:98-107
+    "u101":     (1, 0,     [("c0p_U1p1", "q"), ("a1", "q")]),                                 # SU_2mer_0.py:109-118
+    "v0101":    (4, None,  [("ca0pr_Vp1r1", "qs"), ("ca1", "qs")]),                           # SV_2mer_0.py:25-34
+    "v0001":    (2, 1,     [("cca0pqr_Vpqr1", "s"), ("a1", "s")]),                            # SV_2mer_0.py:36-45
+    "v0100":    (2, 0,     [("caa0psr_Vp1rs", "q"), ("c1", "q")]),                            # SV_2mer_0.py:47-56
+    "v0011":    (1, None,  [("cc0pq_Vpq11", "rs"), ("aa1", "sr")]),                           # SV_2mer_0.py:58-67
     # ---- order 1 --------------------------------------------------------------------------------
-    "s01":      (1, 0,    "c0p_Sp1", "q",            "a1", "q"),                    # S_2mer_1.py:25-34
-    "s01t10":   (-1, None, "ca0Xq_T1q", "tp",        "ca1Xu_S0u", "pt"),            # ST_2mer_1.py:25-36
-    "s01t00":   (1, 1,    "cca0pXq_Tpq", "t",        "a1u_S0u", "t"),               # ST_2mer_1.py:38-49
-    "s01t11":   (1, 1,    "c0t_St1", "u",            "caa1pXq_Tpq", "u"),           # ST_2mer_1.py:51-62
-    "s01t01":   (1, None, "cc0pX_Tp1", "tq",         "aa1uX_S0u", "qt"),            # ST_2mer_1.py:64-75
-    "s01u010":  (-1, None, "ca0Xq_U01q", "tp",       "ca1Xu_S0u", "pt"),            # SU_2mer_1.py
-    "s01u000":  (1, 1,    "cca0pXq_U0pq", "t",       "a1u_S0u", "t"),
-    "s01u011":  (1, 1,    "c0t_St1", "u",            "caa1pXq_U0pq", "u"),
-    "s01u001":  (1, None, "cc0pX_U0p1", "tq",        "aa1uX_S0u", "qt"),
-    "s01u110":  (-1, None, "ca0Xq_U11q", "tp",       "ca1Xu_S0u", "pt"),
-    "s01u100":  (1, 1,    "cca0pXq_U1pq", "t",       "a1u_S0u", "t"),
-    "s01u111":  (1, 1,    "c0t_St1", "u",            "caa1pXq_U1pq", "u"),
-    "s01u101":  (1, None, "cc0pX_U1p1", "tq",        "aa1uX_S0u", "qt"),
-    "s01v0100": (-2, None, "ccaa0pXsr_Vp1rs", "tq",  "ca1Xu_S0u", "qt"),            # SV_2mer_1.py:25-36
-    "s01v1101": (2, None, "ca0tX_St1", "ru",         "ccaa1pqXs_Vpq0s", "ur"),      # SV_2mer_1.py:38-49
-    "s01v0000": (1, 0,    "cccaa0pqXsr_Vpqrs", "t",  "a1u_S0u", "t"),               # SV_2mer_1.py:51-62
-    "s01v0101": (4, 0,    "cca0pXr_Vp1r1", "tqs",    "caa1XuX_S0u", "qst"),         # SV_2mer_1.py:64-75
-    "s01v1100": (1, 0,    "caa0Xsr_V11rs", "tpq",    "cca1XXu_S0u", "pqt"),         # SV_2mer_1.py:77-88
-    "s01v1111": (1, 0,    "c0t_St1", "u",            "ccaaa1pqXsr_Vpqrs", "u"),     # SV_2mer_1.py:90-101
-    "s01v0001": (2, None, "ccca0pqXr_Vpqr1", "ts",   "aa1uX_S0u", "st"),            # SV_2mer_1.py:103-114
-    "s01v0111": (-2, None, "cc0Xt_St1", "pu",        "caaa1qXsr_V0qrs", "up"),      # SV_2mer_1.py:116-127
-    "s01v0011": (1, 0,    "ccc0pqX_Vpq11", "trs",    "aaa1uXX_S0u", "srt"),         # SV_2mer_1.py:129-140
+    "s01":      (1, 0,     [("c0p_Sp1", "q"), ("a1", "q")]),                                  # S_2mer_1.py:25-34
+    "s01t10":   (-1, None, [("ca0Xq_T1q", "tp"), ("ca1Xu_S0u", "pt")]),                       # ST_2mer_1.py:25-36
+    "s01t00":   (1, 1,     [("cca0pXq_Tpq", "t"), ("a1u_S0u", "t")]),                         # ST_2mer_1.py:38-49
+    "s01t11":   (1, 1,     [("c0t_St1", "u"), ("caa1pXq_Tpq", "u")]),                         # ST_2mer_1.py:51-62
+    "s01t01":   (1, None,  [("cc0pX_Tp1", "tq"), ("aa1uX_S0u", "qt")]),                       # ST_2mer_1.py:64-75
+    "s01v0100": (-2, None, [("ccaa0pXsr_Vp1rs", "tq"), ("ca1Xu_S0u", "qt")]),                 # SV_2mer_1.py:25-36
+    "s01v1101": (2, None,  [("ca0tX_St1", "ru"), ("ccaa1pqXs_Vpq0s", "ur")]),                 # SV_2mer_1.py:38-49
+    "s01v0000": (1, 0,     [("cccaa0pqXsr_Vpqrs", "t"), ("a1u_S0u", "t")]),                   # SV_2mer_1.py:51-62
+    "s01v0101": (4, 0,     [("cca0pXr_Vp1r1", "tqs"), ("caa1XuX_S0u", "qst")]),               # SV_2mer_1.py:64-75
+    "s01v1100": (1, 0,     [("caa0Xsr_V11rs", "tpq"), ("cca1XXu_S0u", "pqt")]),               # SV_2mer_1.py:77-88
+    "s01v1111": (1, 0,     [("c0t_St1", "u"), ("ccaaa1pqXsr_Vpqrs", "u")]),                   # SV_2mer_1.py:90-101
+    "s01v0001": (2, None,  [("ccca0pqXr_Vpqr1", "ts"), ("aa1uX_S0u", "st")]),                 # SV_2mer_1.py:103-114
+    "s01v0111": (-2, None, [("cc0Xt_St1", "pu"), ("caaa1qXsr_V0qrs", "up")]),                 # SV_2mer_1.py:116-127
+    "s01v0011": (1, 0,     [("ccc0pqX_Vpq11", "trs"), ("aaa1uXX_S0u", "srt")]),               # SV_2mer_1.py:129-140
+    # ---- order 2 --------------------------------------------------------------------------------
+    "s01s10":   (-1, None, [("ca0pX_Sp1", "sq"), ("ca1rX_Sr0", "qs")]),                       # S_2mer_2.py:25-36
+    "s01s01":   (H, None,  [("cc0pX_Sp1", "rq"), ("aa1sX_S0s", "qr")]),                       # S_2mer_2.py:38-49
+    "s01s10t00": (-1, None, [("ccaa0pXXq_Tpq", "tw"), ("ca1Xu_S0u", "vt"), ("s10", "vw")]),   # ST_2mer_2.py:25-38
+    "s01s01t10": (H, 1,    [("cca0XXq_T1q", "tvp"), ("caa1XXu_S0u", "pwt"), ("s01", "vw")]),  # ST_2mer_2.py:40-53
+    "s01s10t01": (1, 1,    [("cca0pXX_Tp1", "twq"), ("caa1XuX_S0u", "vqt"), ("s10", "vw")]),  # ST_2mer_2.py:55-68
+    "s01s01t00": (H, None, [("ccca0pXXq_Tpq", "tv"), ("aa1Xu_S0u", "wt"), ("s01", "vw")]),    # ST_2mer_2.py:70-83
+    "s01s01t11": (H, None, [("cc0tX_St1", "vu"), ("caaa1pXXq_Tpq", "wu"), ("s01", "vw")]),    # ST_2mer_2.py:85-98
+    "s01s01v1100": (H, None, [("ccaa0XXsr_V11rs", "tvpq"), ("ccaa1XXXu_S0u", "pqwt"), ("s01", "vw")]),   # SV_2mer_2.py
+    "s01s10v0000": (-1, None, [("cccaaa0pqXXsr_Vpqrs", "tw"), ("ca1Xu_S0u", "vt"), ("s10", "vw")]),
+    "s01s10v0101": (-4, None, [("ccaa0pXXr_Vp1r1", "twqs"), ("ccaa1XXuX_S0u", "qvst"), ("s10", "vw")]),
+    "s01s01v0100": (1, 0,  [("cccaa0pXXsr_Vp1rs", "tvq"), ("caa1XXu_S0u", "qwt"), ("s01", "vw")]),
+    "s01s01v1101": (1, 1,  [("cca0tXX_St1", "vru"), ("ccaaa1pqXXs_Vpq0s", "wur"), ("s01", "vw")]),
+    "s01s10v0001": (2, 0,  [("cccaa0pqXXr_Vpqr1", "tws"), ("caa1XuX_S0u", "vst"), ("s10", "vw")]),
+    "s01s10v0100": (2, 1,  [("ccaaa0pXXsr_Vp1rs", "twq"), ("cca1XXu_S0u", "qvt"), ("s10", "vw")]),
+    "s01s01v0000": (H, None, [("ccccaa0pqXXsr_Vpqrs", "tv"), ("aa1Xu_S0u", "wt"), ("s01", "vw")]),
+    "s01s01v0101": (2, None, [("ccca0pXXr_Vp1r1", "tvqs"), ("caaa1XXuX_S0u", "qwst"), ("s01", "vw")]),
+    "s01s01v1111": (H, None, [("cc0tX_St1", "vu"), ("ccaaaa1pqXXsr_Vpqrs", "wu"), ("s01", "vw")]),
+    "s01s10v0011": (-1, None, [("ccca0pqXX_Vpq11", "twrs"), ("caaa1XuXX_S0u", "vsrt"), ("s10", "vw")]),
 }
+for _n in "01":     # SU_2mer_1.py / SU_2mer_2.py: the ST rows with T -> U<nucleus fragment>
+    for _t, _u in (("s01t10", "s01u%s10"), ("s01t00", "s01u%s00"), ("s01t11", "s01u%s11"), ("s01t01", "s01u%s01"),
+                   ("s01s10t00", "s01s10u%s00"), ("s01s01t10", "s01s01u%s10"), ("s01s10t01", "s01s10u%s01"),
+                   ("s01s01t00", "s01s01u%s00"), ("s01s01t11", "s01s01u%s11")):
+        _c, _s, _ops = TWO_FRAGMENT[_t]
+        TWO_FRAGMENT[_u % _n] = (_c, _s, [(_name.replace("_T", "_U" + _n), _idx) for _name, _idx in _ops])
 
 ONE_FRAGMENT = {
     "t00":   "ca0pq_Tpq",          # ST_1mer_0.py:24
@@ -69,27 +90,35 @@ def _contractor(X):
     return X._info.contract_cache.general.contractor
 
 
-def make_two_fragment(label):
-    coef, shift, nameA, freeA, nameB, freeB = TWO_FRAGMENT[label]
+def _state_labels(name):
+    """a density / precontraction of diagram fragment d carries (bra, ket) state axes i<d>, j<d>; a bare integral none"""
+    m = re.match(r"^[ca]+(\d)", name)
+    return ["i" + m.group(1), "j" + m.group(1)] if m else []
 
-    def operands(X):
-        A, B = getattr(X, nameA), getattr(X, nameB)
-        if A is None or B is None:
-            raise RuntimeError("diagram %s: operand %s is not available for these charges" % (label, nameA if A is None else nameB))
+
+def make_two_fragment(label):
+    coef, shift, operands = TWO_FRAGMENT[label]
+
+    def factors(X):
+        out = []
+        for name, free in operands:
+            T = getattr(X, name)
+            if T is None:
+                raise RuntimeError("diagram %s: operand %s is not available for these charges" % (label, name))
+            out.append((T, _state_labels(name) + list(free)))
         factor = float(coef) if shift is None else float(coef) * (-1.0) ** (X.n_j0 + shift)
-        return A, ["i0", "j0"] + list(freeA), B, ["i1", "j1"] + list(freeB), factor
+        return out, factor
 
     def contraction(X, contract_last=False):
         _require_plain(contract_last)
-        A, idxA, B, idxB, factor = operands(X)
-        out = _contractor(X).contract(A, idxA, B, idxB, ["i0", "i1", "j0", "j1"], alpha=factor)
-        return out.host()
+        ops, factor = factors(X)
+        return _contractor(X).multi_contract(ops, ["i0", "i1", "j0", "j1"], alpha=factor).host()
 
     def accumulate(X, phase, out, offset, strides):
         """out[offset + i0*strides['i0'] + i1*strides['i1'] + j0*strides['j0'] + j1*strides['j1']] += phase * diagram"""
-        A, idxA, B, idxB, factor = operands(X)
-        _contractor(X).contract(A, idxA, B, idxB, ["i0", "i1", "j0", "j1"], alpha=phase * factor, out=out,
-                                out_offset=offset, out_strides=strides, accumulate=True)
+        ops, factor = factors(X)
+        _contractor(X).multi_contract(ops, ["i0", "i1", "j0", "j1"], alpha=phase * factor, out=out, out_offset=offset,
+                                      out_strides=strides, accumulate=True)
 
     contraction.__name__ = label
     contraction.accumulate = accumulate

@@ -83,6 +83,18 @@ def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False
         out = dimer_sum([(ST_symm, {1: D.ST1[0]}), (SU_symm, {1: D.SU1[0]}), (SV_symm, {1: D.SV1[0]})], scale=-1.0)
         contractor.contract(store.get(S2inv), ["a", "k"], S2H2, ["k", "b"], ["a", "b"], out=out, accumulate=True)
         H2 = out.host()
+    elif xr_order == 2:                                 # get_xr_result.py:214-296
+        SV_diff = make(struct(S=S, V=bior_ints.V_diff), SV_diagrams)
+        H1 = monomers(ST_symm, SU_symm, SV_symm)
+        S2 = XR_term.dimer_matrix(S_blocks, {0: D.S0[0], 2: D.S2[1] + D.S2[2]}, (0, 1), all_dimer_charges, matrix_timer,
+                                  ordering="final")
+        S2inv = precise_numpy_inverse(S2)
+        S2H2 = dimer_sum([(ST_symm, {1: D.ST1[0], 2: D.ST2[0] + D.ST2[1]}), (SU_symm, {1: D.SU1[0], 2: D.SU2[0] + D.SU2[1]}),
+                          (ST_bior, {2: D.ST2[2]}), (SU_bior, {2: D.SU2[2]}),
+                          (SV_symm, {1: D.SV1[0], 2: D.SV2[0]}), (SV_diff, {2: D.SV2[1]}), (SV_bior, {2: D.SV2[2]})])
+        out = dimer_sum([(ST_symm, {1: D.ST1[0]}), (SU_symm, {1: D.SU1[0]}), (SV_symm, {1: D.SV1[0]})], scale=-1.0)
+        contractor.contract(store.get(S2inv), ["a", "k"], S2H2, ["k", "b"], ["a", "b"], out=out, accumulate=True)
+        H2 = out.host()
     else:
         raise NotImplementedError("xr order %r is not implemented" % (xr_order,))
     return H1, H2

@@ -163,3 +163,54 @@ class Contractor(object):
             self.dev.ctx.gemm_scatter(M, N, K, alpha, A2, K, B2, K, base, offM, 0, offN, accumulate)
         self.flops += 2.0 * M * N * K
         return DeviceTensor(out_buf, self.dev) if out is None else out
+
+
+def _multi_contract(self, factors, idx_out, alpha=1.0, out=None, out_offset=0, out_strides=None, accumulate=False):
+    """Product of any number of tensors: out[idx_out] (+)= alpha * sum over every label not in idx_out.
+    factors = [(DeviceTensor, labels), ...].  Pairs are contracted greedily (smallest intermediate first, the
+    choice opt_einsum's greedy path makes for these chains); the last pairwise contraction writes into `out`."""
+    factors = [(T, list(idx)) for T, idx in factors]
+    idx_out = list(idx_out)
+    if len(factors) == 1:
+        T, idx = factors[0]
+        one = DeviceTensor(self.dev.upload(numpy.ones((1,))), self.dev)
+        if out is None:       # scaled (and possibly permuted) copy: a GEMM against the 1x1 identity
+            res = self.contract(T, idx, one, ["__one"], idx_out + ["__one"], alpha)
+            return DeviceTensor(res.buf.reshape(res.shape[:-1]), self.dev)
+        strides = None if out_strides is None else dict(out_strides, __one=0)
+        if strides is None:
+            strides = dict(zip(idx_out, _strides([T.shape[idx.index(l)] for l in idx_out])), __one=0)
+        return self.contract(T, idx, one, ["__one"], idx_out + ["__one"], alpha, out, out_offset, strides, accumulate)
+    while len(factors) > 2:
+        extent = {}
+        for T, idx in factors:
+            extent.update(zip(idx, T.shape))
+        best = None
+        for a in range(len(factors)):
+            for b in range(a + 1, len(factors)):
+                la, lb = factors[a][1], factors[b][1]
+                shared = [l for l in la if l in lb]
+                if not shared:
+                    continue
+                elsewhere = set(idx_out)
+                for k, (_, ls) in enumerate(factors):
+                    if k not in (a, b):
+                        elsewhere.update(ls)
+                if any(l in elsewhere for l in shared):
+                    raise NotImplementedError("label shared by more than two factors")
+                keep = [l for l in la if l not in shared] + [l for l in lb if l not in shared]
+                size = 1
+                for l in keep:
+                    size *= extent[l]
+                if best is None or size < best[0]:
+                    best = (size, a, b, keep)
+        if best is None:
+            raise NotImplementedError("outer products of unconnected factors")
+        _, a, b, keep = best
+        merged = self.contract(factors[a][0], factors[a][1], factors[b][0], factors[b][1], keep)
+        factors = [f for k, f in enumerate(factors) if k not in (a, b)] + [(merged, keep)]
+    (A, idxA), (B, idxB) = factors
+    return self.contract(A, idxA, B, idxB, idx_out, alpha, out, out_offset, out_strides, accumulate)
+
+
+Contractor.multi_contract = _multi_contract

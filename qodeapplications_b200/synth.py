@@ -36,6 +36,7 @@ N_ELEC_REF = 4
 
 OPS_ORDER0 = ("a", "c", "aa", "cc", "ca", "caa", "cca", "ccaa")
 OPS_ORDER1 = OPS_ORDER0 + ("caaa", "ccca", "ccaaa", "cccaa")
+OPS_ORDER2 = OPS_ORDER1 + ("ccaaaa", "cccaaa", "ccccaa")
 OPS_GENERAL = ("a", "c", "aa", "cc", "ca", "caa", "cca")      # + precontracted scalar "ccaa"
 
 

@@ -41,10 +41,14 @@ def _blocks(system, dev, family, which="symm"):
                                          timings=timer(), precon_timings=timer())
 
 
-def test_every_diagram_block_matches_reference_golden(dev):
-    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_blocks.npz"))
-    toy = synth.make_system("toy", ops=synth.OPS_ORDER1, with_bior=True)
-    family_of = lambda label: "S" if label == "s01" else "S" + label.replace("s01", "")[0].upper()
+@pytest.mark.parametrize("fixture,n_blocks,ops", [("hermitian_toy_blocks.npz", 221, synth.OPS_ORDER1),
+                                                  ("hermitian_toy_blocks2.npz", 165, synth.OPS_ORDER2)])
+def test_every_diagram_block_matches_reference_golden(dev, fixture, n_blocks, ops):
+    g = numpy.load(os.path.join(GOLDEN, fixture))
+    toy = synth.make_system("toy", ops=ops, with_bior=True)       # the fixture was generated from exactly this draw
+    def family_of(label):
+        rest = label.replace("s01", "").replace("s10", "")
+        return "S" if rest == "" else "S" + rest[0].upper()
     cache, count = {}, 0
     for key in g.files:
         if key == "input_sha256":
@@ -61,10 +65,10 @@ def test_every_diagram_block_matches_reference_golden(dev):
             ci0, ci1, cj0, cj1 = (int(x) for x in parts[1].split(","))
             _close(cache[fam][(0, 1)][((ci0, cj0), (ci1, cj1))][label], g[key])
         count += 1
-    assert count == 221
+    assert count == n_blocks
 
 
-@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1)])
+@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1), (2, synth.OPS_ORDER2)])
 def test_get_xr_H_matches_reference_golden(dev, order, ops):
     from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
     g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_order%d.npz" % order))
@@ -99,6 +103,32 @@ def test_mid_order1_against_oracle(dev):
     R1, R2 = ho.get_xr_H(system["symm"], system["bior"], *args)
     _close(H1[0], R1[0])
     _close(H2, R2, 1e-9)
+
+
+def test_mid_order2_against_oracle(dev):
+    """n = 8, N = 5/3/4: get_xr_H(order 2) (rank-6 densities, three-factor diagrams) against the NumPy oracle"""
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    system = synth.make_system("mid", ops=synth.OPS_ORDER2, with_bior=True)
+    charges = system["charges"]
+    args = (system["densities"][:2], 2, [charges, charges])
+    H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), *args, device=dev)
+    R1, R2 = ho.get_xr_H(system["symm"], system["bior"], *args)
+    _close(H2, R2, 1e-9)
+
+
+def test_xr_tensor_expression_syntax(dev):
+    """the tensornet-style seam: raw( A(0,1,"p","q") @ B(2,"q") @ C("p",3) ) evaluated on the GPU"""
+    from qodeapplications_b200.hermitian import XR_tensor
+    from qodeapplications_b200.hermitian.tensor import Contractor, DeviceStore
+    rng = numpy.random.default_rng(3)
+    a, b, c = rng.standard_normal((3, 4, 5, 6)), rng.standard_normal((7, 6)), rng.standard_normal((5, 2))
+    A, B, C = XR_tensor.init(a), XR_tensor.init(b), XR_tensor.init(c)
+    engine = (DeviceStore(dev), Contractor(dev))
+    got = XR_tensor.raw(-2.5 * (A(0, 1, "p", "q") @ B(2, "q") @ C("p", 3)), engine)
+    _close(got, -2.5 * numpy.einsum("ijpq,kq,pl->ijkl", a, b, c), 1e-13)
+    got = XR_tensor.raw(A(1, 0, "p", 2) @ C("p", 3), engine)           # free labels sorted ascending in the result
+    _close(got, numpy.einsum("jipq,pl->ijql", a, c), 1e-13)
+    _close(XR_tensor.raw(3.0 * A(3, 1, 0, 2), engine), 3.0 * a.transpose(2, 1, 3, 0), 1e-15)
 
 
 def test_dimer_matrix_blocked_and_final_orderings(dev):

@@ -15,13 +15,11 @@ def _close(a, b, tol=1e-10):
     assert numpy.abs(numpy.asarray(a) - b).max() <= tol * scale, (numpy.abs(a - b).max(), scale)
 
 
-@pytest.fixture(scope="module")
-def toy():
-    return synth.make_system("toy", ops=synth.OPS_ORDER1, with_bior=True)
-
-
-def test_every_diagram_block_matches_reference(toy):
-    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_blocks.npz"))
+@pytest.mark.parametrize("fixture,n_labels,ops", [("hermitian_toy_blocks.npz", 32, synth.OPS_ORDER1),
+                                                  ("hermitian_toy_blocks2.npz", 28, synth.OPS_ORDER2)])
+def test_every_diagram_block_matches_reference(fixture, n_labels, ops):
+    toy = synth.make_system("toy", ops=ops, with_bior=True)       # the fixture was generated from exactly this draw
+    g = numpy.load(os.path.join(GOLDEN, fixture))
     dens, symm = toy["densities"], toy["symm"]
     ints = ho.integrals(symm.S, symm.T, symm.U, symm.V)
     seen = set()
@@ -40,10 +38,10 @@ def test_every_diagram_block_matches_reference(toy):
             got = ho.dimer_block(label, dens, ints, (0, 1), ((ci0, cj0), (ci1, cj1)))
             assert got is not None, key
             _close(got, g[key])
-    assert len(seen) == 32       # 3 one-fragment + 29 two-fragment diagrams of orders 0-1
+    assert len(seen) == n_labels       # orders 0-1: 3 one-fragment + 29 two-fragment diagrams; order 2: 28
 
 
-@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1)])
+@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1), (2, synth.OPS_ORDER2)])
 def test_get_xr_H_matches_reference(order, ops):
     g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_order%d.npz" % order))
     system = synth.make_system("toy", ops=ops, with_bior=True)

@@ -54,7 +54,7 @@ def test_general_bra_slabs_host_logic():
 
 @pytest.fixture(scope="module")
 def toy1():
-    return synth.make_system("toy", ops=synth.OPS_ORDER1, with_bior=True)
+    return synth.make_system("toy", ops=synth.OPS_ORDER2, with_bior=True)
 
 
 def _hermitian_blocks(system, dev, family):
@@ -72,11 +72,15 @@ def _hermitian_blocks(system, dev, family):
                                          timings=timer(), precon_timings=timer())
 
 
-def test_hermitian_every_diagram_block_host_logic(toy1):
-    """blocks[subsystem][charges][label] -- the reference's own access pattern -- for all 32 diagrams"""
-    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_blocks.npz"))
+@pytest.mark.parametrize("fixture,ops", [("hermitian_toy_blocks.npz", synth.OPS_ORDER1), ("hermitian_toy_blocks2.npz", synth.OPS_ORDER2)])
+def test_hermitian_every_diagram_block_host_logic(fixture, ops):
+    """blocks[subsystem][charges][label] -- the reference's own access pattern -- for all 60 diagrams of orders 0-2"""
+    g = numpy.load(os.path.join(GOLDEN, fixture))
+    toy1 = synth.make_system("toy", ops=ops, with_bior=True)       # the fixture was generated from exactly this draw
     dev = FakeDevice()
-    family_of = lambda label: "S" if label == "s01" else "S" + label.replace("s01", "")[0].upper()
+    def family_of(label):
+        rest = label.replace("s01", "").replace("s10", "")
+        return "S" if rest == "" else "S" + rest[0].upper()
     cache = {}
     for key in g.files:
         if key == "input_sha256":
@@ -96,7 +100,7 @@ def test_hermitian_every_diagram_block_host_logic(toy1):
             _close(blk[(0, 1)][((ci0, cj0), (ci1, cj1))][label], g[key])
 
 
-@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1)])
+@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1), (2, synth.OPS_ORDER2)])
 def test_hermitian_get_xr_H_host_logic(order, ops):
     from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
     g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_order%d.npz" % order))
