@@ -6,6 +6,10 @@ The reference materialises every diagram block on the host, transposes it and sl
 Python loop over spectator states for the Kronecker deltas, :69-80).  Here the matrix lives in HBM and
 every diagram is accumulated in place by the epilogue of its own GEMM; the result is downloaded once.
 
+``bra_det`` / ``ket_det`` (the StateSpaceOptimizer gradient variants, XR_term.py:122-148): the ket (bra) state
+pair of every two-fragment diagram is traced and the result is a VECTOR over the bra (ket) product states, summed
+over all charge blocks of the traced side.
+
 Extra keyword arguments (defaults reproduce the reference):
   ordering="blocked" | "final" -- "final" lays rows/columns out as (global i1, global i2), i.e. what
       get_xr_result.py:300-353 produces from the blocked matrix with a double Python loop;
@@ -16,15 +20,6 @@ Extra keyword arguments (defaults reproduce the reference):
 import numpy
 
 from .tensor import DeviceTensor
-
-
-def _ascending(array):
-    return all(b > a for a, b in zip(array[:-1], array[1:]))
-
-
-def _check_no_det(bra_det, ket_det):
-    if bra_det or ket_det:
-        raise NotImplementedError("bra_det / ket_det matrices (StateSpaceOptimizer gradient variants) are not built yet")
 
 
 def _buffer(into, shape):
@@ -66,64 +61,72 @@ def monomer_matrix(op_blocks, active_diagrams, subsys_index, charge_blocks, timi
     return _finish(dev, Matrix, device_result)
 
 
+def _layout(rho1, rho2, which, charge_blocks, ordering):
+    """{(c1, c2): (index of the block's first product state, stride of the fragment-1 state index)}"""
+    n1, n2 = rho1[which], rho2[which]
+    starts = {}
+    if ordering == "blocked":                       # XR_term.py:153-164
+        beg = 0
+        for c1, c2 in charge_blocks:
+            starts[(c1, c2)] = (beg, n2[c2])
+            beg += n1[c1] * n2[c2]
+    elif ordering == "final":                       # get_xr_result.py:300-353
+        chgs1, chgs2 = [], []
+        for c1, c2 in charge_blocks:
+            if c1 not in chgs1:
+                chgs1.append(c1)
+            if c2 not in chgs2:
+                chgs2.append(c2)
+        if len(chgs1) * len(chgs2) != len(charge_blocks):
+            raise ValueError("ordering='final' needs charge_blocks to be a full product of monomer charges")
+        off1, off2, acc = {}, {}, 0
+        for c in chgs1:
+            off1[c] = acc
+            acc += n1[c]
+        tot2 = 0
+        for c in chgs2:
+            off2[c] = tot2
+            tot2 += n2[c]
+        for c1, c2 in charge_blocks:
+            starts[(c1, c2)] = (off1[c1] * tot2 + off2[c2], tot2)
+    else:
+        raise ValueError("ordering must be 'blocked' or 'final'")
+    return starts
+
+
 def dimer_matrix(op_blocks, active_diagrams, subsys_indices, charge_blocks, timings, bra_det=False, ket_det=False,
                  ordering="blocked", device_result=False, into=None, scale=1.0):
-    _check_no_det(bra_det, ket_det)
     m = tuple(subsys_indices)
     rho1, rho2 = (op_blocks.densities[x] for x in m)
     dev = op_blocks.dev
     dim_bra = sum(rho1["n_states_bra"][c1] * rho2["n_states_bra"][c2] for c1, c2 in charge_blocks)
     dim_ket = sum(rho1["n_states"][c1] * rho2["n_states"][c2] for c1, c2 in charge_blocks)
-    Matrix = dev.zeros((dim_bra, dim_ket)) if into is None else _buffer(into, (dim_bra, dim_ket))
+    det = "bra" if (bra_det and not ket_det) else ("ket" if (ket_det and not bra_det) else None)
+    shape = (dim_bra,) if det == "bra" else ((dim_ket,) if det == "ket" else (dim_bra, dim_ket))
+    Matrix = dev.zeros(shape) if into is None else _buffer(into, shape)
     ld = dim_ket
-
-    # where each charge block starts and how its two state indices stride, for bras (rows) and kets (columns)
-    def layout(which):
-        n1, n2 = rho1[which], rho2[which]
-        starts = {}
-        if ordering == "blocked":                       # XR_term.py:153-164
-            beg = 0
-            for c1, c2 in charge_blocks:
-                starts[(c1, c2)] = (beg, n2[c2])        # (first index, stride of the fragment-1 state)
-                beg += n1[c1] * n2[c2]
-        elif ordering == "final":                       # get_xr_result.py:300-353
-            chgs1, chgs2 = [], []
-            for c1, c2 in charge_blocks:
-                if c1 not in chgs1:
-                    chgs1.append(c1)
-                if c2 not in chgs2:
-                    chgs2.append(c2)
-            if len(chgs1) * len(chgs2) != len(charge_blocks):
-                raise ValueError("ordering='final' needs charge_blocks to be a full product of monomer charges")
-            off1, off2, acc = {}, {}, 0
-            for c in chgs1:
-                off1[c] = acc
-                acc += n1[c]
-            tot2 = 0
-            for c in chgs2:
-                off2[c] = tot2
-                tot2 += n2[c]
-            for c1, c2 in charge_blocks:
-                starts[(c1, c2)] = (off1[c1] * tot2 + off2[c2], tot2)
-        else:
-            raise ValueError("ordering must be 'blocked' or 'final'")
-        return starts
-
-    rows, cols = layout("n_states_bra"), layout("n_states")
-    n_i = lambda x, chg: op_blocks.densities[m[x]]["n_states_bra"][chg]
+    rows = _layout(rho1, rho2, "n_states_bra", charge_blocks, ordering)
+    cols = _layout(rho1, rho2, "n_states", charge_blocks, ordering)
     n_j = lambda x, chg: op_blocks.densities[m[x]]["n_states"][chg]
 
     for chg_i in charge_blocks:
         for chg_j in charge_blocks:
             subsys_charges = [(chg_i[0], chg_j[0]), (chg_i[1], chg_j[1])]
             (Ibeg, Istride), (Jbeg, Jstride) = rows[tuple(chg_i)], cols[tuple(chg_j)]
-            base = Ibeg * ld + Jbeg
-            slot = {("i", 0): Istride * ld, ("i", 1): ld, ("j", 0): Jstride, ("j", 1): 1}
+            if det == "bra":          # vector over bra product states; every ket charge block adds into it (XR_term.py:122-133)
+                base, slot = Ibeg, {("i", 0): Istride, ("i", 1): 1}
+            elif det == "ket":        # vector over ket product states (XR_term.py:134-148)
+                base, slot = Jbeg, {("j", 0): Jstride, ("j", 1): 1}
+            else:
+                base = Ibeg * ld + Jbeg
+                slot = {("i", 0): Istride * ld, ("i", 1): ld, ("j", 0): Jstride, ("j", 1): 1}
             for frag_order, labels in active_diagrams.items():
                 # every ascending group of `frag_order` fragments of the dimer (XR_term.py:41-53)
                 groups = {0: [()], 1: [(0,), (1,)], 2: [(0, 1)]}.get(frag_order)
                 if groups is None:
                     raise NotImplementedError("dimer_matrix with diagrams of fragment order %r" % (frag_order,))
+                if det and frag_order != 2:
+                    raise NotImplementedError("bra_det / ket_det with diagrams of fragment order %r" % (frag_order,))
                 for frags in groups:
                     others = [x for x in (0, 1) if x not in frags]
                     if any(subsys_charges[x][0] != subsys_charges[x][1] for x in others):

@@ -14,12 +14,23 @@ from .util import struct
 
 
 def _build_block(diagram_term, permutation, bra_det, ket_det, label):
-    if bra_det or ket_det:
-        raise NotImplementedError("bra_det / ket_det blocks are not built yet (DESIGN.md, 'next')")
+    """diagrammatic_expansion.py:27-59 of the reference"""
     frag_order = len(permutation)
     if frag_order == 0:
         return diagram_term()
     reorder = [m for m in permutation] + [frag_order + m for m in permutation]
+    if bra_det and not ket_det:
+        if label == "u100":
+            return diagram_term(special_processing=reorder[0])       # transposition is handled inside the diagram
+        if frag_order == 2:
+            result = diagram_term(contract_last="ket")
+            return numpy.asarray(result).transpose(reorder[:2]) if len(result) else []
+    elif ket_det and not bra_det:
+        if label == "u100":
+            return diagram_term(special_processing=reorder[2])
+        if frag_order == 2:
+            result = diagram_term(contract_last="bra")
+            return numpy.asarray(result).transpose([i - 2 for i in reorder[:2]]) if len(result) else []
     return numpy.asarray(diagram_term()).transpose(reorder)
 
 
@@ -47,6 +58,8 @@ class _charges(object):
                 if term_permutation is not None:
                     term, permutation = term_permutation
                     result = _build_block(term, permutation, self._bra_det, self._ket_det, label)
+                    if (self._bra_det or self._ket_det) and numpy.ndim(result) > 0 and len(result) == 0:
+                        continue
                     if self._results[label] is None:
                         self._results[label] = result
                     else:
@@ -55,10 +68,10 @@ class _charges(object):
 
     def accumulate(self, label, out, offset, slot_strides, scale=1.0):
         """out += this block, where slot_strides[("i"|"j", subsystem slot)] is the element stride of that
-        slot's bra/ket state index inside `out` (plus optional "delta"/"n_delta" for spectator deltas).
-        Returns False when no permutation is charge-allowed."""
-        if self._bra_det or self._ket_det:
-            raise NotImplementedError("bra_det / ket_det blocks are not built yet (DESIGN.md, 'next')")
+        slot's bra/ket state index inside `out` (plus optional "delta"/"n_delta" for spectator deltas).  With
+        bra_det (ket_det) only the bra (ket) strides are used: the other pair is traced (diagrammatic_expansion.py:33-56).
+        Returns False when no permutation is charge-allowed (or no trace exists)."""
+        det = "ket" if (self._bra_det and not self._ket_det) else ("bra" if (self._ket_det and not self._bra_det) else False)
         added = False
         for term_permutation in self._get_terms(label):
             if term_permutation is None:
@@ -68,13 +81,20 @@ class _charges(object):
                 raise NotImplementedError("diagram '%s' has no in-place form" % label)
             strides = {}
             for d, slot in enumerate(permutation):
-                strides["i%d" % d] = slot_strides[("i", slot)]
-                strides["j%d" % d] = slot_strides[("j", slot)]
+                for side in ("i", "j"):
+                    if (side, slot) in slot_strides:
+                        strides["%s%d" % (side, d)] = slot_strides[(side, slot)]
             for key in ("delta", "n_delta"):
                 if key in slot_strides:
                     strides[key] = slot_strides[key]
-            term.accumulate_into(out, offset, strides, scale)
-            added = True
+            kw = {}
+            if det and len(permutation) == 2:
+                if label == "u100":
+                    kw["special_processing"] = permutation[0] if det == "ket" else 2 + permutation[0]
+                else:
+                    kw["contract_last"] = det
+            if term.accumulate_into(out, offset, strides, scale, **kw) is not False:
+                added = True
         return added
 
 

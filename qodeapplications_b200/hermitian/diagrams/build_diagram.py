@@ -22,10 +22,11 @@ def build_diagram(contraction, Dchgs, permutations):
                 result = phase * contraction(X, **args)
                 supersys_info.timings.record(label)
                 return result
-            def accumulate_into(out, offset, strides, scale=1.0):
+            def accumulate_into(out, offset, strides, scale=1.0, **args):
                 supersys_info.timings.start()
-                contraction.accumulate(X, phase * scale, out, offset, strides)
+                added = contraction.accumulate(X, phase * scale, out, offset, strides, **args)
                 supersys_info.timings.record(label)
+                return added
             do_contraction.accumulate_into = accumulate_into if hasattr(contraction, "accumulate") else None
             do_contraction.phase = phase
             return do_contraction

@@ -80,10 +80,26 @@ ONE_FRAGMENT = {
 }
 
 
-def _require_plain(contract_last):
+def _state_axes(contract_last):
+    """diagram_hack.state_indices (:26-33): the free state axes of the result and the renaming that makes the two
+    ket (or bra) state indices one contracted label when the last pair is traced"""
+    if contract_last == "ket":
+        return {"j0": "z", "j1": "z"}, ["i0", "i1"]
+    if contract_last == "bra":
+        return {"i0": "z", "i1": "z"}, ["j0", "j1"]
     if contract_last:
-        raise NotImplementedError("contract_last (bra_det/ket_det gradient variants, diagram_hack.py:26-41) is not "
-                                  "built yet; see DESIGN.md 'next'")
+        raise ValueError("contract_last must be False, 'ket' or 'bra'")
+    return {}, ["i0", "i1", "j0", "j1"]
+
+
+def no_result(X, contract):
+    """diagram_hack.no_result (:35-41): a trace over two state indices of different length does not exist"""
+    (i0s, j0s), (i1s, j1s) = X.n_states[0], X.n_states[1]
+    if contract == "ket":
+        return j0s != j1s
+    if contract == "bra":
+        return i0s != i1s
+    return False
 
 
 def _contractor(X):
@@ -99,26 +115,32 @@ def _state_labels(name):
 def make_two_fragment(label):
     coef, shift, operands = TWO_FRAGMENT[label]
 
-    def factors(X):
+    def factors(X, contract_last):
+        rename, free_axes = _state_axes(contract_last)
         out = []
         for name, free in operands:
             T = getattr(X, name)
             if T is None:
                 raise RuntimeError("diagram %s: operand %s is not available for these charges" % (label, name))
-            out.append((T, _state_labels(name) + list(free)))
+            out.append((T, [rename.get(l, l) for l in _state_labels(name)] + list(free)))
         factor = float(coef) if shift is None else float(coef) * (-1.0) ** (X.n_j0 + shift)
-        return out, factor
+        return out, factor, free_axes
 
     def contraction(X, contract_last=False):
-        _require_plain(contract_last)
-        ops, factor = factors(X)
-        return _contractor(X).multi_contract(ops, ["i0", "i1", "j0", "j1"], alpha=factor).host()
+        if no_result(X, contract_last):
+            return []
+        ops, factor, free_axes = factors(X, contract_last)
+        return _contractor(X).multi_contract(ops, free_axes, alpha=factor).host()
 
-    def accumulate(X, phase, out, offset, strides):
-        """out[offset + i0*strides['i0'] + i1*strides['i1'] + j0*strides['j0'] + j1*strides['j1']] += phase * diagram"""
-        ops, factor = factors(X)
-        _contractor(X).multi_contract(ops, ["i0", "i1", "j0", "j1"], alpha=phase * factor, out=out, out_offset=offset,
-                                      out_strides=strides, accumulate=True)
+    def accumulate(X, phase, out, offset, strides, contract_last=False):
+        """out[offset + sum over free state axes a of a*strides[a]] += phase * diagram; free axes are i0,i1,j0,j1, or
+        only i0,i1 / j0,j1 when the ket / bra pair is traced (contract_last).  False if that trace does not exist."""
+        if no_result(X, contract_last):
+            return False
+        ops, factor, free_axes = factors(X, contract_last)
+        _contractor(X).multi_contract(ops, free_axes, alpha=phase * factor, out=out, out_offset=offset,
+                                      out_strides={a: strides[a] for a in free_axes}, accumulate=True)
+        return True
 
     contraction.__name__ = label
     contraction.accumulate = accumulate
@@ -149,27 +171,82 @@ def make_one_fragment(label):
     return contraction
 
 
+def _u100_pieces(X, special_processing):
+    """SU_2mer_0.py:37-96.  Returns (res, K, free axes, transpose?) for the traced variants: with
+    res[i0,j0] = sum_pq ca0[i0,j0,p,q] U[frag1,frag0,frag0][p,q],
+      bra_det (special_processing 0/1): out[i0,i1] = res[i0,i1]                 if N_i1 == N_j1
+                                                   = sum_z res[i0,z] K[z,i1]    otherwise   (K = KetCoeffs1[j1,i1])
+      ket_det (special_processing 2/3): out[j0,j1] = res[j1,j0]                 if N_i1 == N_j1
+                                                   = sum_z res[z,j0] K[z,j1]    otherwise   (K = KetCoeffs1[i1,j1])
+    and the odd values (1, 3) return the transposed array (the reference transposes inside the diagram)."""
+    (i0s, j0s), (i1s, j1s) = X.n_states[0], X.n_states[1]
+    which = "ket" if special_processing <= 1 else "bra"
+    if no_result(X, which):
+        return None
+    res = X.ca0pq_U1pq
+    K = None if i1s == j1s else X.KetCoeffs1
+    if K is None and i1s != j1s:
+        raise RuntimeError("u100: KetCoeffs are needed when bra and ket state counts differ")
+    return res, K, which
+
+
 def u100(X, special_processing=None):
-    """delta(i1,j1) * sum_pq ca0[i0,j0,p,q] U[frag1, frag0, frag0][p,q]   (SU_2mer_0.py:26-48)"""
-    if special_processing is not None:
-        raise NotImplementedError("u100 special_processing (bra_det/ket_det) is not built yet")
+    """delta(i1,j1) * sum_pq ca0[i0,j0,p,q] U[frag1, frag0, frag0][p,q]   (SU_2mer_0.py:26-96)"""
     (i0s, j0s), (i1s, j1s) = X.n_states[0], X.n_states[1]
-    block = X.ca0pq_U1pq.host()
-    result = numpy.zeros((i0s, i1s, j0s, j1s))
-    for i1 in range(min(i1s, j1s)):
-        result[:, i1, :, i1] = block
-    return result
+    if special_processing is None:
+        block = X.ca0pq_U1pq.host()
+        result = numpy.zeros((i0s, i1s, j0s, j1s))
+        for i1 in range(min(i1s, j1s)):
+            result[:, i1, :, i1] = block
+        return result
+    if special_processing not in (0, 1, 2, 3):
+        raise ValueError("special processing %r can not be handled" % (special_processing,))
+    pieces = _u100_pieces(X, special_processing)
+    if pieces is None:
+        return []
+    res, K, which = pieces
+    res = res.host()
+    if which == "ket":
+        out = res if K is None else res @ K.host()
+    else:
+        out = res.T if K is None else res.T @ K.host()
+    return out.T if special_processing in (1, 3) else out
 
 
-def _u100_accumulate(X, phase, out, offset, strides):
-    (i0s, j0s), (i1s, j1s) = X.n_states[0], X.n_states[1]
+def _u100_accumulate(X, phase, out, offset, strides, special_processing=None):
     C = _contractor(X)
-    n_delta = min(i1s, j1s)
-    ones = C.dev.upload(numpy.ones((n_delta, 1)))
-    C.contract(X.ca0pq_U1pq, ["i0", "j0"], DeviceTensor(ones, C.dev), ["d", "one"], ["i0", "j0", "d", "one"], alpha=phase,
-               out=out, out_offset=offset,
-               out_strides={"i0": strides["i0"], "j0": strides["j0"], "d": strides["i1"] + strides["j1"], "one": 0},
-               accumulate=True)
+    if special_processing is None:
+        (i0s, j0s), (i1s, j1s) = X.n_states[0], X.n_states[1]
+        n_delta = min(i1s, j1s)
+        ones = C.dev.upload(numpy.ones((n_delta, 1)))
+        C.contract(X.ca0pq_U1pq, ["i0", "j0"], DeviceTensor(ones, C.dev), ["d", "one"], ["i0", "j0", "d", "one"], alpha=phase,
+                   out=out, out_offset=offset,
+                   out_strides={"i0": strides["i0"], "j0": strides["j0"], "d": strides["i1"] + strides["j1"], "one": 0},
+                   accumulate=True)
+        return True
+    pieces = _u100_pieces(X, special_processing)
+    if pieces is None:
+        return False
+    res, K, which = pieces
+    # (the odd special_processing values only say that the diagram's fragments are swapped with respect to the
+    #  subsystem; here that is already expressed by which subsystem slot strides['i0'] / strides['i1'] point at)
+    if which == "ket":
+        a, b = "i0", "i1"
+        if K is None:
+            C.multi_contract([(res, [a, b])], [a, b], alpha=phase, out=out, out_offset=offset,
+                             out_strides={a: strides[a], b: strides[b]}, accumulate=True)
+        else:
+            C.contract(res, [a, "z"], K, ["z", b], [a, b], alpha=phase, out=out, out_offset=offset,
+                       out_strides={a: strides[a], b: strides[b]}, accumulate=True)
+    else:
+        a, b = "j0", "j1"
+        if K is None:
+            C.multi_contract([(res, [b, a])], [a, b], alpha=phase, out=out, out_offset=offset,
+                             out_strides={a: strides[a], b: strides[b]}, accumulate=True)
+        else:
+            C.contract(res, ["z", a], K, ["z", b], [a, b], alpha=phase, out=out, out_offset=offset,
+                       out_strides={a: strides[a], b: strides[b]}, accumulate=True)
+    return True
 
 
 u100.accumulate = _u100_accumulate

@@ -3,11 +3,13 @@
     get_xr_H(ints=(symm_ints, bior_ints, nuc_rep), dens=[rho0, rho1], xr_order, monomer_charges,
              bra_det=False, ket_det=False) -> (H1, H2)
 
+With ``bra_det`` (``ket_det``) and xr_order 0, H2 is the VECTOR over bra (ket) product states in the same final
+ordering (get_xr_result.py:343-348), as StateSpaceOptimizer/state_gradients.py:173,183 consumes it.
+
 H1 = [monomer matrix of fragment 0, of fragment 1]; H2 = dimer matrix with rows/columns ordered as
 (global state of fragment 0, global state of fragment 1), states of a fragment ordered by the charges of
-``monomer_charges`` (get_xr_result.py:300-353).  Orders 0 and 1 are built (order 2 needs the 28
-second-order diagrams and rank-6 densities: NotImplementedError for now, like the reference does
-for orders it does not know, :298).
+``monomer_charges`` (get_xr_result.py:300-353).  xr_order 0, 1 and 2 are built -- everything the reference's
+get_xr_H implements; any other order raises NotImplementedError as the reference does (:298).
 
 All matrices are assembled in HBM directly in the final ordering, so the reference's O(dim^4)
 Python reorder loop disappears; ``S2inv @ S2H2`` runs through xr_gemm_scatter.  The inverse of the
@@ -33,8 +35,10 @@ def precise_numpy_inverse(M):
 
 
 def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False, device=None):
-    if bra_det or ket_det:
-        raise NotImplementedError("bra_det / ket_det variants are not built yet (DESIGN.md 'next')")
+    if bra_det and ket_det:
+        raise NotImplementedError("bra_det and ket_det together")
+    if (bra_det or ket_det) and xr_order != 0:
+        raise NotImplementedError("bra_det / ket_det are built for xr_order 0 (two-fragment diagrams) only")
     diag_timer, precon_timer, matrix_timer = timer(), timer(), timer()
     symm_ints, bior_ints, nuc_rep = ints
     dev = device or default_device()
@@ -43,7 +47,8 @@ def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False
 
     def make(integrals, diagrams):
         return diagrammatic_expansion.blocks(densities=dens, integrals=integrals, diagrams=diagrams,
-                                             contract_cache=contract_cache, timings=diag_timer, precon_timings=precon_timer)
+                                             contract_cache=contract_cache, timings=diag_timer, precon_timings=precon_timer,
+                                             bra_det=bra_det and diagrams is not S_diagrams, ket_det=ket_det and diagrams is not S_diagrams)
     S = symm_ints.S
     S_blocks = make(S, S_diagrams)
     ST_symm, SU_symm, SV_symm = make(struct(S=S, T=symm_ints.T), ST_diagrams), make(struct(S=S, U=symm_ints.U), SU_diagrams), make(struct(S=S, V=symm_ints.V), SV_diagrams)
@@ -63,8 +68,8 @@ def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False
     def dimer_sum(terms, into=None, scale=1.0):
         """sum of dimer matrices, each term accumulated in place by its own GEMM epilogues"""
         for op_blocks, active in terms:
-            into = XR_term.dimer_matrix(op_blocks, active, (0, 1), all_dimer_charges, matrix_timer, ordering="final",
-                                        device_result=True, into=into, scale=scale)
+            into = XR_term.dimer_matrix(op_blocks, active, (0, 1), all_dimer_charges, matrix_timer, bra_det=bra_det,
+                                        ket_det=ket_det, ordering="final", device_result=True, into=into, scale=scale)
         return into
 
     if xr_order == 0:                                   # get_xr_result.py:86-132

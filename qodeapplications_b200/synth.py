@@ -24,6 +24,7 @@ import numpy
 CONFIGS = {
     "toy":  dict(n_frag=2, n_orb=6,  n_states={0: 3,   +1: 2,   -1: 2}),
     "toy3": dict(n_frag=3, n_orb=5,  n_states={0: 2,   +1: 2,   -1: 2}),
+    "toy5": dict(n_frag=3, n_orb=4,  n_states={0: 2, +1: 2, -1: 2, +2: 1, -2: 1}),   # five charge states (general-XRCC/Be631g.py:73)
     "mid":  dict(n_frag=2, n_orb=8,  n_states={0: 5,   +1: 3,   -1: 4}),
     "cfg1": dict(n_frag=2, n_orb=18, n_states={0: 11,  +1: 4,   -1: 8}),
     "cfg2": dict(n_frag=2, n_orb=18, n_states={0: 11,  +1: 4,   -1: 8}),
@@ -31,7 +32,7 @@ CONFIGS = {
     "cfg4": dict(n_frag=4, n_orb=18, n_states={0: 96,  +1: 34,  -1: 70}),
     "cfg5": dict(n_frag=2, n_orb=48, n_states={0: 478, +1: 174, -1: 348}),
 }
-SEEDS = {"toy": 11, "toy3": 13, "mid": 17, "cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}
+SEEDS = {"toy": 11, "toy3": 13, "mid": 17, "toy5": 19, "cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}
 N_ELEC_REF = 4
 
 OPS_ORDER0 = ("a", "c", "aa", "cc", "ca", "caa", "cca", "ccaa")
@@ -158,6 +159,46 @@ def make_integrals(n_frag, n_orb, rng, with_bior=False):
                         U=blocked_integrals(Ub, n_orb, lead_blocks=True), V=blocked_integrals(Vb, n_orb),
                         V_half=blocked_integrals(Vh, n_orb), V_diff=blocked_integrals(Vh - V, n_orb))
     return symm, bior, nuc
+
+
+def make_det_densities(n_orb, n_states_bra, n_states_ket, rng, ops=OPS_ORDER0, n_elec_ref=N_ELEC_REF):
+    """Density dict of a fragment whose bras (or kets) are determinants (the "bra_det" / "ket_det" options of
+    Be-states/densities.py:96-99,214-231): rectangular [N_bra, N_ket, n...] blocks, every operator string drawn
+    independently (such densities are not symmetric, :205), plus KetCoeffs[(chg,chg)] = [N_states, N_dets]."""
+    rho = {}
+    for op in ops:
+        k, d = len(op), op_dchg(op)
+        rho[op] = {}
+        for ci in n_states_bra:
+            cj = ci - d
+            if cj not in n_states_ket:
+                continue
+            t = rng.standard_normal((n_states_bra[ci], n_states_ket[cj]) + (n_orb,) * k) * n_orb ** (-k / 2)
+            rho[op][(ci, cj)] = antisymmetrize(t, op)
+    rho["n_elec"] = {chg: n_elec_ref - chg for chg in n_states_ket}
+    rho["n_states"] = dict(n_states_ket)
+    rho["n_states_bra"] = dict(n_states_bra)
+    rho["KetCoeffs"] = {}
+    for chg in n_states_ket:
+        n_det, n_st = max(n_states_bra[chg], n_states_ket[chg]), min(n_states_bra[chg], n_states_ket[chg])
+        rho["KetCoeffs"][(chg, chg)] = rng.standard_normal((n_st, n_det))
+    return rho
+
+
+def make_det_system(which, n_orb=6, n_states=None, n_dets=None, seed=23):
+    """2-fragment toy for the bra_det / ket_det variants: fragment 0 has determinant bras (which="bra") or kets
+    (which="ket"), fragment 1 is an ordinary fragment."""
+    n_states = n_states or {0: 3, +1: 2, -1: 2}
+    n_dets = n_dets or {0: 4, +1: 3, -1: 3}
+    rng = numpy.random.default_rng(seed)
+    symm, bior, nuc = make_integrals(2, n_orb, rng, with_bior=True)
+    if which == "bra":
+        rho0 = make_det_densities(n_orb, n_dets, n_states, rng)
+    else:
+        rho0 = make_det_densities(n_orb, n_states, n_dets, rng)
+    rho1 = make_densities(n_orb, n_states, rng)
+    return dict(n_frag=2, n_orb=n_orb, n_states=dict(n_states), charges=list(n_states), densities=[rho0, rho1],
+                symm=symm, bior=bior, nuc=nuc)
 
 
 def make_densities(n_orb, n_states, rng, ops=OPS_ORDER0, n_elec_ref=N_ELEC_REF, dtype=numpy.float64):

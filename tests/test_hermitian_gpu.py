@@ -154,3 +154,17 @@ def test_permute_copy(dev):
     order = [3, 1, 0, 2]
     dev.ctx.permute_copy(out, dA, [a.shape[k] for k in order], [strides[k] for k in order], -2.0)
     assert numpy.array_equal(dev.download(out), -2.0 * a.transpose(order))
+
+
+@pytest.mark.parametrize("which", ["bra", "ket"])
+def test_det_variants_match_reference_golden(dev, which):
+    """get_xr_H(bra_det=True) / (ket_det=True) at xr_order 0 against the reference's own output"""
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_det_%s.npz" % which))
+    system = synth.make_det_system(which)
+    charges = system["charges"]
+    H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), system["densities"], 0, [charges, charges],
+                      bra_det=(which == "bra"), ket_det=(which == "ket"), device=dev)
+    _close(H1[0], g["H1_0"])
+    _close(H1[1], g["H1_1"])
+    _close(H2, g["H2"])

@@ -19,7 +19,7 @@ def _close(a, b, tol=1e-10):
     assert numpy.abs(a - b).max() <= tol * scale, (numpy.abs(a - b).max(), scale)
 
 
-@pytest.mark.parametrize("name", ["toy", "toy3"])
+@pytest.mark.parametrize("name", ["toy", "toy3", "toy5"])
 def test_general_blocks_host_logic(name):
     from qodeapplications_b200.general.build_H import build_matrix_elements
     g = numpy.load(os.path.join(GOLDEN, "general_%s.npz" % name))
@@ -125,3 +125,19 @@ def test_hermitian_dimer_matrix_blocked_ordering(toy1):
     symm = toy1["symm"]
     ref = ho.dimer_matrix(toy1["densities"], ho.integrals(symm.S, V=symm.V), {1: ["v0000"], 2: ["v0101", "v0001", "v0100", "v0011"]}, charges)
     _close(got, ref)
+
+
+@pytest.mark.parametrize("which", ["bra", "ket"])
+def test_hermitian_det_variants_host_logic(which):
+    """get_xr_H(..., bra_det=True) / (ket_det=True): traced two-fragment diagrams, u100 special processing, vector result
+    (StateSpaceOptimizer/state_gradients.py:173,183) against the reference's own output"""
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_det_%s.npz" % which))
+    system = synth.make_det_system(which)
+    charges = system["charges"]
+    H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), system["densities"], 0, [charges, charges],
+                      bra_det=(which == "bra"), ket_det=(which == "ket"), device=FakeDevice())
+    _close(H1[0], g["H1_0"])
+    _close(H1[1], g["H1_1"])
+    assert numpy.count_nonzero(g["H2"]) > 20
+    _close(H2, g["H2"])
