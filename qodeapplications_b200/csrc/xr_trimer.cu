@@ -21,9 +21,7 @@
 
 namespace {
 
-constexpr int TA = 8, TB = 16, ROWS = TA * TB, CT = 128;
-constexpr int CONSUMER_WARPS = 8, CONSUMER_THREADS = CONSUMER_WARPS * 32;
-constexpr int THREADS = CONSUMER_THREADS + 128;   // + one producer warpgroup (register allocation is per 4 warps)
+constexpr int TA = 8, TB = 16, ROWS = TA * TB;
 
 struct TrimerParams {
     int n;
@@ -45,8 +43,15 @@ struct TrimerParams {
     int c_tiles;
 };
 
-template <int KS, int TAIL>
+// WN = consumer warps along c: 2 -> 8 warps, each 32 rows x 64 columns (128-column gamma tiles, 240 registers);
+//                              3 -> 12 warps, each 32 rows x 32 columns (96-column tiles, 152 registers, 3 warps per scheduler)
+template <int KS, int TAIL, int WN>
 struct TrimerCfg {
+    static constexpr int NJ = WN == 2 ? 8 : 4;                                    // 8-column DMMA blocks per warp
+    static constexpr int CT = WN * NJ * 8;                                        // gamma rows (= T columns) per tile
+    static constexpr int CONSUMER_WARPS = 4 * WN, CONSUMER_THREADS = CONSUMER_WARPS * 32;
+    static constexpr int THREADS = CONSUMER_THREADS + 128;                        // + one producer warpgroup (register allocation is per 4 warps)
+    static constexpr int CONSUMER_REGS = WN == 2 ? 240 : 152, PRODUCER_REGS = 24;
     static constexpr int KP = 4 * KS + (TAIL ? 4 : 0);                            // packed row width (k, zero padded)
     static constexpr int GS = (KP % 16 == 4 || KP % 16 == 12) ? KP : KP + 4;       // conflict-free fragment stride
     static constexpr bool AREG = KS <= 5;                                         // A fragments live in registers
@@ -55,19 +60,21 @@ struct TrimerCfg {
                                    2 * SLOTS * sizeof(uint64_t) + 64;
 };
 
-__device__ __forceinline__ void consumer_barrier() {   // named barrier 1: the 8 consumer warps only
+template <int CONSUMER_THREADS>
+__device__ __forceinline__ void consumer_barrier() {   // named barrier 1: the consumer warps only
     asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_THREADS) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int KS, int TAIL>
-__global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerParams p) {
-    using Cfg = TrimerCfg<KS, TAIL>;
-    constexpr int KP = Cfg::KP, GS = Cfg::GS, SLOTS = Cfg::SLOTS;
+template <int KS, int TAIL, int WN>
+__global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_stream_kernel(const TrimerParams p) {
+    using Cfg = TrimerCfg<KS, TAIL, WN>;
+    constexpr int KP = Cfg::KP, GS = Cfg::GS, SLOTS = Cfg::SLOTS, CT = Cfg::CT;
+    constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS, CONSUMER_THREADS = Cfg::CONSUMER_THREADS;
     constexpr bool AREG = Cfg::AREG;
-    constexpr int MI = 4, NJ = 8;
+    constexpr int MI = 4, NJ = Cfg::NJ, WCOLS = NJ * 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* Gs = reinterpret_cast<double*>(smem_raw);                  // [SLOTS][CT][GS]  (bulk-copy destinations: 16B aligned)
     double* Gt = Gs + SLOTS * CT * GS;                                  // [SLOTS][CT][2]   tail columns, compact
@@ -95,7 +102,7 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
 
     if (warp >= CONSUMER_WARPS) {
         // -------------------------------------------------- producer warpgroup (one lane works)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");     // hand registers to the consumers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::PRODUCER_REGS));     // hand registers to the consumers
         if (warp == CONSUMER_WARPS && lane == 0) {
             int ct = 0;
             for (int64_t q = 0; q < total_tiles; ++q) {
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
     }
 
     // ---------------------------------------------------------------------- consumer warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::CONSUMER_REGS));
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
     double s1p[NJ], s2p[NJ];     // NJ independent chains each: the moment epilogue must not be one serial FP64 dependency
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
         const int64_t a0 = p.a_begin + (item / p.tiles_b) * TA;
         const int64_t b0 = (item % p.tiles_b) * TB;
 
-        consumer_barrier();    // every consumer is done with the previous item's Xs
+        consumer_barrier<CONSUMER_THREADS>();    // every consumer is done with the previous item's Xs
         // X[(a,b), s] = sum_r W[a, r*n + s] * beta[b, r]
         for (int idx = tid; idx < ROWS * KP; idx += CONSUMER_THREADS) {
             const int row = idx / KP, s = idx - row * KP;
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
             }
             Xs[row * GS + s] = v;
         }
-        consumer_barrier();
+        consumer_barrier<CONSUMER_THREADS>();
 
         const double* xs = Xs + (32 * wm + g) * GS + t;
         double areg[AREG ? MI : 1][AREG ? KS : 1];
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
 
             double acc[MI][NJ][2];
             const double* gtile = Gs + (size_t)slot * CT * GS;
-            const double* gs = gtile + (64 * wn + g) * GS + t;
+            const double* gs = gtile + (WCOLS * wn + g) * GS + t;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 double b[NJ];
@@ -184,7 +191,7 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
                 // leftover k (n - 4*KS <= 2) on the accumulator layout: lane owns rows 8i+g, columns 8j+2t+{0,1}.
                 // The tail columns come from the compact [c][2] copy: a quad's four 32-byte reads cover 128
                 // contiguous bytes (no bank conflicts; the strided [c][GS] rows would give 2-way conflicts).
-                const double2* gt = reinterpret_cast<const double2*>(Gt + (size_t)slot * CT * 2) + 64 * wn + 2 * t;
+                const double2* gt = reinterpret_cast<const double2*>(Gt + (size_t)slot * CT * 2) + WCOLS * wn + 2 * t;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
 #pragma unroll
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) s2p[j] = fma(acc[i][j][1], acc[i][j][1], s2p[j]);
             } else {
-                const int64_t c_base = (int64_t)ct * CT + 64 * wn + 2 * t;
+                const int64_t c_base = (int64_t)ct * CT + WCOLS * wn + 2 * t;
 #pragma unroll
                 for (int i = 0; i < MI; ++i) {
                     const int row = 32 * wm + 8 * i + g;
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) trimer_stream_kernel(const TrimerP
             red[0][warp] = s1;
             red[1][warp] = s2;
         }
-        consumer_barrier();
+        consumer_barrier<CONSUMER_THREADS>();
         if (tid == 0) {
             double t1 = 0.0, t2 = 0.0;
             for (int w = 0; w < CONSUMER_WARPS; ++w) {
@@ -273,10 +280,11 @@ __global__ void trimer_finalize_kernel(const double* partials, int count, double
     }
 }
 
-template <int KS, int TAIL>
+template <int KS, int TAIL, int WN = 2>
 int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbeta, const double* gamma, int64_t ldgamma,
                   double* moments) {
-    using Cfg = TrimerCfg<KS, TAIL>;
+    using Cfg = TrimerCfg<KS, TAIL, WN>;
+    constexpr int CT = Cfg::CT;
     const int64_t n_a = p.a_end - p.a_begin;
     const int64_t tiles_a = (n_a + TA - 1) / TA;
     p.tiles_b = (p.Pb + TB - 1) / TB;
@@ -312,9 +320,9 @@ int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbet
     p.gammaT = gammaT;
     p.partials = partials;
 
-    auto kernel = trimer_stream_kernel<KS, TAIL>;
+    auto kernel = trimer_stream_kernel<KS, TAIL, WN>;
     XR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    kernel<<<grid, THREADS, Cfg::SMEM, ctx->stream>>>(p);
+    kernel<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(p);
     XR_CUDA(cudaGetLastError());
     ctx->launches++;
     if (p.mode == XR_TRIMER_REDUCE) {
@@ -364,6 +372,8 @@ extern "C" int xr_trimer_stream(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int6
     if (n == 5) return launch_trimer<1, 1>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
     if (n == 6) return launch_trimer<1, 2>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
     if (n <= 8) return launch_trimer<2, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+    // (WN = 3, i.e. 12 consumer warps with 32x32 warp tiles, was measured too: 29.1 vs 29.9 TFLOP/s for WN = 2 at
+    //  n = 18 on B200 -- the kernel is bound by its DMMA:DFMA instruction mix, not by warp-level latency hiding)
     if (n == 18) return launch_trimer<4, 2>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
     if (n <= 20) return launch_trimer<5, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
     return launch_trimer<12, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
