@@ -318,7 +318,7 @@ def run_xr(args):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     achieved = tri_flops / (tri_ms * 1e-3) / 1e12 if tri_ms else None
     roofline = {
-        "bound": "tensor", "kernel": "trimer_stream_kernel<5> (FP64 DMMA.8x8x4)", "achieved": achieved, "peak": peak,
+        "bound": "tensor", "kernel": "trimer_stream_kernel<4,2,2> (FP64 DMMA.8x8x4 + DFMA k-tail, TMA-fed)", "achieved": achieved, "peak": peak,
         "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
         "peak_source": "measured on this pool's B200: DMMA.8x8x4 issue-rate microbenchmark tools/fp64_peaks.cu "
                        "(profiles/r01_fp64_peaks.json; cuBLAS DGEMM 8192^3 reaches 35.5). MEASURED_PEAKS.json has no FP64 entry "
