@@ -1,0 +1,186 @@
+// xr_gemm_scatter, tensor-map TMA variant (used for 16-byte-aligned operands).
+//
+// Same math and epilogue as gemm_nt_scatter_kernel (xr_gemm.cu); the difference is how the A[BM x BK] and
+// B[BN x BK] operand tiles reach shared memory: ONE elected thread issues two cp.async.bulk.tensor.2d loads
+// (SASS UTMALDG) per k-tile against tensor maps that describe A as [M rows][K] and B as [N rows][K]; the
+// copies complete on an mbarrier with a transaction count.  TMA zero-fills everything outside the tensor, so
+// the K tail (K = 326 = 20*16 + 6, K = 36, ...) and the M/N tails need no per-thread predication or source
+// clamping at all.  Tiles are 64 rows x 16 doubles = 64 x 128 bytes and are stored with the 128-byte swizzle:
+// the 16-byte chunk c of row r sits at chunk (c ^ (r & 7)), which keeps the 8-row x 4-k DMMA fragment reads to
+// at most 2-way bank conflicts without padding bytes.
+#include "xr_common.cuh"
+#include <cuda.h>
+
+namespace {
+
+struct GemmTmaParams {
+    int64_t M, N, K;
+    double alpha;
+    double* C;
+    const int64_t* offM;
+    int64_t ldc;
+    const int64_t* offN;
+    int accumulate;
+    int64_t tiles_n;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+constexpr int TBM = 64, TBN = 64, TBK = 16, TSTAGES = 3, TTHREADS = 128;
+constexpr int TILE_A_BYTES = TBM * TBK * 8, TILE_B_BYTES = TBN * TBK * 8;     // 8 KB each, 1024-byte aligned
+constexpr size_t TMA_SMEM = (size_t)TSTAGES * (TILE_A_BYTES + TILE_B_BYTES) + 1024;
+
+// byte offset of element (row r, k) inside a 128-byte-swizzled [rows][16 doubles] tile
+__device__ __forceinline__ int swz(int r, int k) { return r * 128 + ((((k >> 1) ^ (r & 7)) << 4) | ((k & 1) << 3)); }
+
+__global__ void __launch_bounds__(TTHREADS, 4)
+gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmTmaParams p) {
+    constexpr int MI = 4, NJ = 4;      // 2 x 2 warps, each 32 x 32
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[TSTAGES];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int warp_m = warp & 1, warp_n = warp >> 1;
+    const int64_t tile = blockIdx.x;
+    const int64_t m0 = (tile / p.tiles_n) * TBM, n0 = (tile % p.tiles_n) * TBN;
+    const int KT = (int)((p.K + TBK - 1) / TBK);
+
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int kt) {      // one thread: arm the barrier with the byte count, then the two tensor copies
+        const int s = kt % TSTAGES;
+        unsigned char* a = smem + (size_t)s * (TILE_A_BYTES + TILE_B_BYTES);
+        mbar_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
+        tma_load_2d(a, &mapA, kt * TBK, (int)m0, &full[s]);
+        tma_load_2d(a + TILE_A_BYTES, &mapB, kt * TBK, (int)n0, &full[s]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES - 1 && s < KT; ++s) issue(s);
+    }
+
+    double acc[MI][NJ][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % TSTAGES;
+        mbar_wait(&full[s], (uint32_t)(kt / TSTAGES) & 1);
+        __syncthreads();                                   // every warp has finished reading stage (kt-1) % TSTAGES
+        if (tid == 0 && kt + TSTAGES - 1 < KT) issue(kt + TSTAGES - 1);
+        const unsigned char* as = smem + (size_t)s * (TILE_A_BYTES + TILE_B_BYTES);
+        const unsigned char* bs = as + TILE_A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < TBK / 4; ++ks) {
+            double a[MI], b[NJ];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const double*>(as + swz(warp_m * 32 + i * 8 + g, ks * 4 + t));
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double*>(bs + swz(warp_n * 32 + j * 8 + g, ks * 4 + t));
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+
+    // epilogue (identical to gemm_nt_scatter_kernel): lane holds C[8i+g][8j+2t], C[8i+g][8j+2t+1]
+    int64_t on[NJ][2];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        int64_t col = n0 + warp_n * 32 + j * 8 + 2 * t;
+        on[j][0] = col < p.N ? (p.offN ? p.offN[col] : col) : -1;
+        on[j][1] = col + 1 < p.N ? (p.offN ? p.offN[col + 1] : col + 1) : -1;
+    }
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        int64_t row = m0 + warp_m * 32 + i * 8 + g;
+        if (row >= p.M) continue;
+        int64_t om = p.offM ? p.offM[row] : row * p.ldc;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            double* dst0 = p.C + om + on[j][0];
+            if (on[j][0] >= 0 && on[j][1] == on[j][0] + 1 && (reinterpret_cast<uintptr_t>(dst0) & 15) == 0) {
+                double2 v = make_double2(p.alpha * acc[i][j][0], p.alpha * acc[i][j][1]);
+                if (p.accumulate) {
+                    const double2 old = *reinterpret_cast<double2*>(dst0);
+                    v.x += old.x;
+                    v.y += old.y;
+                }
+                *reinterpret_cast<double2*>(dst0) = v;
+                continue;
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (on[j][e] < 0) continue;
+                double* dst = p.C + om + on[j][e];
+                double v = p.alpha * acc[i][j][e];
+                *dst = p.accumulate ? *dst + v : v;
+            }
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// [rows][K] row-major doubles with leading dimension ld -> 2-D tensor map, box = 16 (k) x 64 (rows), 128-byte swizzle
+bool make_map(CUtensorMap* map, const double* base, int64_t rows, int64_t K, int64_t ld) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)TBM};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estride,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// returns XR_ERR_UNSUPPORTED when the operands cannot be described by a tensor map (caller falls back to cp.async staging)
+int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                        const double* B, int64_t ldb, double* C, const int64_t* offM, int64_t ldc, const int64_t* offN,
+                        int accumulate) {
+    if (K < 1 || M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return XR_ERR_UNSUPPORTED;
+    CUtensorMap mapA, mapB;
+    if (!make_map(&mapA, A, M, K, lda) || !make_map(&mapB, B, N, K, ldb)) return XR_ERR_UNSUPPORTED;
+    GemmTmaParams p{M, N, K, alpha, C, offM, ldc, offN, accumulate, (N + TBN - 1) / TBN};
+    const int64_t tiles = ((M + TBM - 1) / TBM) * p.tiles_n;
+    XR_REQUIRE(tiles < (1ll << 31), "xr_gemm_scatter: too many tiles (%lld)", (long long)tiles);
+    XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+    gemm_tma_scatter_kernel<<<(unsigned)tiles, TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
+    XR_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return XR_OK;
+}
