@@ -25,6 +25,7 @@ CONFIGS = {
     "toy":  dict(n_frag=2, n_orb=6,  n_states={0: 3,   +1: 2,   -1: 2}),
     "toy3": dict(n_frag=3, n_orb=5,  n_states={0: 2,   +1: 2,   -1: 2}),
     "toy5": dict(n_frag=3, n_orb=4,  n_states={0: 2, +1: 2, -1: 2, +2: 1, -2: 1}),   # five charge states (general-XRCC/Be631g.py:73)
+    "toyh": dict(n_frag=2, n_orb=[6, 4], n_states={0: 3, +1: 2, -1: 2}),             # fragments with different orbital counts
     "mid":  dict(n_frag=2, n_orb=8,  n_states={0: 5,   +1: 3,   -1: 4}),
     "cfg1": dict(n_frag=2, n_orb=18, n_states={0: 11,  +1: 4,   -1: 8}),
     "cfg2": dict(n_frag=2, n_orb=18, n_states={0: 11,  +1: 4,   -1: 8}),
@@ -32,7 +33,7 @@ CONFIGS = {
     "cfg4": dict(n_frag=4, n_orb=18, n_states={0: 96,  +1: 34,  -1: 70}),
     "cfg5": dict(n_frag=2, n_orb=48, n_states={0: 478, +1: 174, -1: 348}),
 }
-SEEDS = {"toy": 11, "toy3": 13, "mid": 17, "toy5": 19, "cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}
+SEEDS = {"toy": 11, "toy3": 13, "mid": 17, "toy5": 19, "toyh": 29, "cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}
 N_ELEC_REF = 4
 
 OPS_ORDER0 = ("a", "c", "aa", "cc", "ca", "caa", "cca", "ccaa")
@@ -98,19 +99,23 @@ class blocked_integrals(object):
     """``X[m1, m2, ...]`` -> contiguous fragment block of one global tensor (cached)."""
     def __init__(self, full, n_orb, lead_blocks=None):
         self._full = full          # ndarray, or list of ndarrays when lead_blocks (U: one per nucleus fragment)
-        self._n = n_orb
+        self._n = n_orb            # int (homogeneous fragments) or list of per-fragment orbital counts
         self._lead = lead_blocks
         self._cache = {}
+    def _slice(self, m):
+        if isinstance(self._n, int):
+            return slice(m * self._n, (m + 1) * self._n)
+        lo = sum(self._n[:m])
+        return slice(lo, lo + self._n[m])
     def __getitem__(self, frags):
         if not isinstance(frags, tuple):
             frags = (frags,)
         if frags not in self._cache:
-            n = self._n
             if self._lead:
                 full, rest = self._full[frags[0]], frags[1:]
             else:
                 full, rest = self._full, frags
-            index = tuple(slice(m * n, (m + 1) * n) for m in rest)
+            index = tuple(self._slice(m) for m in rest)
             self._cache[frags] = numpy.ascontiguousarray(full[index])
         return self._cache[frags]
 
@@ -125,6 +130,8 @@ class integral_set(object):
 
 
 def make_integrals(n_frag, n_orb, rng, with_bior=False):
+    if not isinstance(n_orb, int):
+        return _make_integrals_hetero(list(n_orb), rng)
     dim = n_frag * n_orb
     def sym2():
         h = rng.standard_normal((dim, dim))
@@ -159,6 +166,20 @@ def make_integrals(n_frag, n_orb, rng, with_bior=False):
                         U=blocked_integrals(Ub, n_orb, lead_blocks=True), V=blocked_integrals(Vb, n_orb),
                         V_half=blocked_integrals(Vh, n_orb), V_diff=blocked_integrals(Vh - V, n_orb))
     return symm, bior, nuc
+
+
+def _make_integrals_hetero(n_orbs, rng):
+    """fragments with different orbital counts (general-XRCC's C kernels take n_orb1, n_orb2 separately)"""
+    dim = sum(n_orbs)
+    sym2 = lambda: (lambda h: (h + h.T) / 2)(rng.standard_normal((dim, dim)))
+    V = rng.standard_normal((dim,) * 4)
+    V = (V + V.transpose(1, 0, 3, 2)) / 2
+    V = (V + V.transpose(2, 3, 0, 1)) / 2 / max(n_orbs)
+    S = numpy.eye(dim) + 0.05 * sym2() * (1 - numpy.eye(dim))
+    symm = integral_set(S=blocked_integrals(S, n_orbs), T=blocked_integrals(sym2(), n_orbs),
+                        U=blocked_integrals([sym2() for _ in n_orbs], n_orbs, lead_blocks=True), V=blocked_integrals(V, n_orbs))
+    nuc = rng.standard_normal((len(n_orbs), len(n_orbs)))
+    return symm, (nuc + nuc.T) / 2
 
 
 def make_det_densities(n_orb, n_states_bra, n_states_ket, rng, ops=OPS_ORDER0, n_elec_ref=N_ELEC_REF):
@@ -286,7 +307,8 @@ def make_system(name=None, n_frag=None, n_orb=None, n_states=None, seed=None, op
         (symm, nuc), bior = ints, None
     if general_ccaa == "random":
         ops = tuple(op for op in ops if op != "ccaa")
-    dens = [make_densities(n_orb, n_states, rng, ops=ops) for _ in range(n_frag)]
+    orb_of = (lambda m: n_orb) if isinstance(n_orb, int) else (lambda m: n_orb[m])
+    dens = [make_densities(orb_of(m), n_states, rng, ops=ops) for m in range(n_frag)]
     frags = []
     for m in range(n_frag):
         grho = general_rho_from_hermitian(dens[m], symm.V[m, m, m, m])
