@@ -71,9 +71,53 @@ TWO_FRAGMENT.update({
     "s01s01v1111": (_H, None, [("cc0", "ijtv"), ("ccaaaa1", "klpqwusr"), ("s01", "tu"), ("s01", "vw"), ("v1111", "pqrs")]),
     "s01s10v0011": (-1, None, [("ccca0", "ijpqtw"), ("caaa1", "klvusr"), ("s01", "tu"), ("s10", "vw"), ("v0011", "pqrs")]),
 })
-for _n in "01":      # SU_2mer_2.py: the ST forms with t## -> u<n>_##
+# ---- S-orders 3 and 4 (S_2mer_{3,4}.py, ST_2mer_{3,4}.py, SV_2mer_{3,4}.py), the diagrams diagram_lists.py activates ----
+TWO_FRAGMENT.update({
+    "s01s01s10":         (1 / 2, 1, [("cca0", "ijpru"), ("caa1", "kltsq"), ("s01", "pq"), ("s01", "rs"), ("s10", "tu")]),
+    "s01s01s10s10":      (1 / 4, None, [("ccaa0", "ijprwu"), ("ccaa1", "kltvsq"), ("s01", "pq"), ("s01", "rs"), ("s10", "tu"), ("s10", "vw")]),
+    "s01s01s01s10":      (-1 / 6, None, [("ccca0", "ijprtw"), ("caaa1", "klvusq"), ("s01", "pq"), ("s01", "rs"), ("s01", "tu"), ("s10", "vw")]),
+    "s01s01s10t10":      (1 / 2, None, [("ccaa0", "ijtvyq"), ("ccaa1", "klpxwu"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("t10", "pq")]),
+    "s01s01s10t00":      (1 / 2, 0, [("cccaa0", "ijptvyq"), ("caa1", "klxwu"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("t00", "pq")]),
+    "s01s01s10t11":      (1 / 2, 0, [("cca0", "ijtvy"), ("ccaaa1", "klpxwuq"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("t11", "pq")]),
+    "s01s01s01t10":      (-1 / 6, None, [("ccca0", "ijtvxq"), ("caaa1", "klpywu"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("t10", "pq")]),
+    "s01s01s10t01":      (-1 / 2, None, [("ccca0", "ijptvy"), ("caaa1", "klxwuq"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("t01", "pq")]),
+    "s01s01s10s10t00":   (1 / 4, None, [("cccaaa0", "ijptvayq"), ("ccaa1", "klxzwu"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("s10", "za"), ("t00", "pq")]),
+    "s01s01s01s10t10":   (1 / 6, 0, [("cccaa0", "ijtvxaq"), ("ccaaa1", "klpzywu"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("s10", "za"), ("t10", "pq")]),
+    "s01s01s10s10t01":   (1 / 4, 0, [("cccaa0", "ijptvay"), ("ccaaa1", "klxzwuq"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("s10", "za"), ("t01", "pq")]),
+    "s01s01s01s10t00":   (-1 / 6, None, [("ccccaa0", "ijptvxaq"), ("caaa1", "klzywu"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("s10", "za"), ("t00", "pq")]),
+    "s01s01s01s10t11":   (-1 / 6, None, [("ccca0", "ijtvxa"), ("ccaaaa1", "klpzywuq"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("s10", "za"), ("t11", "pq")]),
+    "s01s01s10v0100":    (1, None, [("cccaaa0", "ijptvysr"), ("ccaa1", "klqxwu"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("v0100", "pqrs")]),
+    "s01s01s10v1101":    (-1, None, [("ccaa0", "ijtvyr"), ("cccaaa1", "klpqxwus"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("v1101", "pqrs")]),
+    "s01s01s01v1100":    (1 / 6, 0, [("cccaa0", "ijtvxsr"), ("ccaaa1", "klpqywu"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("v1100", "pqrs")]),
+    "s01s01s10v0000":    (1 / 2, 1, [("ccccaaa0", "ijpqtvysr"), ("caa1", "klxwu"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("v0000", "pqrs")]),
+    "s01s01s10v0101":    (2, 1, [("cccaa0", "ijptvyr"), ("ccaaa1", "klqxwus"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("v0101", "pqrs")]),
+    "s01s01s10v1100":    (1 / 2, 1, [("ccaaa0", "ijtvysr"), ("cccaa1", "klpqxwu"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("v1100", "pqrs")]),
+    "s01s01s10v1111":    (1 / 2, 1, [("cca0", "ijtvy"), ("cccaaaa1", "klpqxwusr"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("v1111", "pqrs")]),
+    "s01s01s01v0100":    (-1 / 3, None, [("ccccaa0", "ijptvxsr"), ("caaa1", "klqywu"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("v0100", "pqrs")]),
+    "s01s01s01v1101":    (1 / 3, None, [("ccca0", "ijtvxr"), ("ccaaaa1", "klpqywus"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("v1101", "pqrs")]),
+    "s01s01s10v0001":    (-1, None, [("ccccaa0", "ijpqtvyr"), ("caaa1", "klxwus"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("v0001", "pqrs")]),
+    "s01s01s10v0111":    (1, None, [("ccca0", "ijptvy"), ("ccaaaa1", "klqxwusr"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("v0111", "pqrs")]),
+    "s01s01s01s10v1100": (-1 / 6, None, [("cccaaa0", "ijtvxasr"), ("cccaaa1", "klpqzywu"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("s10", "za"), ("v1100", "pqrs")]),
+    "s01s01s10s10v0000": (1 / 4, None, [("ccccaaaa0", "ijpqtvaysr"), ("ccaa1", "klxzwu"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("s10", "za"), ("v0000", "pqrs")]),
+    "s01s01s10s10v0101": (1, None, [("cccaaa0", "ijptvayr"), ("cccaaa1", "klqxzwus"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("s10", "za"), ("v0101", "pqrs")]),
+    "s01s01s01s10v0100": (1 / 3, 1, [("ccccaaa0", "ijptvxasr"), ("ccaaa1", "klqzywu"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("s10", "za"), ("v0100", "pqrs")]),
+    "s01s01s01s10v1101": (1 / 3, 0, [("cccaa0", "ijtvxar"), ("cccaaaa1", "klpqzywus"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("s10", "za"), ("v1101", "pqrs")]),
+    "s01s01s10s10v0001": (1 / 2, 1, [("ccccaaa0", "ijpqtvayr"), ("ccaaa1", "klxzwus"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("s10", "za"), ("v0001", "pqrs")]),
+    "s01s01s10s10v0100": (1 / 2, 0, [("cccaaaa0", "ijptvaysr"), ("cccaa1", "klqxzwu"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("s10", "za"), ("v0100", "pqrs")]),
+    "s01s01s01s01v1100": (1 / 24, None, [("ccccaa0", "ijtvxzsr"), ("ccaaaa1", "klpqaywu"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("s01", "za"), ("v1100", "pqrs")]),
+    "s01s01s01s10v0000": (-1 / 6, None, [("cccccaaa0", "ijpqtvxasr"), ("caaa1", "klzywu"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("s10", "za"), ("v0000", "pqrs")]),
+    "s01s01s01s10v0101": (-2 / 3, None, [("ccccaa0", "ijptvxar"), ("ccaaaa1", "klqzywus"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("s10", "za"), ("v0101", "pqrs")]),
+    "s01s01s01s10v1111": (-1 / 6, None, [("ccca0", "ijtvxa"), ("cccaaaaa1", "klpqzywusr"), ("s01", "tu"), ("s01", "vw"), ("s01", "xy"), ("s10", "za"), ("v1111", "pqrs")]),
+    "s01s01s10s10v0011": (1 / 4, None, [("ccccaa0", "ijpqtvay"), ("ccaaaa1", "klxzwusr"), ("s01", "tu"), ("s01", "vw"), ("s10", "xy"), ("s10", "za"), ("v0011", "pqrs")]),
+})
+for _n in "01":      # SU_2mer_{2,3,4}.py: the ST forms with t## -> u<n>_##
     for _t, _u in (("s01s10t00", "s01s10u%s00"), ("s01s01t10", "s01s01u%s10"), ("s01s10t01", "s01s10u%s01"),
-                   ("s01s01t00", "s01s01u%s00"), ("s01s01t11", "s01s01u%s11")):
+                   ("s01s01t00", "s01s01u%s00"), ("s01s01t11", "s01s01u%s11"),
+                   ("s01s01s10t10", "s01s01s10u%s10"), ("s01s01s10t00", "s01s01s10u%s00"), ("s01s01s10t11", "s01s01s10u%s11"),
+                   ("s01s01s01t10", "s01s01s01u%s10"), ("s01s01s10t01", "s01s01s10u%s01"),
+                   ("s01s01s10s10t00", "s01s01s10s10u%s00"), ("s01s01s01s10t10", "s01s01s01s10u%s10"),
+                   ("s01s01s10s10t01", "s01s01s10s10u%s01"), ("s01s01s01s10t00", "s01s01s01s10u%s00"),
+                   ("s01s01s01s10t11", "s01s01s01s10u%s11")):
         _c, _s, _terms = TWO_FRAGMENT[_t]
         TWO_FRAGMENT[_u % _n] = (_c, _s, [(("u%s_%s" % (_n, _nm[1:])) if _nm[0] == "t" else _nm, _ix) for _nm, _ix in _terms])
 
@@ -102,6 +146,25 @@ CATALOG2.update({
     "s01s01v0100": ((-1, 1), _PM), "s01s01v1101": ((-1, 1), _PM), "s01s10v0001": ((-1, 1), _PM), "s01s10v0100": ((1, -1), _PM),
     "s01s01v0000": ((-2, 2), _PP), "s01s01v0101": ((-2, 2), _PP), "s01s01v1111": ((-2, 2), _PP), "s01s10v0011": ((-2, 2), _PP),
 })
+_P1 = [(+1, (0, 1))]
+CATALOG2.update({
+    "s01s01s10": ((-1, 1), _PM), "s01s01s10s10": ((0, 0), _P1), "s01s01s01s10": ((-2, 2), _PP),
+    "s01s01s10t10": ((0, 0), _PP), "s01s01s10t00": ((-1, 1), _PM), "s01s01s10t11": ((-1, 1), _PM), "s01s01s01t10": ((-2, 2), _PP),
+    "s01s01s10t01": ((-2, 2), _PP), "s01s01s10s10t00": ((0, 0), _PP), "s01s01s01s10t10": ((-1, 1), _PM),
+    "s01s01s10s10t01": ((-1, 1), _PM), "s01s01s01s10t00": ((-2, 2), _PP), "s01s01s01s10t11": ((-2, 2), _PP),
+    "s01s01s10v0100": ((0, 0), _PP), "s01s01s10v1101": ((0, 0), _PP), "s01s01s01v1100": ((-1, 1), _PM), "s01s01s10v0000": ((-1, 1), _PM),
+    "s01s01s10v0101": ((-1, 1), _PM), "s01s01s10v1100": ((1, -1), _PM), "s01s01s10v1111": ((-1, 1), _PM), "s01s01s01v0100": ((-2, 2), _PP),
+    "s01s01s01v1101": ((-2, 2), _PP), "s01s01s10v0001": ((-2, 2), _PP), "s01s01s10v0111": ((-2, 2), _PP),
+    "s01s01s01s10v1100": ((0, 0), _PP), "s01s01s10s10v0000": ((0, 0), _PP), "s01s01s10s10v0101": ((0, 0), _P1),
+    "s01s01s01s10v0100": ((-1, 1), _PM), "s01s01s01s10v1101": ((-1, 1), _PM), "s01s01s10s10v0001": ((-1, 1), _PM),
+    "s01s01s10s10v0100": ((1, -1), _PM), "s01s01s01s01v1100": ((-2, 2), _PP), "s01s01s01s10v0000": ((-2, 2), _PP),
+    "s01s01s01s10v0101": ((-2, 2), _PP), "s01s01s01s10v1111": ((-2, 2), _PP), "s01s01s10s10v0011": ((-2, 2), _PP),
+})
+for _n in "01":
+    for _t in ("s01s01s10t10", "s01s01s10t00", "s01s01s10t11", "s01s01s01t10", "s01s01s10t01",
+               "s01s01s10s10t00", "s01s01s01s10t10", "s01s01s10s10t01", "s01s01s01s10t00", "s01s01s01s10t11"):
+        _k = _t.index("t")
+        CATALOG2[_t[:_k] + "u" + _n + _t[_k + 1:]] = CATALOG2[_t]
 for _n in "01":
     CATALOG2["s01s10u%s00" % _n] = ((0, 0), _PP)
     CATALOG2["s01s01u%s10" % _n] = ((-1, 1), _PM)

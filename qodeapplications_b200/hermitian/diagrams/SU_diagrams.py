@@ -1,15 +1,11 @@
-"""catalog of S*U diagrams (hermitian-XRCC/diagrams/SU_diagrams.py:27-62; S-orders 0-2 built so far)."""
+"""catalog of S*U diagrams (hermitian-XRCC/diagrams/SU_diagrams.py:27-90; every diagram diagram_lists.py activates, orders 0-4).
+Apart from u100 they are the S*T diagrams with T replaced by U<nucleus fragment> (nucleus 0 or 1), same charge rules."""
 from .build_diagram import build_diagram
 from .specs import make_one_fragment, make_two_fragment, u100
+from .ST_diagrams import RULES as _T_RULES
 
 u000 = make_one_fragment("u000")
-_pm = [(+1, (0, 1)), (-1, (1, 0))]
 _pp = [(+1, (0, 1)), (+1, (1, 0))]
-
-# label suffix (after "u<nucleus>") -> (Dchgs, permutations), identical for both nucleus choices
-_rules = {"s01u%s10": ((0, 0), _pp), "s01u%s00": ((-1, +1), _pm), "s01u%s11": ((-1, +1), _pm), "s01u%s01": ((-2, +2), _pp),
-          "s01s10u%s00": ((0, 0), _pp), "s01s01u%s10": ((-1, +1), _pm), "s01s10u%s01": ((-1, +1), _pm),
-          "s01s01u%s00": ((-2, +2), _pp), "s01s01u%s11": ((-2, +2), _pp)}
 
 catalog = {}
 catalog[1] = {
@@ -17,12 +13,13 @@ catalog[1] = {
 }
 catalog[2] = {
     "u100": build_diagram(u100, Dchgs=(0, 0), permutations=_pp),
-    "u001": build_diagram(make_two_fragment("u001"), Dchgs=(-1, +1), permutations=_pm),
-    "u101": build_diagram(make_two_fragment("u101"), Dchgs=(-1, +1), permutations=_pm),
 }
-for _pattern, (_Dchgs, _perms) in _rules.items():
+for _t_label, (_Dchgs, _perms) in _T_RULES.items():
+    _k = _t_label.index("t")
     for _n in "01":
-        _label = _pattern % _n
+        _label = _t_label[:_k] + "u" + _n + _t_label[_k + 1:]
+        if _label == "u100":
+            continue          # the nucleus-on-the-other-fragment one-electron term is the special delta diagram above
         _fn = make_two_fragment(_label)
         globals()[_label] = _fn
         catalog[2][_label] = build_diagram(_fn, Dchgs=_Dchgs, permutations=_perms)

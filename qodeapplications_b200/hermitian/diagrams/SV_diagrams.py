@@ -1,4 +1,4 @@
-"""catalog of S*V diagrams (hermitian-XRCC/diagrams/SV_diagrams.py:27-62; S-orders 0-2 built so far)."""
+"""catalog of S*V diagrams (hermitian-XRCC/diagrams/SV_diagrams.py:27-90; every diagram diagram_lists.py activates, orders 0-4)."""
 from .build_diagram import build_diagram
 from .specs import make_one_fragment, make_two_fragment
 
@@ -16,6 +16,14 @@ _rules = {
     "s01s01v0100": ((-1, +1), _pm), "s01s01v1101": ((-1, +1), _pm), "s01s10v0001": ((-1, +1), _pm),
     "s01s10v0100": ((+1, -1), _pm), "s01s01v0000": ((-2, +2), _pp), "s01s01v0101": ((-2, +2), _pp),
     "s01s01v1111": ((-2, +2), _pp), "s01s10v0011": ((-2, +2), _pp),
+    "s01s01s10v0100": ((0, 0), _pp), "s01s01s10v1101": ((0, 0), _pp), "s01s01s01v1100": ((-1, +1), _pm),
+    "s01s01s10v0000": ((-1, +1), _pm), "s01s01s10v0101": ((-1, +1), _pm), "s01s01s10v1100": ((+1, -1), _pm),
+    "s01s01s10v1111": ((-1, +1), _pm), "s01s01s01v0100": ((-2, +2), _pp), "s01s01s01v1101": ((-2, +2), _pp),
+    "s01s01s10v0001": ((-2, +2), _pp), "s01s01s10v0111": ((-2, +2), _pp),
+    "s01s01s01s10v1100": ((0, 0), _pp), "s01s01s10s10v0000": ((0, 0), _pp), "s01s01s10s10v0101": ((0, 0), _p),
+    "s01s01s01s10v0100": ((-1, +1), _pm), "s01s01s01s10v1101": ((-1, +1), _pm), "s01s01s10s10v0001": ((-1, +1), _pm),
+    "s01s01s10s10v0100": ((+1, -1), _pm), "s01s01s01s01v1100": ((-2, +2), _pp), "s01s01s01s10v0000": ((-2, +2), _pp),
+    "s01s01s01s10v0101": ((-2, +2), _pp), "s01s01s01s10v1111": ((-2, +2), _pp), "s01s01s10s10v0011": ((-2, +2), _pp),
 }
 
 catalog = {}

@@ -5,7 +5,7 @@ Every two-fragment diagram of the reference (hermitian-XRCC/diagrams/S*_2mer_*.p
     coefficient * (-1)**(X.n_j0 + shift) * raw( A(i0,j0, ...) @ B(i1,j1, ...) [@ s01(v,w) | s10(v,w)] )
 
 with A a density or rho x integral precontraction of diagram fragment 0, B the same for fragment 1,
-from S-order 2 on a bare overlap block as third factor, and equal letters contracted.  A row of the
+from S-order 2 on one or more bare overlap blocks as further factors, and equal letters contracted.  A row of the
 table is ``label: (coefficient, parity shift or None, [(operand name, free letters), ...])``; the
 operand names are exactly the attribute names the reference reads from ``X`` (build_diagram.py:116-134),
 so ``frag_resolve`` resolves them the same way.  A row becomes a function with the reference's signature
@@ -65,11 +65,53 @@ TWO_FRAGMENT = {
     "s01s01v0101": (2, None, [("ccca0pXXr_Vp1r1", "tvqs"), ("caaa1XXuX_S0u", "qwst"), ("s01", "vw")]),
     "s01s01v1111": (H, None, [("cc0tX_St1", "vu"), ("ccaaaa1pqXXsr_Vpqrs", "wu"), ("s01", "vw")]),
     "s01s10v0011": (-1, None, [("ccca0pqXX_Vpq11", "twrs"), ("caaa1XuXX_S0u", "vsrt"), ("s10", "vw")]),
+    # ---- orders 3 and 4 (the diagrams diagram_lists.py:10-71 activates) ------------------------------------------
+    "s01s01s10":         (1 / 2, 1, [("cca0pXX_Sp1", "ruq"), ("caa1XsX_S0s", "tqr"), ("s10", "tu")]),   # S_2mer_3.py
+    "s01s01s10s10":      (1 / 4, None, [("ccaa0pXXX_Sp1", "rwuq"), ("ccaa1XXsX_S0s", "tvqr"), ("s10", "tu"), ("s10", "vw")]),   # S_2mer_4.py
+    "s01s01s01s10":      (-1 / 6, None, [("ccca0pXXX_Sp1", "rtwq"), ("caaa1XXsX_S0s", "vuqr"), ("s01", "tu"), ("s10", "vw")]),   # S_2mer_4.py
+    "s01s01s10t10":      (1 / 2, None, [("ccaa0XXXq_T1q", "tvyp"), ("ccaa1XXXu_S0u", "pxwt"), ("s01", "vw"), ("s10", "xy")]),   # ST_2mer_3.py
+    "s01s01s10t00":      (1 / 2, 0, [("cccaa0pXXXq_Tpq", "tvy"), ("caa1XXu_S0u", "xwt"), ("s01", "vw"), ("s10", "xy")]),   # ST_2mer_3.py
+    "s01s01s10t11":      (1 / 2, 0, [("cca0tXX_St1", "vyu"), ("ccaaa1pXXXq_Tpq", "xwu"), ("s01", "vw"), ("s10", "xy")]),   # ST_2mer_3.py
+    "s01s01s01t10":      (-1 / 6, None, [("ccca0XXXq_T1q", "tvxp"), ("caaa1XXXu_S0u", "pywt"), ("s01", "vw"), ("s01", "xy")]),   # ST_2mer_3.py
+    "s01s01s10t01":      (-1 / 2, None, [("ccca0pXXX_Tp1", "tvyq"), ("caaa1XXuX_S0u", "xwqt"), ("s01", "vw"), ("s10", "xy")]),   # ST_2mer_3.py
+    "s01s01s10s10t00":   (1 / 4, None, [("cccaaa0pXXXXq_Tpq", "tvay"), ("ccaa1XXXu_S0u", "xzwt"), ("s01", "vw"), ("s10", "xy"), ("s10", "za")]),   # ST_2mer_4.py
+    "s01s01s01s10t10":   (1 / 6, 0, [("cccaa0XXXXq_T1q", "tvxap"), ("ccaaa1XXXXu_S0u", "pzywt"), ("s01", "vw"), ("s01", "xy"), ("s10", "za")]),   # ST_2mer_4.py
+    "s01s01s10s10t01":   (1 / 4, 0, [("cccaa0pXXXX_Tp1", "tvayq"), ("ccaaa1XXXuX_S0u", "xzwqt"), ("s01", "vw"), ("s10", "xy"), ("s10", "za")]),   # ST_2mer_4.py
+    "s01s01s01s10t00":   (-1 / 6, None, [("ccccaa0pXXXXq_Tpq", "tvxa"), ("caaa1XXXu_S0u", "zywt"), ("s01", "vw"), ("s01", "xy"), ("s10", "za")]),   # ST_2mer_4.py
+    "s01s01s01s10t11":   (-1 / 6, None, [("ccca0tXXX_St1", "vxau"), ("ccaaaa1pXXXXq_Tpq", "zywu"), ("s01", "vw"), ("s01", "xy"), ("s10", "za")]),   # ST_2mer_4.py
+    "s01s01s10v0100":    (1, None, [("cccaaa0pXXXsr_Vp1rs", "tvyq"), ("ccaa1XXXu_S0u", "qxwt"), ("s01", "vw"), ("s10", "xy")]),   # SV_2mer_3.py
+    "s01s01s10v1101":    (-1, None, [("ccaa0tXXX_St1", "vyru"), ("cccaaa1pqXXXs_Vpq0s", "xwur"), ("s01", "vw"), ("s10", "xy")]),   # SV_2mer_3.py
+    "s01s01s01v1100":    (1 / 6, 0, [("cccaa0XXXsr_V11rs", "tvxpq"), ("ccaaa1XXXXu_S0u", "pqywt"), ("s01", "vw"), ("s01", "xy")]),   # SV_2mer_3.py
+    "s01s01s10v0000":    (1 / 2, 1, [("ccccaaa0pqXXXsr_Vpqrs", "tvy"), ("caa1XXu_S0u", "xwt"), ("s01", "vw"), ("s10", "xy")]),   # SV_2mer_3.py
+    "s01s01s10v0101":    (2, 1, [("cccaa0pXXXr_Vp1r1", "tvyqs"), ("ccaaa1XXXuX_S0u", "qxwst"), ("s01", "vw"), ("s10", "xy")]),   # SV_2mer_3.py
+    "s01s01s10v1100":    (1 / 2, 1, [("ccaaa0XXXsr_V11rs", "tvypq"), ("cccaa1XXXXu_S0u", "pqxwt"), ("s01", "vw"), ("s10", "xy")]),   # SV_2mer_3.py
+    "s01s01s10v1111":    (1 / 2, 1, [("cca0tXX_St1", "vyu"), ("cccaaaa1pqXXXsr_Vpqrs", "xwu"), ("s01", "vw"), ("s10", "xy")]),   # SV_2mer_3.py
+    "s01s01s01v0100":    (-1 / 3, None, [("ccccaa0pXXXsr_Vp1rs", "tvxq"), ("caaa1XXXu_S0u", "qywt"), ("s01", "vw"), ("s01", "xy")]),   # SV_2mer_3.py
+    "s01s01s01v1101":    (1 / 3, None, [("ccca0tXXX_St1", "vxru"), ("ccaaaa1pqXXXs_Vpq0s", "ywur"), ("s01", "vw"), ("s01", "xy")]),   # SV_2mer_3.py
+    "s01s01s10v0001":    (-1, None, [("ccccaa0pqXXXr_Vpqr1", "tvys"), ("caaa1XXuX_S0u", "xwst"), ("s01", "vw"), ("s10", "xy")]),   # SV_2mer_3.py
+    "s01s01s10v0111":    (1, None, [("ccca0XtXX_St1", "pvyu"), ("ccaaaa1qXXXsr_V0qrs", "xwup"), ("s01", "vw"), ("s10", "xy")]),   # SV_2mer_3.py
+    "s01s01s01s10v1100": (-1 / 6, None, [("cccaaa0XXXXsr_V11rs", "tvxapq"), ("cccaaa1XXXXXu_S0u", "pqzywt"), ("s01", "vw"), ("s01", "xy"), ("s10", "za")]),   # SV_2mer_4.py
+    "s01s01s10s10v0000": (1 / 4, None, [("ccccaaaa0pqXXXXsr_Vpqrs", "tvay"), ("ccaa1XXXu_S0u", "xzwt"), ("s01", "vw"), ("s10", "xy"), ("s10", "za")]),   # SV_2mer_4.py
+    "s01s01s10s10v0101": (1, None, [("cccaaa0pXXXXr_Vp1r1", "tvayqs"), ("cccaaa1XXXXuX_S0u", "qxzwst"), ("s01", "vw"), ("s10", "xy"), ("s10", "za")]),   # SV_2mer_4.py
+    "s01s01s01s10v0100": (1 / 3, 1, [("ccccaaa0pXXXXsr_Vp1rs", "tvxaq"), ("ccaaa1XXXXu_S0u", "qzywt"), ("s01", "vw"), ("s01", "xy"), ("s10", "za")]),   # SV_2mer_4.py
+    "s01s01s01s10v1101": (1 / 3, 0, [("cccaa0tXXXX_St1", "vxaru"), ("cccaaaa1pqXXXXs_Vpq0s", "zywur"), ("s01", "vw"), ("s01", "xy"), ("s10", "za")]),   # SV_2mer_4.py
+    "s01s01s10s10v0001": (1 / 2, 1, [("ccccaaa0pqXXXXr_Vpqr1", "tvays"), ("ccaaa1XXXuX_S0u", "xzwst"), ("s01", "vw"), ("s10", "xy"), ("s10", "za")]),   # SV_2mer_4.py
+    "s01s01s10s10v0100": (1 / 2, 0, [("cccaaaa0pXXXXsr_Vp1rs", "tvayq"), ("cccaa1XXXXu_S0u", "qxzwt"), ("s01", "vw"), ("s10", "xy"), ("s10", "za")]),   # SV_2mer_4.py
+    "s01s01s01s01v1100": (1 / 24, None, [("ccccaa0XXXXsr_V11rs", "tvxzpq"), ("ccaaaa1XXXXXu_S0u", "pqaywt"), ("s01", "vw"), ("s01", "xy"), ("s01", "za")]),   # SV_2mer_4.py
+    "s01s01s01s10v0000": (-1 / 6, None, [("cccccaaa0pqXXXXsr_Vpqrs", "tvxa"), ("caaa1XXXu_S0u", "zywt"), ("s01", "vw"), ("s01", "xy"), ("s10", "za")]),   # SV_2mer_4.py
+    "s01s01s01s10v0101": (-2 / 3, None, [("ccccaa0pXXXXr_Vp1r1", "tvxaqs"), ("ccaaaa1XXXXuX_S0u", "qzywst"), ("s01", "vw"), ("s01", "xy"), ("s10", "za")]),   # SV_2mer_4.py
+    "s01s01s01s10v1111": (-1 / 6, None, [("ccca0tXXX_St1", "vxau"), ("cccaaaaa1pqXXXXsr_Vpqrs", "zywu"), ("s01", "vw"), ("s01", "xy"), ("s10", "za")]),   # SV_2mer_4.py
+    "s01s01s10s10v0011": (1 / 4, None, [("ccccaa0pqXXXX_Vpq11", "tvayrs"), ("ccaaaa1XXXuXX_S0u", "xzwsrt"), ("s01", "vw"), ("s10", "xy"), ("s10", "za")]),   # SV_2mer_4.py
 }
 for _n in "01":     # SU_2mer_1.py / SU_2mer_2.py: the ST rows with T -> U<nucleus fragment>
     for _t, _u in (("s01t10", "s01u%s10"), ("s01t00", "s01u%s00"), ("s01t11", "s01u%s11"), ("s01t01", "s01u%s01"),
                    ("s01s10t00", "s01s10u%s00"), ("s01s01t10", "s01s01u%s10"), ("s01s10t01", "s01s10u%s01"),
-                   ("s01s01t00", "s01s01u%s00"), ("s01s01t11", "s01s01u%s11")):
+                   ("s01s01t00", "s01s01u%s00"), ("s01s01t11", "s01s01u%s11"),
+                   ("s01s01s10t10", "s01s01s10u%s10"), ("s01s01s10t00", "s01s01s10u%s00"), ("s01s01s10t11", "s01s01s10u%s11"),
+                   ("s01s01s01t10", "s01s01s01u%s10"), ("s01s01s10t01", "s01s01s10u%s01"),
+                   ("s01s01s10s10t00", "s01s01s10s10u%s00"), ("s01s01s01s10t10", "s01s01s01s10u%s10"),
+                   ("s01s01s10s10t01", "s01s01s10s10u%s01"), ("s01s01s01s10t00", "s01s01s01s10u%s00"),
+                   ("s01s01s01s10t11", "s01s01s01s10u%s11")):
         _c, _s, _ops = TWO_FRAGMENT[_t]
         TWO_FRAGMENT[_u % _n] = (_c, _s, [(_name.replace("_T", "_U" + _n), _idx) for _name, _idx in _ops])
 
@@ -84,9 +126,9 @@ def _state_axes(contract_last):
     """diagram_hack.state_indices (:26-33): the free state axes of the result and the renaming that makes the two
     ket (or bra) state indices one contracted label when the last pair is traced"""
     if contract_last == "ket":
-        return {"j0": "z", "j1": "z"}, ["i0", "i1"]
+        return {"j0": "_tr", "j1": "_tr"}, ["i0", "i1"]
     if contract_last == "bra":
-        return {"i0": "z", "i1": "z"}, ["j0", "j1"]
+        return {"i0": "_tr", "i1": "_tr"}, ["j0", "j1"]
     if contract_last:
         raise ValueError("contract_last must be False, 'ket' or 'bra'")
     return {}, ["i0", "i1", "j0", "j1"]

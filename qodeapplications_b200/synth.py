@@ -25,6 +25,7 @@ CONFIGS = {
     "toy":  dict(n_frag=2, n_orb=6,  n_states={0: 3,   +1: 2,   -1: 2}),
     "toy3": dict(n_frag=3, n_orb=5,  n_states={0: 2,   +1: 2,   -1: 2}),
     "toy5": dict(n_frag=3, n_orb=4,  n_states={0: 2, +1: 2, -1: 2, +2: 1, -2: 1}),   # five charge states (general-XRCC/Be631g.py:73)
+    "toy4": dict(n_frag=2, n_orb=5,  n_states={0: 3,   +1: 2,   -1: 2}),               # S-orders 3-4 (8-operator densities)
     "toyh": dict(n_frag=2, n_orb=[6, 4], n_states={0: 3, +1: 2, -1: 2}),             # fragments with different orbital counts
     "mid":  dict(n_frag=2, n_orb=8,  n_states={0: 5,   +1: 3,   -1: 4}),
     "cfg1": dict(n_frag=2, n_orb=18, n_states={0: 11,  +1: 4,   -1: 8}),
@@ -33,12 +34,13 @@ CONFIGS = {
     "cfg4": dict(n_frag=4, n_orb=18, n_states={0: 96,  +1: 34,  -1: 70}),
     "cfg5": dict(n_frag=2, n_orb=48, n_states={0: 478, +1: 174, -1: 348}),
 }
-SEEDS = {"toy": 11, "toy3": 13, "mid": 17, "toy5": 19, "toyh": 29, "cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}
+SEEDS = {"toy": 11, "toy3": 13, "mid": 17, "toy5": 19, "toyh": 29, "toy4": 31, "cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}
 N_ELEC_REF = 4
 
 OPS_ORDER0 = ("a", "c", "aa", "cc", "ca", "caa", "cca", "ccaa")
 OPS_ORDER1 = OPS_ORDER0 + ("caaa", "ccca", "ccaaa", "cccaa")
 OPS_ORDER2 = OPS_ORDER1 + ("ccaaaa", "cccaaa", "ccccaa")
+OPS_ORDER4 = OPS_ORDER2 + ("cccaaaa", "ccccaaa", "cccaaaaa", "ccccaaaa", "cccccaaa")
 OPS_GENERAL = ("a", "c", "aa", "cc", "ca", "caa", "cca")      # + precontracted scalar "ccaa"
 
 

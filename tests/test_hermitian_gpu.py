@@ -41,11 +41,12 @@ def _blocks(system, dev, family, which="symm"):
                                          timings=timer(), precon_timings=timer())
 
 
-@pytest.mark.parametrize("fixture,n_blocks,ops", [("hermitian_toy_blocks.npz", 221, synth.OPS_ORDER1),
-                                                  ("hermitian_toy_blocks2.npz", 165, synth.OPS_ORDER2)])
-def test_every_diagram_block_matches_reference_golden(dev, fixture, n_blocks, ops):
+@pytest.mark.parametrize("fixture,n_blocks,ops,name", [("hermitian_toy_blocks.npz", 221, synth.OPS_ORDER1, "toy"),
+                                                       ("hermitian_toy_blocks2.npz", 165, synth.OPS_ORDER2, "toy"),
+                                                       ("hermitian_toy4_blocks34.npz", 328, synth.OPS_ORDER4, "toy4")])
+def test_every_diagram_block_matches_reference_golden(dev, fixture, n_blocks, ops, name):
     g = numpy.load(os.path.join(GOLDEN, fixture))
-    toy = synth.make_system("toy", ops=ops, with_bior=True)       # the fixture was generated from exactly this draw
+    toy = synth.make_system(name, ops=ops, with_bior=True)       # the fixture was generated from exactly this draw
     def family_of(label):
         rest = label.replace("s01", "").replace("s10", "")
         return "S" if rest == "" else "S" + rest[0].upper()

@@ -15,10 +15,11 @@ def _close(a, b, tol=1e-10):
     assert numpy.abs(numpy.asarray(a) - b).max() <= tol * scale, (numpy.abs(a - b).max(), scale)
 
 
-@pytest.mark.parametrize("fixture,n_labels,ops", [("hermitian_toy_blocks.npz", 32, synth.OPS_ORDER1),
-                                                  ("hermitian_toy_blocks2.npz", 28, synth.OPS_ORDER2)])
-def test_every_diagram_block_matches_reference(fixture, n_labels, ops):
-    toy = synth.make_system("toy", ops=ops, with_bior=True)       # the fixture was generated from exactly this draw
+@pytest.mark.parametrize("fixture,n_labels,ops,name", [("hermitian_toy_blocks.npz", 32, synth.OPS_ORDER1, "toy"),
+                                                       ("hermitian_toy_blocks2.npz", 28, synth.OPS_ORDER2, "toy"),
+                                                       ("hermitian_toy4_blocks34.npz", 56, synth.OPS_ORDER4, "toy4")])
+def test_every_diagram_block_matches_reference(fixture, n_labels, ops, name):
+    toy = synth.make_system(name, ops=ops, with_bior=True)       # the fixture was generated from exactly this draw
     g = numpy.load(os.path.join(GOLDEN, fixture))
     dens, symm = toy["densities"], toy["symm"]
     ints = ho.integrals(symm.S, symm.T, symm.U, symm.V)

@@ -72,11 +72,13 @@ def _hermitian_blocks(system, dev, family):
                                          timings=timer(), precon_timings=timer())
 
 
-@pytest.mark.parametrize("fixture,ops", [("hermitian_toy_blocks.npz", synth.OPS_ORDER1), ("hermitian_toy_blocks2.npz", synth.OPS_ORDER2)])
-def test_hermitian_every_diagram_block_host_logic(fixture, ops):
-    """blocks[subsystem][charges][label] -- the reference's own access pattern -- for all 60 diagrams of orders 0-2"""
+@pytest.mark.parametrize("fixture,ops,name", [("hermitian_toy_blocks.npz", synth.OPS_ORDER1, "toy"),
+                                              ("hermitian_toy_blocks2.npz", synth.OPS_ORDER2, "toy"),
+                                              ("hermitian_toy4_blocks34.npz", synth.OPS_ORDER4, "toy4")])
+def test_hermitian_every_diagram_block_host_logic(fixture, ops, name):
+    """blocks[subsystem][charges][label] -- the reference's own access pattern -- for all 116 diagrams of orders 0-4"""
     g = numpy.load(os.path.join(GOLDEN, fixture))
-    toy1 = synth.make_system("toy", ops=ops, with_bior=True)       # the fixture was generated from exactly this draw
+    toy1 = synth.make_system(name, ops=ops, with_bior=True)       # the fixture was generated from exactly this draw
     dev = FakeDevice()
     def family_of(label):
         rest = label.replace("s01", "").replace("s10", "")
