@@ -107,7 +107,7 @@ int xr_copy2d_scaled(xr_ctx* ctx, double* dst, int64_t dst_ld, const double* src
                      int64_t rows, int64_t cols, double alpha);
 
 /* dst (contiguous, row-major over `shape`) <- alpha * src viewed with arbitrary element strides:
- *   dst[i0,...,i_{nd-1}] = alpha * src[ sum_d i_d * src_strides[d] ]      (nd <= 8; host arrays of length nd)
+ *   dst[i0,...,i_{nd-1}] = alpha * src[ sum_d i_d * src_strides[d] ]      (nd <= 12; host arrays of length nd)
  * The index-permutation step of a tensor contraction (hermitian-XRCC operands whose contracted
  * indices are not trailing, e.g. "ccaa0pXsr_Vp1rs" in hermitian-XRCC/diagrams/SV_2mer_1.py:30-31). */
 int xr_permute_copy(xr_ctx* ctx, double* dst, const double* src, int nd, const int64_t* shape,

@@ -197,8 +197,8 @@ extern "C" int xr_scatter_const(xr_ctx* ctx, double* C, const int64_t* idx, int6
 
 struct PermuteParams {
     int nd;
-    int64_t shape[8];
-    int64_t stride[8];
+    int64_t shape[12];
+    int64_t stride[12];
     int64_t total;
 };
 
@@ -206,7 +206,7 @@ __global__ void permute_copy_kernel(double* __restrict__ dst, const double* __re
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < p.total; t += (int64_t)gridDim.x * blockDim.x) {
         int64_t rem = t, at = 0;
 #pragma unroll
-        for (int d = 7; d >= 0; --d) {
+        for (int d = 11; d >= 0; --d) {
             if (d < p.nd) {
                 int64_t i = rem % p.shape[d];
                 rem /= p.shape[d];
@@ -220,7 +220,7 @@ __global__ void permute_copy_kernel(double* __restrict__ dst, const double* __re
 extern "C" int xr_permute_copy(xr_ctx* ctx, double* dst, const double* src, int nd, const int64_t* shape,
                                const int64_t* src_strides, double alpha) {
     XR_REQUIRE(ctx && dst && src && shape && src_strides, "xr_permute_copy: null argument");
-    XR_REQUIRE(nd >= 1 && nd <= 8, "xr_permute_copy: nd=%d unsupported (1..8)", nd);
+    XR_REQUIRE(nd >= 1 && nd <= 12, "xr_permute_copy: nd=%d unsupported (1..12)", nd);
     PermuteParams p{};
     p.nd = nd;
     p.total = 1;

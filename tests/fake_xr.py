@@ -71,6 +71,7 @@ class FakeContext(object):
 
     def permute_copy(self, dst, src, shape, src_strides, alpha=1.0):
         self.launches += 1
+        assert 1 <= len(shape) <= 12, "xr_permute_copy supports 1..12 dimensions"      # same limit as the CUDA kernel
         total = int(numpy.prod(shape))
         if total == 0:
             return
