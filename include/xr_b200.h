@@ -101,6 +101,13 @@ int xr_gemm_scatter(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
                     const double* A, int64_t lda, const double* B, int64_t ldb,
                     double* C, const int64_t* offM, int64_t ldc, const int64_t* offN, int accumulate);
 
+/* The same product handed to the streaming consumer instead of memory:
+ *     moments[0] += alpha * sum_{m,n} C[m,n],   moments[1] += alpha^2 * sum_{m,n} C[m,n]^2,   C = A . B^T
+ * (device doubles, caller zeroes; bit-reproducible).  For dimer blocks that cannot be stored (the 1e12-element H2 of
+ * the 1000-states/fragment stress configuration).  Operands must be 16-byte aligned with even leading dimensions. */
+int xr_gemm_reduce(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
+                   const double* A, int64_t lda, const double* B, int64_t ldb, double* moments);
+
 /* dst[r*dst_ld + c] = alpha * src[r*src_ld + c]  (rows x cols, device to device).  Used to lay
  * densities into zero-padded, sign-folded factor matrices. */
 int xr_copy2d_scaled(xr_ctx* ctx, double* dst, int64_t dst_ld, const double* src, int64_t src_ld,

@@ -22,6 +22,7 @@ struct GemmTmaParams {
     const int64_t* offN;
     int accumulate;
     int64_t tiles_n;
+    double* partials;      // REDUCE mode: [tiles][2] per-CTA (sum, sum of squares); nothing is stored to C
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -39,6 +40,7 @@ constexpr size_t TMA_SMEM = (size_t)TSTAGES * (TILE_A_BYTES + TILE_B_BYTES) + 10
 // byte offset of element (row r, k) inside a 128-byte-swizzled [rows][16 doubles] tile
 __device__ __forceinline__ int swz(int r, int k) { return r * 128 + ((((k >> 1) ^ (r & 7)) << 4) | ((k & 1) << 3)); }
 
+template <bool REDUCE>
 __global__ void __launch_bounds__(TTHREADS, 4)
 gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmTmaParams p) {
     constexpr int MI = 4, NJ = 4;      // 2 x 2 warps, each 32 x 32
@@ -95,6 +97,38 @@ gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
+    }
+
+    if (REDUCE) {
+        // streaming consumer: the tile never leaves the SM.  Rows/columns beyond M/N were zero-filled by the TMA unit and add 0.
+        __shared__ double red[2][TTHREADS / 32];
+        double s1p[NJ], s2p[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) s1p[j] = s2p[j] = 0.0;
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                s1p[j] += acc[i][j][0] + acc[i][j][1];
+                s2p[j] = fma(acc[i][j][0], acc[i][j][0], s2p[j]);
+                s2p[j] = fma(acc[i][j][1], acc[i][j][1], s2p[j]);
+            }
+        double s1 = (s1p[0] + s1p[1]) + (s1p[2] + s1p[3]), s2 = (s2p[0] + s2p[1]) + (s2p[2] + s2p[3]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            red[0][warp] = s1;
+            red[1][warp] = s2;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            p.partials[2 * tile] = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+            p.partials[2 * tile + 1] = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+        }
+        return;
     }
 
     // epilogue (identical to gemm_nt_scatter_kernel): lane holds C[8i+g][8j+2t], C[8i+g][8j+2t+1]
@@ -175,12 +209,88 @@ int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alp
     if (K < 1 || M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return XR_ERR_UNSUPPORTED;
     CUtensorMap mapA, mapB;
     if (!make_map(&mapA, A, M, K, lda) || !make_map(&mapB, B, N, K, ldb)) return XR_ERR_UNSUPPORTED;
-    GemmTmaParams p{M, N, K, alpha, C, offM, ldc, offN, accumulate, (N + TBN - 1) / TBN};
+    GemmTmaParams p{M, N, K, alpha, C, offM, ldc, offN, accumulate, (N + TBN - 1) / TBN, nullptr};
     const int64_t tiles = ((M + TBM - 1) / TBM) * p.tiles_n;
     XR_REQUIRE(tiles < (1ll << 31), "xr_gemm_scatter: too many tiles (%lld)", (long long)tiles);
-    XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
-    gemm_tma_scatter_kernel<<<(unsigned)tiles, TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
+    XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+    gemm_tma_scatter_kernel<false><<<(unsigned)tiles, TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
     XR_CUDA(cudaGetLastError());
     ctx->launches++;
+    return XR_OK;
+}
+
+namespace {
+
+// fixed-shape two-level sum of the per-CTA partials (bit-reproducible: no atomics, fixed assignment and order)
+constexpr int RED_BLOCKS = 256, RED_THREADS = 256;
+
+__global__ void __launch_bounds__(RED_THREADS) reduce_partials_kernel(const double* __restrict__ partials, int64_t count,
+                                                                        double* __restrict__ block_out) {
+    __shared__ double sh[2][RED_THREADS];
+    const int64_t per_block = (count + RED_BLOCKS - 1) / RED_BLOCKS;
+    const int64_t lo = blockIdx.x * per_block, hi = lo + per_block < count ? lo + per_block : count;
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += RED_THREADS) {
+        s1 += partials[2 * i];
+        s2 += partials[2 * i + 1];
+    }
+    sh[0][threadIdx.x] = s1;
+    sh[1][threadIdx.x] = s2;
+    __syncthreads();
+    for (int o = RED_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        block_out[2 * blockIdx.x] = sh[0][0];
+        block_out[2 * blockIdx.x + 1] = sh[1][0];
+    }
+}
+
+__global__ void finalize_moments_kernel(const double* __restrict__ block_out, double alpha, double* moments) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int i = 0; i < RED_BLOCKS; ++i) {
+            t1 += block_out[2 * i];
+            t2 += block_out[2 * i + 1];
+        }
+        moments[0] += alpha * t1;
+        moments[1] += alpha * alpha * t2;
+    }
+}
+
+}  // namespace
+
+// moments[0] += alpha * sum(C), moments[1] += alpha^2 * sum(C^2) for C = A.B^T, without ever storing C: the consumer for
+// dimer blocks that do not fit in HBM (cfg5: 1e12 elements).  Needs 16-byte-aligned operands (tensor maps).
+extern "C" int xr_gemm_reduce(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                              const double* B, int64_t ldb, double* moments) {
+    XR_REQUIRE(ctx, "xr_gemm_reduce: null ctx");
+    if (M <= 0 || N <= 0) return XR_OK;
+    XR_REQUIRE(K >= 1 && A && B && moments, "xr_gemm_reduce: null pointer or K < 1");
+    XR_REQUIRE(lda >= K && ldb >= K, "xr_gemm_reduce: lda/ldb smaller than K");
+    XR_REQUIRE(lda % 2 == 0 && ldb % 2 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+               "xr_gemm_reduce: operands must be 16-byte aligned with even leading dimensions");
+    XR_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "xr_gemm_reduce: dimension too large");
+    CUtensorMap mapA, mapB;
+    XR_REQUIRE(make_map(&mapA, A, M, K, lda) && make_map(&mapB, B, N, K, ldb), "xr_gemm_reduce: cuTensorMapEncodeTiled failed");
+    GemmTmaParams p{M, N, K, alpha, nullptr, nullptr, 0, nullptr, 0, (N + TBN - 1) / TBN, nullptr};
+    const int64_t tiles = ((M + TBM - 1) / TBM) * p.tiles_n;
+    XR_REQUIRE(tiles < (1ll << 31), "xr_gemm_reduce: too many tiles (%lld)", (long long)tiles);
+    int rc = xr_ensure_scratch(ctx, (size_t)(tiles + RED_BLOCKS) * 2 * sizeof(double) + 256);
+    if (rc != XR_OK) return rc;
+    p.partials = static_cast<double*>(ctx->scratch);
+    double* block_out = p.partials + 2 * tiles;
+    XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+    gemm_tma_scatter_kernel<true><<<(unsigned)tiles, TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
+    XR_CUDA(cudaGetLastError());
+    reduce_partials_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(p.partials, tiles, block_out);
+    XR_CUDA(cudaGetLastError());
+    finalize_moments_kernel<<<1, 32, 0, ctx->stream>>>(block_out, alpha, moments);
+    XR_CUDA(cudaGetLastError());
+    ctx->launches += 3;
     return XR_OK;
 }

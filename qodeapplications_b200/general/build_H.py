@@ -42,9 +42,12 @@ class _FragInfo(object):
         self.n_elec_ref = fragment.n_elec_ref
         rho = fragment.rho
         self.n_states = {}
-        for (ci, cj), block in rho["ca"].items():
-            if ci == cj:
-                self.n_states[ci] = len(block)
+        if hasattr(fragment, "n_states"):       # explicit (needed when only a slab of the densities is held)
+            self.n_states = dict(fragment.n_states)
+        else:
+            for (ci, cj), block in rho["ca"].items():
+                if ci == cj:
+                    self.n_states[ci] = len(block)
         if hasattr(fragment, "state_indices"):
             self.state_indices = list(fragment.state_indices)
         else:   # general-XRCC/Be631g.py:81-85 with ref_state=(0,0)
@@ -115,12 +118,17 @@ def _even(k):
 
 
 class build_matrix_elements(object):
-    def __init__(self, supersystem, integrals, nuc_repulsion, device=None):
+    def __init__(self, supersystem, integrals, nuc_repulsion, device=None, held=None):
+        """held (optional, for sharded inputs): {fragment index: (lo, hi)} -- the densities of that fragment are only
+        supplied for bra states whose matrix position lies in [lo, hi): rho[op][(ci,cj)] then has one leading row per HELD
+        bra state of charge ci (and the fragment object must carry ``n_states``).  Density blocks may also be CUDA torch
+        tensors already resident on the device."""
         n_elec = [fragment.n_elec_ref for fragment in supersystem]
         rho = [fragment.rho for fragment in supersystem]
         self.data = rho, integrals.T, integrals.U, integrals.V, nuc_repulsion, n_elec     # as build_H.py:41
         self._supersystem = supersystem
         self._device_arg = device
+        self._held = dict(held or {})
         self._dev = None
         self._info = None
         self._rho_dev = {}
@@ -175,16 +183,44 @@ class build_matrix_elements(object):
             self._info = [_FragInfo(f, T[k, k].shape[0]) for k, f in enumerate(self._supersystem)]
         return self._info[m]
 
+    def _held_range(self, m, chg):
+        """[h_lo, h_hi): the bra states of charge chg of fragment m whose densities are held here"""
+        info = self._frag(m)
+        if m not in self._held:
+            return 0, info.n_states[chg]
+        lo, hi = self._held[m]
+        inside = numpy.nonzero((info.pos[chg] >= lo) & (info.pos[chg] < hi))[0]
+        if len(inside) == 0:
+            return 0, 0
+        if int(inside[-1]) + 1 - int(inside[0]) != len(inside):
+            raise NotImplementedError("held bra slab is not contiguous inside charge sector %r" % (chg,))
+        return int(inside[0]), int(inside[-1]) + 1
+
     def _rho(self, m, op, sector):
-        """device tensor [N_bra*N_ket, n^k] of rho[m][op][sector]"""
+        """device tensor [N_bra(held)*N_ket, n^k] of rho[m][op][sector]"""
         key = (m, op, sector)
         if key not in self._rho_dev:
             info = self._frag(m)
             block = self.data[0][m][op][sector]
-            arr = numpy.asarray(block, dtype=numpy.float64)
-            Ni, Nj = info.n_states[sector[0]], info.n_states[sector[1]]
-            self._rho_dev[key] = self.dev.upload(arr.reshape(Ni * Nj, -1))
+            h_lo, h_hi = self._held_range(m, sector[0])
+            rows = (h_hi - h_lo) * info.n_states[sector[1]]
+            if isinstance(block, torch.Tensor):
+                if block.dtype != torch.float64 or not block.is_contiguous():
+                    raise TypeError("device-resident densities must be contiguous float64 tensors")
+                self._rho_dev[key] = block.reshape(rows, -1)
+            else:
+                arr = numpy.asarray(block, dtype=numpy.float64)
+                self._rho_dev[key] = self.dev.upload(arr.reshape(rows, -1))
         return self._rho_dev[key]
+
+    def _rho_rows(self, m, op, ci, cj, i_lo, i_hi):
+        """(device tensor, element offset of bra state i_lo) for rows [i_lo, i_hi) of rho[m][op][(ci,cj)]"""
+        src = self._rho(m, op, (ci, cj))
+        h_lo, h_hi = self._held_range(m, ci)
+        if i_lo < h_lo or i_hi > h_hi:
+            raise ValueError("fragment %d: bra states [%d,%d) of charge %r requested but only [%d,%d) are held"
+                             % (m, i_lo, i_hi, ci, h_lo, h_hi))
+        return src, (i_lo - h_lo) * self._frag(m).n_states[cj] * src.shape[1]
 
     def _ints(self, key, make):
         """device copy of a (permuted) integral block, cached by key"""
@@ -235,10 +271,10 @@ class build_matrix_elements(object):
         info = self._frag(m)
         for ci, cj, i_lo, i_hi, off in cls.sectors:
             Nj = info.n_states[cj]
-            src = self._rho(m, op, (ci, cj))
+            src, first = self._rho_rows(m, op, ci, cj, i_lo, i_hi)
             F = src.shape[1]
             alpha = 1.0 if sign is None else sign(ci)
-            ctx.copy2d_scaled(out.data_ptr() + 8 * (off * ld + col0), ld, src.data_ptr() + 8 * (i_lo * Nj * F), F,
+            ctx.copy2d_scaled(out.data_ptr() + 8 * (off * ld + col0), ld, src.data_ptr() + 8 * first, F,
                               (i_hi - i_lo) * Nj, F, alpha)
 
     def _fill_contracted(self, out, ld, col0, m, op, cls, Wt, scale=1.0, sign=None, accumulate=False):
@@ -248,10 +284,10 @@ class build_matrix_elements(object):
         F, K = Wt.shape
         for ci, cj, i_lo, i_hi, off in cls.sectors:
             Nj = info.n_states[cj]
-            src = self._rho(m, op, (ci, cj))
+            src, first = self._rho_rows(m, op, ci, cj, i_lo, i_hi)
             assert src.shape[1] == K, (op, src.shape, K)
             alpha = scale * (1.0 if sign is None else sign(ci))
-            ctx.gemm_scatter((i_hi - i_lo) * Nj, F, K, alpha, src.data_ptr() + 8 * (i_lo * Nj * K), K, Wt, K,
+            ctx.gemm_scatter((i_hi - i_lo) * Nj, F, K, alpha, src.data_ptr() + 8 * first, K, Wt, K,
                              out.data_ptr() + 8 * (off * ld + col0), None, ld, None, accumulate)
 
     # -------------------------------------------------------------------------------- blocks
@@ -286,9 +322,7 @@ class build_matrix_elements(object):
         """Device tensor [(hi-lo)*dim2, dim1*dim2]: rows of H2[m1][m2] whose fragment-1 bra state has
         matrix position in bra_range=[lo,hi) (default: all).  Rows outside every charge-allowed class
         stay zero (build_H.py:65)."""
-        rho, T, U, V, nuc, n_elec = self.data
         f1, f2 = self._frag(m1), self._frag(m2)
-        n1, n2 = f1.n_orb, f2.n_orb
         ctx = self.dev.ctx
         lo, hi = (0, f1.dim) if bra_range is None else bra_range
         D = f1.dim * f2.dim
@@ -297,15 +331,65 @@ class build_matrix_elements(object):
         else:
             assert out.shape == ((hi - lo) * f2.dim, D)
             out.zero_()
+        for d1, c1, c2, A, B, K, ld in self._dimer_class_factors(m1, m2, (lo, hi) if bra_range is not None else None):
+            off1 = self._index(lambda: c1.offsets(f1, f2.dim * D, f2.dim, bra_base=lo), ("off1", m1, m2, d1, lo, hi))
+            off2 = self._index(lambda: c2.offsets(f2, D, 1), ("off2", m1, m2, d1))
+            with self._timed(self, "dimer_class_d%+d" % d1, 2.0 * c1.P * c2.P * K):
+                ctx.gemm_scatter(c1.P, c2.P, K, 1.0, A, ld, B, ld, out, off1, 0, off2, False)
+        return out
+
+    def H2_moments_device(self, m1, m2, shard=(0, 1), group=None):
+        """Streamed dimer block: device tensor [5, 2] = (sum, sum of squares) of every element of each charge-transfer
+        class of H2[m1][m2], formed tile by tile and consumed on chip (xr_gemm_reduce) -- for blocks that cannot be
+        stored (1e12 elements at 1000 states/fragment).  With shard=(rank, world) each rank builds the factor rows of ITS
+        bra slab of BOTH fragments (so it only ever needs its slab of the densities); the fragment-2 factor slabs are
+        exchanged by one NCCL all-gather per class -- the one real exchange step of the path -- and every rank then
+        streams its slab of rows against all columns.  Sum the results over ranks."""
+        import torch.distributed as dist
+        from .distributed import slab_bounds
+        rank, world = shard
+        f1, f2 = self._frag(m1), self._frag(m2)
+        ctx = self.dev.ctx
+        r1 = slab_bounds(f1.dim, rank, world)[:2] if world > 1 else None
+        r2 = slab_bounds(f2.dim, rank, world)[:2] if world > 1 else None
+        moments = self.dev.zeros((5, 2))
+        for d1, c1, c2, A, B, K, ld in self._dimer_class_factors(m1, m2, r1, r2, skip_empty=False):
+            n_cols = c2.P
+            if world > 1:
+                # equal-size slabs for the collective: pad with zero rows (they add nothing to either moment)
+                rows = max(_PairClass(f2, -d1, slab_bounds(f2.dim, r, world)[:2]).P for r in range(world))
+                if rows == 0:
+                    continue
+                mine = self.dev.zeros((rows, ld))
+                if c2.P:
+                    ctx.copy2d_scaled(mine, ld, B, ld, c2.P, ld, 1.0)
+                B = self.dev.empty((world * rows, ld))
+                dist.all_gather_into_tensor(B, mine, group=group)
+                n_cols = world * rows
+            if c1.P == 0 or n_cols == 0:
+                continue
+            with self._timed(self, "dimer_stream_d%+d" % d1, 2.0 * c1.P * n_cols * K):
+                ctx.gemm_reduce(c1.P, n_cols, K, 1.0, A, ld, B, ld, moments.data_ptr() + 16 * (d1 + 2))
+        return moments
+
+    def H2_moments(self, m1, m2, shard=(0, 1)):
+        out = self.dev.download(self.H2_moments_device(m1, m2, shard))
+        return float(out[:, 0].sum()), float(out[:, 1].sum())
+
+    def _dimer_class_factors(self, m1, m2, bra_range1=None, bra_range2=None, skip_empty=True):
+        """Yields (d1, class of fragment 1, class of fragment 2, A [P1, ld], B [P2, ld], K, ld) for the five
+        charge-transfer classes of build_H.py:69-100; H2[(i1,i2),(j1,j2)] = sum_k A[(i1,j1),k] B[(i2,j2),k]."""
+        rho, T, U, V, nuc, n_elec = self.data
+        f1, f2 = self._frag(m1), self._frag(m2)
+        n1, n2 = f1.n_orb, f2.n_orb
+        ctx = self.dev.ctx
         s2 = lambda c2: _parity(f2.n_elec_ref, c2)
 
         for d1 in (-2, -1, 0, 1, 2):
-            c1 = _PairClass(f1, d1, (lo, hi) if bra_range is not None else None)
-            c2 = _PairClass(f2, -d1)
-            if c1.P == 0 or c2.P == 0:
-                continue
-            off1 = self._index(lambda: c1.offsets(f1, f2.dim * D, f2.dim, bra_base=lo), ("off1", m1, m2, d1, lo, hi))
-            off2 = self._index(lambda: c2.offsets(f2, D, 1), ("off2", m1, m2, d1))
+            c1 = _PairClass(f1, d1, bra_range1)
+            c2 = _PairClass(f2, -d1, bra_range2)
+            if (c1.P == 0 or c2.P == 0) and skip_empty:
+                continue            # (skip_empty=False: ranks with an empty slab still take part in the factor exchange)
             if d1 == 0:
                 K = n2 * n2 + 2
                 ld = _even(K)
@@ -363,9 +447,7 @@ class build_matrix_elements(object):
                 # annihilator side: [ a | 2 V1222.caa ]
                 self._fill_raw(Y, ld, 0, y, "a", cy, sign=sy)
                 self._fill_contracted(Y, ld, ny, y, "caa", cy, V2, scale=2.0, sign=sy)
-            with self._timed(self, "dimer_class_d%+d" % d1, 2.0 * c1.P * c2.P * K):
-                ctx.gemm_scatter(c1.P, c2.P, K, 1.0, A, ld, B, ld, out, off1, 0, off2, False)
-        return out
+            yield d1, c1, c2, A, B, K, ld
 
     # ------------------------------------------------------------------------------ trimers
     def _trimer_classes(self, ms):

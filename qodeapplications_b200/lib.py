@@ -39,6 +39,7 @@ _PROTOTYPES = {
     "xr_upload": (_int, [_ptr, _ptr, _ptr, ctypes.c_size_t]),
     "xr_download": (_int, [_ptr, _ptr, _ptr, ctypes.c_size_t]),
     "xr_gemm_scatter": (_int, [_ptr, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _int]),
+    "xr_gemm_reduce": (_int, [_ptr, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr]),
     "xr_copy2d_scaled": (_int, [_ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _dbl]),
     "xr_scatter_const": (_int, [_ptr, _ptr, _ptr, _i64, _dbl, _int]),
     "xr_permute_copy": (_int, [_ptr, _ptr, _ptr, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _dbl]),
@@ -150,6 +151,9 @@ class Context(object):
     def gemm_scatter(self, M, N, K, alpha, A, lda, B, ldb, C, offM=None, ldc=0, offN=None, accumulate=False):
         check(self.lib.xr_gemm_scatter(self.handle, M, N, K, float(alpha), _p(A), lda, _p(B), ldb, _p(C), _p(offM),
                                        ldc, _p(offN), 1 if accumulate else 0), "xr_gemm_scatter")
+
+    def gemm_reduce(self, M, N, K, alpha, A, lda, B, ldb, moments):
+        check(self.lib.xr_gemm_reduce(self.handle, M, N, K, float(alpha), _p(A), lda, _p(B), ldb, _p(moments)), "xr_gemm_reduce")
 
     def copy2d_scaled(self, dst, dst_ld, src, src_ld, rows, cols, alpha=1.0):
         check(self.lib.xr_copy2d_scaled(self.handle, _p(dst), dst_ld, _p(src), src_ld, rows, cols, float(alpha)),

@@ -262,6 +262,22 @@ class fragment(object):
         self.state_indices = state_indices
 
 
+def slab_fragment(frag, lo, hi, n_states):
+    """The same fragment holding only the densities whose BRA state sits at matrix positions [lo, hi)
+    (the per-rank input of a sharded build: build_matrix_elements(..., held={m: (lo, hi)}))."""
+    where = {state: p for p, state in enumerate(frag.state_indices)}
+    keep = {chg: [i for i in range(n) if lo <= where[(chg, i)] < hi] for chg, n in n_states.items()}
+    rho = {}
+    for op, blocks in frag.rho.items():
+        rho[op] = {}
+        for (ci, cj), block in blocks.items():
+            arr = numpy.asarray(block)
+            rho[op][(ci, cj)] = numpy.ascontiguousarray(arr[keep[ci]]) if keep[ci] else arr[:0]
+    out = fragment(rho, frag.n_elec_ref, frag.state_indices)
+    out.n_states = dict(n_states)
+    return out
+
+
 def general_state_indices(n_states, ref_state=(0, 0)):
     """general-XRCC/Be631g.py:81-85: reference state first, rest of its charge, then other charges."""
     ref_chg, ref_idx = ref_state

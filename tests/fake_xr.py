@@ -48,6 +48,18 @@ class FakeContext(object):
         else:
             c[at] = val
 
+    def gemm_reduce(self, M, N, K, alpha, A, lda, B, ldb, moments):
+        self.launches += 1
+        if M <= 0 or N <= 0:
+            return
+        assert lda % 2 == 0 and ldb % 2 == 0, "xr_gemm_reduce needs even leading dimensions"
+        Am = numpy.lib.stride_tricks.as_strided(_view(A, (M - 1) * lda + K).copy(), (M, K), (8 * lda, 8))
+        Bm = numpy.lib.stride_tricks.as_strided(_view(B, (N - 1) * ldb + K).copy(), (N, K), (8 * ldb, 8))
+        C = alpha * (Am @ Bm.T)
+        m = _view(moments, 2)
+        m[0] += C.sum()
+        m[1] += (C * C).sum()
+
     def copy2d_scaled(self, dst, dst_ld, src, src_ld, rows, cols, alpha=1.0):
         self.launches += 1
         if rows <= 0 or cols <= 0:

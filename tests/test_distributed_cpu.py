@@ -37,6 +37,22 @@ def _worker(rank, world, port, out_dir):
     moments = build.reduced_moments()
     payload = {"H2_%d%d" % k: build.full(*k).numpy() for k in dimers}
     payload["moments"] = numpy.array(moments[(0, 1, 2)])
+    # streamed dimer with the factor exchange (all-gather of the fragment-2 factor slabs)
+    t = eng.H2_moments_device(0, 2, shard=(rank, world))
+    dist.all_reduce(t)
+    payload["dimer_moments"] = t.numpy().sum(axis=0)
+    # the same with each rank holding only ITS bra slab of the densities (the cfg5 input layout)
+    from qodeapplications_b200.general.distributed import slab_bounds
+    n_states = synth.CONFIGS["toy3"]["n_states"]
+    held, frags = {}, list(system["fragments"])
+    for m in (0, 2):
+        lo, hi = slab_bounds(len(frags[m].state_indices), rank, world)[:2]
+        held[m] = (lo, hi)
+        frags[m] = synth.slab_fragment(frags[m], lo, hi, n_states)
+    eng_slab = build_matrix_elements(frags, system["symm"], system["nuc"], device=FakeDevice(), held=held)
+    t = eng_slab.H2_moments_device(0, 2, shard=(rank, world))
+    dist.all_reduce(t)
+    payload["dimer_moments_held"] = t.numpy().sum(axis=0)
     numpy.savez(os.path.join(out_dir, "rank%d.npz" % rank), **payload)
     dist.destroy_process_group()
 
@@ -55,3 +71,7 @@ def test_two_rank_sharded_build_matches_reference(tmp_path):
             assert numpy.abs(out["H2_%d%d" % (m1, m2)] - ref).max() <= 1e-10 * numpy.abs(ref).max()
         assert abs(out["moments"][1] - (ref3 ** 2).sum()) <= 1e-10 * (ref3 ** 2).sum()
         assert abs(out["moments"][0] - ref3.sum()) <= 1e-9 * numpy.abs(ref3).sum()
+        ref2 = g["H2_02"]
+        assert abs(out["dimer_moments"][1] - (ref2 ** 2).sum()) <= 1e-11 * (ref2 ** 2).sum()
+        assert abs(out["dimer_moments"][0] - ref2.sum()) <= 1e-10 * numpy.abs(ref2).sum()
+        assert numpy.allclose(out["dimer_moments_held"], out["dimer_moments"], rtol=1e-12, atol=0)

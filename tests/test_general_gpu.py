@@ -242,3 +242,63 @@ def test_cfg3_trimer_moments_and_sampled_elements(dev):
         J = numpy.unravel_index(j, dims)
         ref = eo.trimer((0, 1, 2), tuple(st[k][I[k]] for k in range(3)), tuple(st[k][J[k]] for k in range(3)))
         assert abs(val - (ref or 0.0)) <= TOL * scale
+
+
+# ------------------------------------------------------------------------------- streamed dimers (cfg5 path)
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 2), (7, 5, 3), (64, 64, 16), (130, 70, 37), (257, 300, 326), (1000, 333, 36),
+                                   (3000, 2100, 2306)])
+def test_gemm_reduce(dev, M, N, K):
+    rng = numpy.random.default_rng(M + 7 * N + 13 * K)
+    lda = K + K % 2
+    ldb = lda + 2
+    A, B = rng.standard_normal((M, lda)), rng.standard_normal((N, ldb))
+    C = -0.5 * A[:, :K] @ B[:, :K].T
+    moments = dev.upload(numpy.array([[1.0, 2.0], [0.0, 0.0]]))
+    dev.ctx.gemm_reduce(M, N, K, -0.5, dev.upload(A), lda, dev.upload(B), ldb, moments)
+    out = dev.download(moments)
+    assert abs(out[0, 1] - 2.0 - (C * C).sum()) <= 1e-12 * (C * C).sum()
+    assert abs(out[0, 0] - 1.0 - C.sum()) <= 1e-12 * numpy.abs(C).sum()
+    assert numpy.array_equal(out[1], [0.0, 0.0])
+    again = dev.upload(numpy.array([[1.0, 2.0], [0.0, 0.0]]))
+    dev.ctx.gemm_reduce(M, N, K, -0.5, dev.upload(A), lda, dev.upload(B), ldb, again)
+    assert numpy.array_equal(dev.download(again), out), "the reduction must be deterministic"
+
+
+@pytest.mark.parametrize("name", ["toy", "toy5", "toyh", "cfg1"])
+def test_streamed_dimer_moments_equal_dense_block(dev, name):
+    system = synth.make_system(name)
+    eng = _engine(system, dev)
+    H2 = eng.H2_device(0, 1)
+    per_class = dev.download(eng.H2_moments_device(0, 1))
+    sumsq, total = float((H2 * H2).sum()), float(H2.sum())
+    assert abs(per_class[:, 1].sum() - sumsq) <= 1e-12 * sumsq
+    assert abs(per_class[:, 0].sum() - total) <= 1e-11 * float(H2.abs().sum())
+
+
+def test_streamed_dimer_from_device_resident_bra_slabs(dev):
+    """Each 'rank' holds only its bra slab of the densities, already on the device (the cfg5 input layout);
+    the slabs' class moments add up to those of the whole block."""
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    from qodeapplications_b200.general.distributed import slab_bounds
+    name = "mid"
+    system = synth.make_system(name)
+    n_states = synth.CONFIGS[name]["n_states"]
+    whole = dev.download(_engine(system, dev).H2_moments_device(0, 1))
+    dim = len(system["fragments"][0].state_indices)
+    world, acc = 3, numpy.zeros((5, 2))
+    for rank in range(world):
+        lo, hi = slab_bounds(dim, rank, world)[:2]
+        frags = list(system["fragments"])
+        frags[0] = synth.slab_fragment(frags[0], lo, hi, n_states)
+        for op in frags[0].rho:
+            for key, block in frags[0].rho[op].items():
+                frags[0].rho[op][key] = dev.upload(block)          # device-resident input
+        eng = build_matrix_elements(frags, system["symm"], system["nuc"], device=dev, held={0: (lo, hi)})
+        part = dev.zeros((5, 2))
+        for d1, c1, c2, A, B, K, ld in eng._dimer_class_factors(0, 1, (lo, hi), None):
+            dev.ctx.gemm_reduce(c1.P, c2.P, K, 1.0, A, ld, B, ld, part.data_ptr() + 16 * (d1 + 2))
+        acc += dev.download(part)
+        with pytest.raises(ValueError):
+            eng.H2_device(0, 1)                                     # needs bra states this engine does not hold
+    assert numpy.allclose(acc, whole, rtol=1e-12, atol=1e-12 * numpy.abs(whole).max())

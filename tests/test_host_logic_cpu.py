@@ -143,3 +143,16 @@ def test_hermitian_det_variants_host_logic(which):
     _close(H1[1], g["H1_1"])
     assert numpy.count_nonzero(g["H2"]) > 20
     _close(H2, g["H2"])
+
+
+@pytest.mark.parametrize("name", ["toy", "toy5"])
+def test_general_streamed_dimer_moments_host_logic(name):
+    """H2_moments (the consumer for dimer blocks that cannot be stored) equals the moments of the dense block"""
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    g = numpy.load(os.path.join(GOLDEN, "general_%s.npz" % name))
+    system = synth.make_system(name)
+    eng = build_matrix_elements(system["fragments"], system["symm"], system["nuc"], device=FakeDevice())
+    ref = g["H2_01"]
+    s, q = eng.H2_moments(0, 1)
+    assert abs(q - (ref ** 2).sum()) <= 1e-11 * (ref ** 2).sum()
+    assert abs(s - ref.sum()) <= 1e-10 * numpy.abs(ref).sum()
