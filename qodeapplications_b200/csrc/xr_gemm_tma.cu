@@ -21,7 +21,7 @@ struct GemmTmaParams {
     int64_t ldc;
     const int64_t* offN;
     int accumulate;
-    int64_t tiles_n;
+    int64_t tiles_m, tiles_n;
     double* partials;      // REDUCE mode: [tiles][2] per-CTA (sum, sum of squares); nothing is stored to C
 };
 
@@ -35,6 +35,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
 
 constexpr int TBM = 64, TBN = 64, TBK = 16, TSTAGES = 3, TTHREADS = 128;
 constexpr int TILE_A_BYTES = TBM * TBK * 8, TILE_B_BYTES = TBN * TBK * 8;     // 8 KB each, 1024-byte aligned
+constexpr int GROUP_M = 16;
 constexpr size_t TMA_SMEM = (size_t)TSTAGES * (TILE_A_BYTES + TILE_B_BYTES) + 1024;
 
 // byte offset of element (row r, k) inside a 128-byte-swizzled [rows][16 doubles] tile
@@ -51,8 +52,13 @@ gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int warp_m = warp & 1, warp_n = warp >> 1;
+    // Grouped rasterisation: consecutive CTAs walk GROUP_M row tiles before moving to the next column tile, so one resident
+    // wave (592 CTAs) touches ~16 + 37 tile strips instead of 1 + 592 and both operands stay in L2 for large N.
     const int64_t tile = blockIdx.x;
-    const int64_t m0 = (tile / p.tiles_n) * TBM, n0 = (tile % p.tiles_n) * TBN;
+    const int64_t per_group = GROUP_M * p.tiles_n;
+    const int64_t first_m = (tile / per_group) * GROUP_M;
+    const int64_t group_m = p.tiles_m - first_m < GROUP_M ? p.tiles_m - first_m : GROUP_M;
+    const int64_t m0 = (first_m + (tile % per_group) % group_m) * TBM, n0 = ((tile % per_group) / group_m) * TBN;
     const int KT = (int)((p.K + TBK - 1) / TBK);
 
     if (tid == 0) {
@@ -209,8 +215,8 @@ int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alp
     if (K < 1 || M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return XR_ERR_UNSUPPORTED;
     CUtensorMap mapA, mapB;
     if (!make_map(&mapA, A, M, K, lda) || !make_map(&mapB, B, N, K, ldb)) return XR_ERR_UNSUPPORTED;
-    GemmTmaParams p{M, N, K, alpha, C, offM, ldc, offN, accumulate, (N + TBN - 1) / TBN, nullptr};
-    const int64_t tiles = ((M + TBM - 1) / TBM) * p.tiles_n;
+    GemmTmaParams p{M, N, K, alpha, C, offM, ldc, offN, accumulate, (M + TBM - 1) / TBM, (N + TBN - 1) / TBN, nullptr};
+    const int64_t tiles = p.tiles_m * p.tiles_n;
     XR_REQUIRE(tiles < (1ll << 31), "xr_gemm_scatter: too many tiles (%lld)", (long long)tiles);
     XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
     gemm_tma_scatter_kernel<false><<<(unsigned)tiles, TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
@@ -277,8 +283,8 @@ extern "C" int xr_gemm_reduce(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, doub
     XR_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "xr_gemm_reduce: dimension too large");
     CUtensorMap mapA, mapB;
     XR_REQUIRE(make_map(&mapA, A, M, K, lda) && make_map(&mapB, B, N, K, ldb), "xr_gemm_reduce: cuTensorMapEncodeTiled failed");
-    GemmTmaParams p{M, N, K, alpha, nullptr, nullptr, 0, nullptr, 0, (N + TBN - 1) / TBN, nullptr};
-    const int64_t tiles = ((M + TBM - 1) / TBM) * p.tiles_n;
+    GemmTmaParams p{M, N, K, alpha, nullptr, nullptr, 0, nullptr, 0, (M + TBM - 1) / TBM, (N + TBN - 1) / TBN, nullptr};
+    const int64_t tiles = p.tiles_m * p.tiles_n;
     XR_REQUIRE(tiles < (1ll << 31), "xr_gemm_reduce: too many tiles (%lld)", (long long)tiles);
     int rc = xr_ensure_scratch(ctx, (size_t)(tiles + RED_BLOCKS) * 2 * sizeof(double) + 256);
     if (rc != XR_OK) return rc;

@@ -71,23 +71,35 @@ class _FragInfo(object):
         return [(ci, ci - delta) for ci in self.charges if (ci - delta) in self.n_states]
 
 
+def _bra_states(info, chg, bra_range):
+    """[i_lo, i_hi): the states of charge chg selected by a bra range, which is None (all), a pair (lo, hi) of MATRIX
+    positions (a row slab of the block) or a dict {charge: (i_lo, i_hi)} of per-sector state ranges (a balanced shard:
+    every rank gets the same share of every charge sector)."""
+    if bra_range is None:
+        return 0, info.n_states[chg]
+    if isinstance(bra_range, dict):
+        i_lo, i_hi = bra_range.get(chg, (0, 0))
+        if not 0 <= i_lo <= i_hi <= info.n_states[chg]:
+            raise ValueError("state range %r outside charge sector %r" % ((i_lo, i_hi), chg))
+        return int(i_lo), int(i_hi)
+    inside = numpy.nonzero((info.pos[chg] >= bra_range[0]) & (info.pos[chg] < bra_range[1]))[0]
+    if len(inside) == 0:
+        return 0, 0
+    if int(inside[-1]) + 1 - int(inside[0]) != len(inside):
+        raise NotImplementedError("bra slab is not contiguous inside charge sector %r" % (chg,))
+    return int(inside[0]), int(inside[-1]) + 1
+
+
 class _PairClass(object):
     """All (bra,ket) state pairs of one fragment with bra charge - ket charge = delta, optionally
-    restricted to bra states whose matrix position lies in [bra_lo, bra_hi)."""
+    restricted to the bra states a bra range selects (_bra_states)."""
     def __init__(self, info, delta, bra_range=None):
         self.delta = delta
         self.sectors = []          # (ci, cj, i_lo, i_hi, row_offset)
         rows = 0
         for ci, cj in info.sectors(delta):
-            Ni, Nj = info.n_states[ci], info.n_states[cj]
-            i_lo, i_hi = 0, Ni
-            if bra_range is not None:
-                inside = numpy.nonzero((info.pos[ci] >= bra_range[0]) & (info.pos[ci] < bra_range[1]))[0]
-                if len(inside) == 0:
-                    continue
-                i_lo, i_hi = int(inside[0]), int(inside[-1]) + 1
-                if i_hi - i_lo != len(inside):
-                    raise NotImplementedError("bra slab is not contiguous inside charge sector %r" % (ci,))
+            Nj = info.n_states[cj]
+            i_lo, i_hi = _bra_states(info, ci, bra_range)
             if i_hi > i_lo and Nj > 0:
                 self.sectors.append((ci, cj, i_lo, i_hi, rows))
                 rows += (i_hi - i_lo) * Nj
@@ -119,10 +131,10 @@ def _even(k):
 
 class build_matrix_elements(object):
     def __init__(self, supersystem, integrals, nuc_repulsion, device=None, held=None):
-        """held (optional, for sharded inputs): {fragment index: (lo, hi)} -- the densities of that fragment are only
-        supplied for bra states whose matrix position lies in [lo, hi): rho[op][(ci,cj)] then has one leading row per HELD
-        bra state of charge ci (and the fragment object must carry ``n_states``).  Density blocks may also be CUDA torch
-        tensors already resident on the device."""
+        """held (optional, for sharded inputs): {fragment index: bra range} -- the densities of that fragment are only
+        supplied for the bra states the range selects, either (lo, hi) matrix positions or {charge: (i_lo, i_hi)} state
+        ranges per charge sector: rho[op][(ci,cj)] then has one leading row per HELD bra state of charge ci (and the
+        fragment object must carry ``n_states``).  Density blocks may also be CUDA torch tensors already on the device."""
         n_elec = [fragment.n_elec_ref for fragment in supersystem]
         rho = [fragment.rho for fragment in supersystem]
         self.data = rho, integrals.T, integrals.U, integrals.V, nuc_repulsion, n_elec     # as build_H.py:41
@@ -185,16 +197,7 @@ class build_matrix_elements(object):
 
     def _held_range(self, m, chg):
         """[h_lo, h_hi): the bra states of charge chg of fragment m whose densities are held here"""
-        info = self._frag(m)
-        if m not in self._held:
-            return 0, info.n_states[chg]
-        lo, hi = self._held[m]
-        inside = numpy.nonzero((info.pos[chg] >= lo) & (info.pos[chg] < hi))[0]
-        if len(inside) == 0:
-            return 0, 0
-        if int(inside[-1]) + 1 - int(inside[0]) != len(inside):
-            raise NotImplementedError("held bra slab is not contiguous inside charge sector %r" % (chg,))
-        return int(inside[0]), int(inside[-1]) + 1
+        return _bra_states(self._frag(m), chg, self._held.get(m))
 
     def _rho(self, m, op, sector):
         """device tensor [N_bra(held)*N_ket, n^k] of rho[m][op][sector]"""
@@ -207,10 +210,10 @@ class build_matrix_elements(object):
             if isinstance(block, torch.Tensor):
                 if block.dtype != torch.float64 or not block.is_contiguous():
                     raise TypeError("device-resident densities must be contiguous float64 tensors")
-                self._rho_dev[key] = block.reshape(rows, -1)
+                self._rho_dev[key] = block.reshape(rows, info.n_orb ** len(op))
             else:
                 arr = numpy.asarray(block, dtype=numpy.float64)
-                self._rho_dev[key] = self.dev.upload(arr.reshape(rows, -1))
+                self._rho_dev[key] = self.dev.upload(arr.reshape(rows, info.n_orb ** len(op)))
         return self._rho_dev[key]
 
     def _rho_rows(self, m, op, ci, cj, i_lo, i_hi):
@@ -338,39 +341,58 @@ class build_matrix_elements(object):
                 ctx.gemm_scatter(c1.P, c2.P, K, 1.0, A, ld, B, ld, out, off1, 0, off2, False)
         return out
 
-    def H2_moments_device(self, m1, m2, shard=(0, 1), group=None):
+    def H2_moments_device(self, m1, m2, shard=(0, 1), group=None, inspect=None):
         """Streamed dimer block: device tensor [5, 2] = (sum, sum of squares) of every element of each charge-transfer
         class of H2[m1][m2], formed tile by tile and consumed on chip (xr_gemm_reduce) -- for blocks that cannot be
         stored (1e12 elements at 1000 states/fragment).  With shard=(rank, world) each rank builds the factor rows of ITS
-        bra slab of BOTH fragments (so it only ever needs its slab of the densities); the fragment-2 factor slabs are
+        bra states of BOTH fragments (_shard_range; so it only ever needs that part of the densities); the fragment-2 factor slabs are
         exchanged by one NCCL all-gather per class -- the one real exchange step of the path -- and every rank then
-        streams its slab of rows against all columns.  Sum the results over ranks."""
+        streams its slab of rows against all columns.  Sum the results over ranks.  inspect(d1, A, B, P1, P2, K), if given,
+        sees the factors of every class after the exchange (used by the tests' Gram-matrix identity at sizes where the
+        block itself cannot exist)."""
         import torch.distributed as dist
-        from .distributed import slab_bounds
         rank, world = shard
         f1, f2 = self._frag(m1), self._frag(m2)
         ctx = self.dev.ctx
-        r1 = slab_bounds(f1.dim, rank, world)[:2] if world > 1 else None
-        r2 = slab_bounds(f2.dim, rank, world)[:2] if world > 1 else None
+        r1, r2 = self._shard_range(m1, rank, world), self._shard_range(m2, rank, world)
         moments = self.dev.zeros((5, 2))
+        widest = None
+        if world > 1:       # rows of the widest fragment-2 factor slab of every class (equal-size slabs for the collective)
+            mine = [_PairClass(f2, -d1, r2).P for d1 in (-2, -1, 0, 1, 2)]
+            widest = self.dev.upload(numpy.array(mine, dtype=numpy.int64), numpy.int64)
+            dist.all_reduce(widest, op=dist.ReduceOp.MAX, group=group)
+            widest = self.dev.download(widest)
         for d1, c1, c2, A, B, K, ld in self._dimer_class_factors(m1, m2, r1, r2, skip_empty=False):
             n_cols = c2.P
             if world > 1:
-                # equal-size slabs for the collective: pad with zero rows (they add nothing to either moment)
-                rows = max(_PairClass(f2, -d1, slab_bounds(f2.dim, r, world)[:2]).P for r in range(world))
+                rows = int(widest[d1 + 2])       # zero rows pad the narrower slabs (they add nothing to either moment)
                 if rows == 0:
                     continue
-                mine = self.dev.zeros((rows, ld))
-                if c2.P:
-                    ctx.copy2d_scaled(mine, ld, B, ld, c2.P, ld, 1.0)
+                mine = B
+                if c2.P != rows:
+                    mine = self.dev.zeros((rows, ld))
+                    if c2.P:
+                        ctx.copy2d_scaled(mine, ld, B, ld, c2.P, ld, 1.0)
                 B = self.dev.empty((world * rows, ld))
                 dist.all_gather_into_tensor(B, mine, group=group)
                 n_cols = world * rows
             if c1.P == 0 or n_cols == 0:
                 continue
+            if inspect is not None:
+                inspect(d1, A, B, c1.P, n_cols, K)
             with self._timed(self, "dimer_stream_d%+d" % d1, 2.0 * c1.P * n_cols * K):
                 ctx.gemm_reduce(c1.P, n_cols, K, 1.0, A, ld, B, ld, moments.data_ptr() + 16 * (d1 + 2))
         return moments
+
+    def _shard_range(self, m, rank, world):
+        """The bra states of fragment m this rank streams: the slab it holds when the densities are sharded (held=),
+        else an equal share of EVERY charge sector (balanced: each rank gets the same pair count in every class)."""
+        if m in self._held:
+            return self._held[m]
+        if world == 1:
+            return None
+        from .distributed import balanced_shard
+        return balanced_shard(self._frag(m).n_states, rank, world)
 
     def H2_moments(self, m1, m2, shard=(0, 1)):
         out = self.dev.download(self.H2_moments_device(m1, m2, shard))

@@ -19,6 +19,17 @@ def slab_bounds(dim, rank, world):
     return min(rank * per, dim), min((rank + 1) * per, dim), per
 
 
+def balanced_shard(n_states, rank, world):
+    """{charge: (i_lo, i_hi)}: an equal share of the states of every charge sector -- the bra range of a rank in the
+    streamed dimer build, where every rank then has the same pair count in every charge-transfer class"""
+    out = {}
+    for chg, n in n_states.items():
+        base, extra = divmod(n, world)
+        lo = rank * base + min(rank, extra)
+        out[chg] = (lo, lo + base + (1 if rank < extra else 0))
+    return out
+
+
 class sharded_build(object):
     """Holds the output buffers of a (possibly multi-rank) build and runs one build step."""
     def __init__(self, engine, dimers, trimers, rank=0, world=1, group=None):

@@ -262,11 +262,21 @@ class fragment(object):
         self.state_indices = state_indices
 
 
-def slab_fragment(frag, lo, hi, n_states):
-    """The same fragment holding only the densities whose BRA state sits at matrix positions [lo, hi)
-    (the per-rank input of a sharded build: build_matrix_elements(..., held={m: (lo, hi)}))."""
+def _held_states(where, n_states, held, chg):
+    """state indices of charge chg selected by a bra range: (lo, hi) matrix positions or {charge: (i_lo, i_hi)}"""
+    if held is None:
+        return list(range(n_states[chg]))
+    if isinstance(held, dict):
+        i_lo, i_hi = held.get(chg, (0, 0))
+        return list(range(i_lo, i_hi))
+    return [i for i in range(n_states[chg]) if held[0] <= where[(chg, i)] < held[1]]
+
+
+def slab_fragment(frag, held, n_states):
+    """The same fragment holding only the densities whose BRA state the range ``held`` selects -- (lo, hi) matrix
+    positions or {charge: (i_lo, i_hi)} -- the per-rank input of a sharded build: build_matrix_elements(..., held={m: held})."""
     where = {state: p for p, state in enumerate(frag.state_indices)}
-    keep = {chg: [i for i in range(n) if lo <= where[(chg, i)] < hi] for chg, n in n_states.items()}
+    keep = {chg: _held_states(where, n_states, held, chg) for chg in n_states}
     rho = {}
     for op, blocks in frag.rho.items():
         rho[op] = {}
@@ -276,6 +286,41 @@ def slab_fragment(frag, lo, hi, n_states):
     out = fragment(rho, frag.n_elec_ref, frag.state_indices)
     out.n_states = dict(n_states)
     return out
+
+
+def make_device_slab_fragments(n_frag, n_orb, n_states, held, torch_device, seed=0, ops=("a", "c", "aa", "cc", "ca", "caa", "cca"),
+                               n_elec_ref=N_ELEC_REF):
+    """Fragments whose densities are drawn ON THE DEVICE and only for the bra states held[m] selects (see slab_fragment)
+    (BASELINE configs[4]: the full densities of 1000 states x 48 orbitals are ~450 GB per fragment and only ever exist
+    sharded).  Block (ci,cj) of op is a CUDA tensor [n_held_ci, N_cj, n, ...]; the random stream of a bra state depends
+    on (seed, fragment, op, sector, state) alone, so any sharding draws the same numbers."""
+    import torch
+    order = general_state_indices(n_states)
+    where = {state: p for p, state in enumerate(order)}
+    charges = list(n_states)
+    frags = []
+    for m in range(n_frag):
+        rho = {}
+        for o, op in enumerate(ops):
+            k, dchg = len(op), op_dchg(op)
+            rho[op] = {}
+            for ci in charges:
+                cj = ci - dchg
+                if cj not in n_states:
+                    continue
+                rows = _held_states(where, n_states, held.get(m), ci)
+                block = torch.empty((len(rows), n_states[cj]) + (n_orb,) * k, dtype=torch.float64, device=torch_device)
+                gen = torch.Generator(device=torch_device)
+                for r, i in enumerate(rows):
+                    gen.manual_seed(((seed * 64 + m) * 16 + o) * 1000003 + (ci + 8) * 100003 + i)
+                    # drawn in float32 (fast generator path), widened exactly: 110 GB per GPU at configs[4]
+                    draw = torch.empty(block[r].shape, dtype=torch.float32, device=torch_device)
+                    block[r].copy_(draw.normal_(0.0, n_orb ** (-k / 2), generator=gen))
+                rho[op][(ci, cj)] = block
+        f = fragment(rho, n_elec_ref, order)
+        f.n_states = dict(n_states)
+        frags.append(f)
+    return frags
 
 
 def general_state_indices(n_states, ref_state=(0, 0)):

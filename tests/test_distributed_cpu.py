@@ -48,11 +48,21 @@ def _worker(rank, world, port, out_dir):
     for m in (0, 2):
         lo, hi = slab_bounds(len(frags[m].state_indices), rank, world)[:2]
         held[m] = (lo, hi)
-        frags[m] = synth.slab_fragment(frags[m], lo, hi, n_states)
+        frags[m] = synth.slab_fragment(frags[m], (lo, hi), n_states)
     eng_slab = build_matrix_elements(frags, system["symm"], system["nuc"], device=FakeDevice(), held=held)
     t = eng_slab.H2_moments_device(0, 2, shard=(rank, world))
     dist.all_reduce(t)
     payload["dimer_moments_held"] = t.numpy().sum(axis=0)
+    # ... and with the balanced per-charge-sector shard as the held range
+    from qodeapplications_b200.general.distributed import balanced_shard
+    mine = balanced_shard(n_states, rank, world)
+    frags = list(system["fragments"])
+    for m in (0, 2):
+        frags[m] = synth.slab_fragment(frags[m], mine, n_states)
+    eng_sect = build_matrix_elements(frags, system["symm"], system["nuc"], device=FakeDevice(), held={0: mine, 2: mine})
+    t = eng_sect.H2_moments_device(0, 2, shard=(rank, world))
+    dist.all_reduce(t)
+    payload["dimer_moments_sector"] = t.numpy().sum(axis=0)
     numpy.savez(os.path.join(out_dir, "rank%d.npz" % rank), **payload)
     dist.destroy_process_group()
 
@@ -75,3 +85,4 @@ def test_two_rank_sharded_build_matches_reference(tmp_path):
         assert abs(out["dimer_moments"][1] - (ref2 ** 2).sum()) <= 1e-11 * (ref2 ** 2).sum()
         assert abs(out["dimer_moments"][0] - ref2.sum()) <= 1e-10 * numpy.abs(ref2).sum()
         assert numpy.allclose(out["dimer_moments_held"], out["dimer_moments"], rtol=1e-12, atol=0)
+        assert numpy.allclose(out["dimer_moments_sector"], out["dimer_moments"], rtol=1e-12, atol=0)

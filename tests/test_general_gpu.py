@@ -290,7 +290,7 @@ def test_streamed_dimer_from_device_resident_bra_slabs(dev):
     for rank in range(world):
         lo, hi = slab_bounds(dim, rank, world)[:2]
         frags = list(system["fragments"])
-        frags[0] = synth.slab_fragment(frags[0], lo, hi, n_states)
+        frags[0] = synth.slab_fragment(frags[0], (lo, hi), n_states)
         for op in frags[0].rho:
             for key, block in frags[0].rho[op].items():
                 frags[0].rho[op][key] = dev.upload(block)          # device-resident input

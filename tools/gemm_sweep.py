@@ -29,3 +29,19 @@ for (M, N, K, scatter) in [(15272, 15272, 326, False), (15272, 15272, 326, True)
     print(json.dumps({"M": M, "N": N, "K": K, "scatter": scatter, "ms": best, "tflops": 2.0 * M * N * K / best / 1e9,
                       "write_GBs": 8.0 * M * N / best / 1e6}))
     del A, B, C
+
+# xr_gemm_reduce (streamed dimer classes; nothing is written) at configs[4] per-rank shapes
+for (M, N, K) in [(47483, 379864, 2306), (31190, 249516, 96), (7569, 60552, 2304), (15272, 15272, 326)]:
+    ld = K + (K & 1)
+    A = torch.randn((M, ld), dtype=torch.float64, device=dev.torch_device)
+    B = torch.randn((N, ld), dtype=torch.float64, device=dev.torch_device)
+    mom = dev.zeros((2,))
+    run = lambda: dev.ctx.gemm_reduce(M, N, K, 1.0, A, ld, B, ld, mom)
+    run(); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    print(json.dumps({"op": "gemm_reduce", "M": M, "N": N, "K": K, "ms": best, "tflops": 2.0 * M * N * K / best / 1e9}))
+    del A, B
