@@ -123,6 +123,20 @@ int xr_permute_copy(xr_ctx* ctx, double* dst, const double* src, int nd, const i
 /* C[idx[t]] (= or +=) value for t < count  (Kronecker-delta terms; idx is a device int64 table). */
 int xr_scatter_const(xr_ctx* ctx, double* C, const int64_t* idx, int64_t count, double value, int accumulate);
 
+/* Expansion of a fragment block into the supersystem matrix (the consumer of the build): replaces the interpreter loops
+ * of general-XRCC/hamiltonian.py:21-84 (braket_loops; hermitian-XRCC/hamiltonian.py is the two-body subset) and the
+ * H1 (x) 1 einsums of hermitian-XRCC/mains/workflow.py:216-226.
+ *
+ *     H[offR[r] + offC[c] + offS[s]] += alpha * src[r*ld + c]        r < R, c < Cn, s < S
+ *
+ * offR/offC place the bra/ket states of the block's k fragments, offS the common state of the spectator fragments
+ * (device int64 tables; offS may be NULL when S == 1).  With min_transitions > 0 an element is skipped unless at least
+ * that many of the k sub-fragments change state between r and c, the digits of r and c over dims_sub[0..k) (a HOST
+ * array, k <= 4, last fastest): hamiltonian.py:44-56 reads trimer couplings only where >= 2 fragments change. */
+int xr_embed_add(xr_ctx* ctx, double* H, const double* src, int64_t ld, int64_t R, int64_t Cn, int64_t S,
+                 const int64_t* offR, const int64_t* offC, const int64_t* offS, int k, const int64_t* dims_sub,
+                 int min_transitions, double alpha);
+
 /* Streamed three-factor contraction, the trimer classes of general-XRCC/build_H.py:103-188
  * after the rho x V precontraction:
  *

@@ -307,3 +307,40 @@ def trimer_class_moments(W, beta, gamma):
     Gb, Gg = beta.T @ beta, gamma.T @ gamma
     sumsq = numpy.einsum("rsuv,ru,sv->", GW, Gb, Gg, optimize=True)
     return float(total), float(sumsq)
+
+
+# ------------------------------------------------------------------------------- consumer: supersystem matrix
+
+def supersystem_matrix(dims, H):
+    """NumPy restatement of general-XRCC/hamiltonian.py:21-84 (braket_loops; hermitian-XRCC/hamiltonian.py when H has no
+    trimer member), allowing unequal fragment dimensions.  Every block is embedded with Kronecker deltas on the spectator
+    fragments; trimer couplings are read only where at least two of their fragments change state (hamiltonian.py:44-56)."""
+    import itertools
+    F = len(dims)
+    D = int(numpy.prod(dims))
+    Hmat = numpy.zeros(tuple(dims) + tuple(dims))
+    eyes = [numpy.eye(d) for d in dims]
+    letters_b, letters_k = "abcdefgh"[:F], "ijklmnop"[:F]
+
+    def embed(frags, block):
+        block = numpy.asarray(block, dtype=numpy.float64).reshape([dims[m] for m in frags] * 2)
+        operands, subs = [block], ["".join(letters_b[m] for m in frags) + "".join(letters_k[m] for m in frags)]
+        for m in range(F):
+            if m not in frags:
+                operands.append(eyes[m])
+                subs.append(letters_b[m] + letters_k[m])
+        return numpy.einsum(",".join(subs) + "->" + letters_b + letters_k, *operands)
+
+    for M in range(F):
+        Hmat += embed((M,), H[0][M])
+    for M, N in itertools.combinations(range(F), 2):
+        Hmat += embed((M, N), H[1][M][N])
+    if len(H) > 2:
+        for M, N, O in itertools.combinations(range(F), 3):
+            sub = [dims[M], dims[N], dims[O]]
+            block = numpy.array(H[2][M][N][O], dtype=numpy.float64).reshape(sub * 2)
+            idx = numpy.indices(sub * 2)
+            changed = sum((idx[t] != idx[3 + t]).astype(int) for t in range(3))
+            block[changed < 2] = 0.0
+            Hmat += embed((M, N, O), block)
+    return Hmat.reshape(D, D)

@@ -42,6 +42,7 @@ _PROTOTYPES = {
     "xr_gemm_reduce": (_int, [_ptr, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr]),
     "xr_copy2d_scaled": (_int, [_ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _dbl]),
     "xr_scatter_const": (_int, [_ptr, _ptr, _ptr, _i64, _dbl, _int]),
+    "xr_embed_add": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _int, _ptr, _int, _dbl]),
     "xr_permute_copy": (_int, [_ptr, _ptr, _ptr, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _dbl]),
     "xr_trimer_stream": (_int, [_ptr, _int, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _int,
                                 _ptr, _ptr, _ptr, _ptr, _ptr]),
@@ -164,6 +165,11 @@ class Context(object):
         arr = _i64 * nd
         check(self.lib.xr_permute_copy(self.handle, _p(dst), _p(src), nd, arr(*[int(x) for x in shape]),
                                        arr(*[int(x) for x in src_strides]), float(alpha)), "xr_permute_copy")
+
+    def embed_add(self, H, src, ld, R, Cn, S, offR, offC, offS=None, dims_sub=(), min_transitions=0, alpha=1.0):
+        dims = (ctypes.c_int64 * max(1, len(dims_sub)))(*[int(d) for d in dims_sub])
+        check(self.lib.xr_embed_add(self.handle, _p(H), _p(src), ld, R, Cn, S, _p(offR), _p(offC), _p(offS), len(dims_sub),
+                                    dims, int(min_transitions), float(alpha)), "xr_embed_add")
 
     def scatter_const(self, C, idx, count, value, accumulate=False):
         check(self.lib.xr_scatter_const(self.handle, _p(C), _p(idx), count, float(value), 1 if accumulate else 0),

@@ -70,6 +70,23 @@ class FakeContext(object):
         D = numpy.lib.stride_tricks.as_strided(d, (rows, cols), (8 * dst_ld, 8))
         D[...] = alpha * S
 
+    def embed_add(self, H, src, ld, R, Cn, S, offR, offC, offS=None, dims_sub=(), min_transitions=0, alpha=1.0):
+        self.launches += 1
+        if R <= 0 or Cn <= 0 or S <= 0:
+            return
+        assert S == 1 or offS is not None
+        block = numpy.lib.stride_tricks.as_strided(_view(src, (R - 1) * ld + Cn), (R, Cn), (8 * ld, 8)).copy()
+        if min_transitions > 0:
+            assert 1 <= len(dims_sub) <= 4 and int(numpy.prod(dims_sub)) == R == Cn
+            digits = numpy.indices(list(dims_sub)).reshape(len(dims_sub), -1)
+            changed = (digits[:, :, None] != digits[:, None, :]).sum(axis=0)
+            block[changed < min_transitions] = 0.0
+        oR, oC = _view(offR, R, numpy.int64), _view(offC, Cn, numpy.int64)
+        oS = _view(offS, S, numpy.int64) if offS is not None else numpy.zeros(1, dtype=numpy.int64)
+        at = (oR[:, None, None] + oS[None, :, None] + oC[None, None, :])
+        h = _view(H, int(at.max()) + 1)
+        numpy.add.at(h, at.reshape(-1), numpy.broadcast_to(alpha * block[:, None, :], at.shape).reshape(-1))
+
     def scatter_const(self, C, idx, count, value, accumulate=False):
         self.launches += 1
         if count <= 0:

@@ -1,0 +1,63 @@
+"""Consumer of the build (supersystem-matrix expansion, general-XRCC/hamiltonian.py): the oracle restatement against the
+reference's own outputs (tests/golden/supersystem_hmat.npz, oracle/gen_golden_hmat.py), and the product's host logic
+(offset tables, transition mask plumbing) on the TEST-ONLY NumPy device stand-in."""
+import os
+import sys
+import numpy
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+GOLDEN = os.path.join(HERE, "golden")
+
+from oracle import general_oracle as go
+from gen_golden_hmat import random_blocks, toy3_blocks
+from fake_xr import FakeDevice
+
+CASES = ["rand4x3", "rand3x4", "herm3x4", "herm2x5"]
+
+
+def _case(tag):
+    g = numpy.load(os.path.join(GOLDEN, "supersystem_hmat.npz"))
+    seed, F, spf, trimers = (int(x) for x in g[tag + "_meta"])
+    return random_blocks(seed, F, spf, bool(trimers)), F, spf, g[tag]
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_oracle_matches_reference_braket_loops(tag):
+    H, F, spf, ref = _case(tag)
+    assert numpy.abs(go.supersystem_matrix([spf] * F, H) - ref).max() <= 1e-13 * numpy.abs(ref).max()
+
+
+def test_oracle_matches_reference_on_toy3_blocks():
+    H, spf = toy3_blocks()
+    ref = numpy.load(os.path.join(GOLDEN, "supersystem_hmat.npz"))["toy3"]
+    assert numpy.abs(go.supersystem_matrix([spf] * 3, H) - ref).max() <= 1e-13 * numpy.abs(ref).max()
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_braket_loops_host_logic(tag):
+    from qodeapplications_b200.general.hamiltonian import braket_loops
+    H, F, spf, ref = _case(tag)
+    Hmat = numpy.zeros((spf ** F, spf ** F))
+    braket_loops(Hmat, F, spf, H, device=FakeDevice())
+    assert numpy.abs(Hmat - ref).max() <= 1e-13 * numpy.abs(ref).max()
+    braket_loops(Hmat, F, spf, H, device=FakeDevice())            # the reference accumulates: Hmat[I,J] += ...
+    assert numpy.abs(Hmat - 2 * ref).max() <= 1e-13 * numpy.abs(ref).max()
+
+
+def test_unequal_fragment_dimensions_host_logic():
+    from qodeapplications_b200.general.hamiltonian import supersystem_matrix
+    rng = numpy.random.default_rng(5)
+    dims = [2, 4, 3]
+    H1 = [rng.standard_normal((d, d)) for d in dims]
+    H2 = [[rng.standard_normal((dims[M] * dims[N],) * 2) if M < N else None for N in range(3)] for M in range(3)]
+    H3 = [[[rng.standard_normal((24, 24)) if (M, N, O) == (0, 1, 2) else None for O in range(3)] for N in range(3)] for M in range(3)]
+    big = supersystem_matrix(dims, FakeDevice()).add_all((H1, H2, H3))
+    ref = go.supersystem_matrix(dims, (H1, H2, H3))
+    assert numpy.abs(big.matrix.numpy() - ref).max() <= 1e-13 * numpy.abs(ref).max()
+    with pytest.raises(ValueError):
+        big.add((1, 0), H2[0][1])
+    with pytest.raises(ValueError):
+        big.add((0, 1), H2[0][2])
