@@ -137,6 +137,13 @@ int xr_embed_add(xr_ctx* ctx, double* H, const double* src, int64_t ld, int64_t 
                  const int64_t* offR, const int64_t* offC, const int64_t* offS, int k, const int64_t* dims_sub,
                  int min_transitions, double alpha);
 
+/* out[i*ldo + j] = C0[i*ldc0 + j] (delta_ij when C0 is NULL) + sign * sum_k A[i*lda + k] * B[k*ldb + j],  sign = +-1,
+ * with every product and the running sum carried in double-double (~106 bits).  The two halves of the Newton polish
+ * X <- X + X (I - M X) of the overlap inverse: hermitian-XRCC/get_xr_result.py:165,202,246,285 call
+ * qode.math.precise_numpy_inverse (an extended-precision refinement of numpy's inverse). out must not alias A or B. */
+int xr_gemm_dd(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb,
+               const double* C0, int64_t ldc0, double sign, double* out, int64_t ldo);
+
 /* Streamed three-factor contraction, the trimer classes of general-XRCC/build_H.py:103-188
  * after the rho x V precontraction:
  *

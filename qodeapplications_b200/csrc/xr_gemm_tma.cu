@@ -23,7 +23,11 @@ struct GemmTmaParams {
     int accumulate;
     int64_t tiles_m, tiles_n;
     double* partials;      // REDUCE mode: [tiles][2] per-CTA (sum, sum of squares); nothing is stored to C
+    int kt_per_split;      // SPLITK mode: k-tiles per blockIdx.y slice; raw partial tiles go to ws[split][M][N]
+    double* ws;
 };
+
+enum { MODE_SCATTER = 0, MODE_REDUCE = 1, MODE_SPLITK = 2 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
@@ -41,7 +45,7 @@ constexpr size_t TMA_SMEM = (size_t)TSTAGES * (TILE_A_BYTES + TILE_B_BYTES) + 10
 // byte offset of element (row r, k) inside a 128-byte-swizzled [rows][16 doubles] tile
 __device__ __forceinline__ int swz(int r, int k) { return r * 128 + ((((k >> 1) ^ (r & 7)) << 4) | ((k & 1) << 3)); }
 
-template <bool REDUCE>
+template <int MODE>
 __global__ void __launch_bounds__(TTHREADS, 4)
 gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmTmaParams p) {
     constexpr int MI = 4, NJ = 4;      // 2 x 2 warps, each 32 x 32
@@ -59,7 +63,11 @@ gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
     const int64_t first_m = (tile / per_group) * GROUP_M;
     const int64_t group_m = p.tiles_m - first_m < GROUP_M ? p.tiles_m - first_m : GROUP_M;
     const int64_t m0 = (first_m + (tile % per_group) % group_m) * TBM, n0 = ((tile % per_group) / group_m) * TBN;
-    const int KT = (int)((p.K + TBK - 1) / TBK);
+    int KT = (int)((p.K + TBK - 1) / TBK), kt_begin = 0;
+    if (MODE == MODE_SPLITK) {      // this CTA owns k-tiles [kt_begin, kt_begin + KT) of its output tile
+        kt_begin = (int)blockIdx.y * p.kt_per_split;
+        KT = KT - kt_begin < p.kt_per_split ? KT - kt_begin : p.kt_per_split;
+    }
 
     if (tid == 0) {
         for (int s = 0; s < TSTAGES; ++s) mbar_init(&full[s], 1);
@@ -71,8 +79,8 @@ gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
         const int s = kt % TSTAGES;
         unsigned char* a = smem + (size_t)s * (TILE_A_BYTES + TILE_B_BYTES);
         mbar_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
-        tma_load_2d(a, &mapA, kt * TBK, (int)m0, &full[s]);
-        tma_load_2d(a + TILE_A_BYTES, &mapB, kt * TBK, (int)n0, &full[s]);
+        tma_load_2d(a, &mapA, (kt_begin + kt) * TBK, (int)m0, &full[s]);
+        tma_load_2d(a + TILE_A_BYTES, &mapB, (kt_begin + kt) * TBK, (int)n0, &full[s]);
     };
     if (tid == 0) {
         for (int s = 0; s < TSTAGES - 1 && s < KT; ++s) issue(s);
@@ -105,7 +113,23 @@ gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
         }
     }
 
-    if (REDUCE) {
+    if (MODE == MODE_SPLITK) {
+        double* ws = p.ws + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N;
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const int64_t row = m0 + warp_m * 32 + i * 8 + g;
+            if (row >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int64_t col = n0 + warp_n * 32 + j * 8 + 2 * t;
+                if (col < p.N) ws[row * p.N + col] = acc[i][j][0];
+                if (col + 1 < p.N) ws[row * p.N + col + 1] = acc[i][j][1];
+            }
+        }
+        return;
+    }
+
+    if (MODE == MODE_REDUCE) {
         // streaming consumer: the tile never leaves the SM.  Rows/columns beyond M/N were zero-filled by the TMA unit and add 0.
         __shared__ double red[2][TTHREADS / 32];
         double s1p[NJ], s2p[NJ];
@@ -208,6 +232,23 @@ bool make_map(CUtensorMap* map, const double* base, int64_t rows, int64_t K, int
 
 }  // namespace
 
+namespace {
+
+// second pass of a split-K product: fixed-order sum of the K slices (bit-reproducible), then the scatter epilogue
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const double* __restrict__ ws, int splits, const GemmTmaParams p) {
+    const int64_t total = p.M * p.N;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        double v = 0.0;
+        for (int s = 0; s < splits; ++s) v += ws[(size_t)s * (size_t)total + e];
+        const int64_t row = e / p.N, col = e % p.N;
+        double* dst = p.C + (p.offM ? p.offM[row] : row * p.ldc) + (p.offN ? p.offN[col] : col);
+        v *= p.alpha;
+        *dst = p.accumulate ? *dst + v : v;
+    }
+}
+
+}  // namespace
+
 // returns XR_ERR_UNSUPPORTED when the operands cannot be described by a tensor map (caller falls back to cp.async staging)
 int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                         const double* B, int64_t ldb, double* C, const int64_t* offM, int64_t ldc, const int64_t* offN,
@@ -215,11 +256,36 @@ int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alp
     if (K < 1 || M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return XR_ERR_UNSUPPORTED;
     CUtensorMap mapA, mapB;
     if (!make_map(&mapA, A, M, K, lda) || !make_map(&mapB, B, N, K, ldb)) return XR_ERR_UNSUPPORTED;
-    GemmTmaParams p{M, N, K, alpha, C, offM, ldc, offN, accumulate, (M + TBM - 1) / TBM, (N + TBN - 1) / TBN, nullptr};
+    GemmTmaParams p{M, N, K, alpha, C, offM, ldc, offN, accumulate, (M + TBM - 1) / TBM, (N + TBN - 1) / TBN, nullptr, 0, nullptr};
     const int64_t tiles = p.tiles_m * p.tiles_n;
     XR_REQUIRE(tiles < (1ll << 31), "xr_gemm_scatter: too many tiles (%lld)", (long long)tiles);
-    XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
-    gemm_tma_scatter_kernel<false><<<(unsigned)tiles, TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
+    // Few output tiles but a long contraction (the rho x V precontractions of hermitian-XRCC: [P, n^4] x [n^4, 1..n]): split K
+    // over blockIdx.y so the whole GPU streams the operand, partial tiles to scratch, fixed-order second pass.
+    const int64_t KT = (K + TBK - 1) / TBK;
+    int64_t splits = 1;
+    if (tiles < 2 * (int64_t)ctx->sm_count && KT >= 16) {
+        splits = (4 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
+        if (splits > KT / 8) splits = KT / 8;
+        if (splits > 512) splits = 512;
+    }
+    if (splits >= 2) {
+        p.kt_per_split = (int)((KT + splits - 1) / splits);
+        splits = (KT + p.kt_per_split - 1) / p.kt_per_split;
+        int rc = xr_ensure_scratch(ctx, (size_t)splits * (size_t)M * (size_t)N * sizeof(double));
+        if (rc != XR_OK) return rc;
+        p.ws = static_cast<double*>(ctx->scratch);
+        XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel<MODE_SPLITK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+        gemm_tma_scatter_kernel<MODE_SPLITK><<<dim3((unsigned)tiles, (unsigned)splits), TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
+        XR_CUDA(cudaGetLastError());
+        int64_t blocks = (M * N + 255) / 256;
+        if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+        splitk_finish_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p.ws, (int)splits, p);
+        XR_CUDA(cudaGetLastError());
+        ctx->launches += 2;
+        return XR_OK;
+    }
+    XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel<MODE_SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+    gemm_tma_scatter_kernel<MODE_SCATTER><<<(unsigned)tiles, TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
     XR_CUDA(cudaGetLastError());
     ctx->launches++;
     return XR_OK;
@@ -283,15 +349,15 @@ extern "C" int xr_gemm_reduce(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, doub
     XR_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "xr_gemm_reduce: dimension too large");
     CUtensorMap mapA, mapB;
     XR_REQUIRE(make_map(&mapA, A, M, K, lda) && make_map(&mapB, B, N, K, ldb), "xr_gemm_reduce: cuTensorMapEncodeTiled failed");
-    GemmTmaParams p{M, N, K, alpha, nullptr, nullptr, 0, nullptr, 0, (M + TBM - 1) / TBM, (N + TBN - 1) / TBN, nullptr};
+    GemmTmaParams p{M, N, K, alpha, nullptr, nullptr, 0, nullptr, 0, (M + TBM - 1) / TBM, (N + TBN - 1) / TBN, nullptr, 0, nullptr};
     const int64_t tiles = p.tiles_m * p.tiles_n;
     XR_REQUIRE(tiles < (1ll << 31), "xr_gemm_reduce: too many tiles (%lld)", (long long)tiles);
     int rc = xr_ensure_scratch(ctx, (size_t)(tiles + RED_BLOCKS) * 2 * sizeof(double) + 256);
     if (rc != XR_OK) return rc;
     p.partials = static_cast<double*>(ctx->scratch);
     double* block_out = p.partials + 2 * tiles;
-    XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
-    gemm_tma_scatter_kernel<true><<<(unsigned)tiles, TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
+    XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel<MODE_REDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+    gemm_tma_scatter_kernel<MODE_REDUCE><<<(unsigned)tiles, TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
     XR_CUDA(cudaGetLastError());
     reduce_partials_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(p.partials, tiles, block_out);
     XR_CUDA(cudaGetLastError());

@@ -13,8 +13,10 @@ get_xr_H implements; any other order raises NotImplementedError as the reference
 
 All matrices are assembled in HBM directly in the final ordering, so the reference's O(dim^4)
 Python reorder loop disappears; ``S2inv @ S2H2`` runs through xr_gemm_scatter.  The inverse of the
-(dim <= ~1e3) overlap matrix itself is taken with NumPy plus one Newton-Schulz refinement step in
-extended precision, on the host, as the reference does with ``qode.math.precise_numpy_inverse`` (:165).
+(dim <= ~1e3) overlap matrix is NumPy's (LAPACK, on the host, where the reference's
+``qode.math.precise_numpy_inverse`` (:165) takes it too) polished by one Newton step X + X (I - S2 X)
+carried in double-double arithmetic on the GPU (xr_gemm_dd) -- the host version of that polish in
+numpy.longdouble was 2/3 of the whole order-1 call at Be2/6-31G sizes.
 """
 import numpy
 
@@ -26,12 +28,15 @@ from .tensor import Contractor, DeviceStore, DeviceTensor, default_device
 from .util import struct, timer
 
 
-def precise_numpy_inverse(M):
-    M = numpy.asarray(M, dtype=numpy.float64)
-    X = numpy.linalg.inv(M)
-    ML, XL = M.astype(numpy.longdouble), X.astype(numpy.longdouble)
-    XL = XL + XL @ (numpy.eye(M.shape[0], dtype=numpy.longdouble) - ML @ XL)
-    return numpy.asarray(XL, dtype=numpy.float64)
+def precise_inverse(M, dev):
+    """device tensor of M^-1: LAPACK inverse, then one Newton step with double-double products and sums on the GPU"""
+    M = numpy.ascontiguousarray(M, dtype=numpy.float64)
+    n = M.shape[0]
+    dM, dX = dev.upload(M), dev.upload(numpy.linalg.inv(M))
+    R, out = dev.empty((n, n)), dev.empty((n, n))
+    dev.ctx.gemm_dd(n, n, n, dM, n, dX, n, None, 0, -1.0, R, n)       # R = I - M X
+    dev.ctx.gemm_dd(n, n, n, dX, n, R, n, dX, n, +1.0, out, n)        # X + X R
+    return DeviceTensor(out, dev)
 
 
 def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False, device=None):
@@ -79,26 +84,26 @@ def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False
         SV_diff = make(struct(S=S, V=bior_ints.V_diff), SV_diagrams)
         H1 = monomers(ST_symm, SU_symm, SV_symm)
         S2 = XR_term.dimer_matrix(S_blocks, {0: D.S0[0], 2: D.S2[1]}, (0, 1), all_dimer_charges, matrix_timer, ordering="final")
-        S2inv = precise_numpy_inverse(S2)
+        S2inv = precise_inverse(S2, dev)
         S2H2 = dimer_sum([(ST_symm, {1: D.ST1[0], 2: D.ST2[0]}), (SU_symm, {1: D.SU1[0], 2: D.SU2[0]}),
                           (ST_bior, {2: D.ST2[1]}), (SU_bior, {2: D.SU2[1]}),
                           (SV_diff, {1: D.SV1[0], 2: D.SV2[0]}), (SV_bior, {2: D.SV2[1]})])
         # H2 = S2inv @ S2H2 - (monomer terms in the dimer basis): the subtraction is accumulated first, with
         # scale -1, and the matrix product is then added on top by the GEMM epilogue
         out = dimer_sum([(ST_symm, {1: D.ST1[0]}), (SU_symm, {1: D.SU1[0]}), (SV_symm, {1: D.SV1[0]})], scale=-1.0)
-        contractor.contract(store.get(S2inv), ["a", "k"], S2H2, ["k", "b"], ["a", "b"], out=out, accumulate=True)
+        contractor.contract(S2inv, ["a", "k"], S2H2, ["k", "b"], ["a", "b"], out=out, accumulate=True)
         H2 = out.host()
     elif xr_order == 2:                                 # get_xr_result.py:214-296
         SV_diff = make(struct(S=S, V=bior_ints.V_diff), SV_diagrams)
         H1 = monomers(ST_symm, SU_symm, SV_symm)
         S2 = XR_term.dimer_matrix(S_blocks, {0: D.S0[0], 2: D.S2[1] + D.S2[2]}, (0, 1), all_dimer_charges, matrix_timer,
                                   ordering="final")
-        S2inv = precise_numpy_inverse(S2)
+        S2inv = precise_inverse(S2, dev)
         S2H2 = dimer_sum([(ST_symm, {1: D.ST1[0], 2: D.ST2[0] + D.ST2[1]}), (SU_symm, {1: D.SU1[0], 2: D.SU2[0] + D.SU2[1]}),
                           (ST_bior, {2: D.ST2[2]}), (SU_bior, {2: D.SU2[2]}),
                           (SV_symm, {1: D.SV1[0], 2: D.SV2[0]}), (SV_diff, {2: D.SV2[1]}), (SV_bior, {2: D.SV2[2]})])
         out = dimer_sum([(ST_symm, {1: D.ST1[0]}), (SU_symm, {1: D.SU1[0]}), (SV_symm, {1: D.SV1[0]})], scale=-1.0)
-        contractor.contract(store.get(S2inv), ["a", "k"], S2H2, ["k", "b"], ["a", "b"], out=out, accumulate=True)
+        contractor.contract(S2inv, ["a", "k"], S2H2, ["k", "b"], ["a", "b"], out=out, accumulate=True)
         H2 = out.host()
     else:
         raise NotImplementedError("xr order %r is not implemented" % (xr_order,))

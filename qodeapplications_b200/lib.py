@@ -42,6 +42,7 @@ _PROTOTYPES = {
     "xr_gemm_reduce": (_int, [_ptr, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr]),
     "xr_copy2d_scaled": (_int, [_ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _dbl]),
     "xr_scatter_const": (_int, [_ptr, _ptr, _ptr, _i64, _dbl, _int]),
+    "xr_gemm_dd": (_int, [_ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _dbl, _ptr, _i64]),
     "xr_embed_add": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _int, _ptr, _int, _dbl]),
     "xr_permute_copy": (_int, [_ptr, _ptr, _ptr, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _dbl]),
     "xr_trimer_stream": (_int, [_ptr, _int, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _int,
@@ -165,6 +166,9 @@ class Context(object):
         arr = _i64 * nd
         check(self.lib.xr_permute_copy(self.handle, _p(dst), _p(src), nd, arr(*[int(x) for x in shape]),
                                        arr(*[int(x) for x in src_strides]), float(alpha)), "xr_permute_copy")
+
+    def gemm_dd(self, M, N, K, A, lda, B, ldb, C0, ldc0, sign, out, ldo):
+        check(self.lib.xr_gemm_dd(self.handle, M, N, K, _p(A), lda, _p(B), ldb, _p(C0), ldc0, float(sign), _p(out), ldo), "xr_gemm_dd")
 
     def embed_add(self, H, src, ld, R, Cn, S, offR, offC, offS=None, dims_sub=(), min_transitions=0, alpha=1.0):
         dims = (ctypes.c_int64 * max(1, len(dims_sub)))(*[int(d) for d in dims_sub])

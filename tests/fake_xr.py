@@ -70,6 +70,19 @@ class FakeContext(object):
         D = numpy.lib.stride_tricks.as_strided(d, (rows, cols), (8 * dst_ld, 8))
         D[...] = alpha * S
 
+    def gemm_dd(self, M, N, K, A, lda, B, ldb, C0, ldc0, sign, out, ldo):
+        self.launches += 1
+        if M <= 0 or N <= 0:
+            return
+        a = numpy.lib.stride_tricks.as_strided(_view(A, (M - 1) * lda + K), (M, K), (8 * lda, 8)).astype(numpy.longdouble)
+        b = numpy.lib.stride_tricks.as_strided(_view(B, (K - 1) * ldb + N), (K, N), (8 * ldb, 8)).astype(numpy.longdouble)
+        if C0 is None:
+            c = numpy.eye(M, N, dtype=numpy.longdouble)
+        else:
+            c = numpy.lib.stride_tricks.as_strided(_view(C0, (M - 1) * ldc0 + N), (M, N), (8 * ldc0, 8)).astype(numpy.longdouble)
+        o = numpy.lib.stride_tricks.as_strided(_view(out, (M - 1) * ldo + N), (M, N), (8 * ldo, 8))
+        o[...] = (c + sign * (a @ b)).astype(numpy.float64)
+
     def embed_add(self, H, src, ld, R, Cn, S, offR, offC, offS=None, dims_sub=(), min_transitions=0, alpha=1.0):
         self.launches += 1
         if R <= 0 or Cn <= 0 or S <= 0:

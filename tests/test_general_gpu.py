@@ -40,7 +40,8 @@ def _engine(system, dev):
 # ------------------------------------------------------------------------------- kernels
 
 @pytest.mark.parametrize("M,N,K", [(1, 1, 1), (7, 5, 3), (64, 64, 16), (130, 70, 37), (257, 300, 324), (1000, 33, 18),
-                                   (129, 1, 325), (300, 520, 36)])
+                                   (129, 1, 325), (300, 520, 36),
+                                   (130, 3, 5000), (64, 1, 104976), (300, 18, 5832), (1584, 1, 20000)])     # split-K path
 @pytest.mark.parametrize("aligned", [True, False])
 def test_gemm_scatter_plain(dev, M, N, K, aligned):
     rng = numpy.random.default_rng(M * 1000 + N * 10 + K)
@@ -242,6 +243,33 @@ def test_cfg3_trimer_moments_and_sampled_elements(dev):
         J = numpy.unravel_index(j, dims)
         ref = eo.trimer((0, 1, 2), tuple(st[k][I[k]] for k in range(3)), tuple(st[k][J[k]] for k in range(3)))
         assert abs(val - (ref or 0.0)) <= TOL * scale
+
+
+def test_gemm_dd_newton_polish_of_an_inverse(dev):
+    """xr_gemm_dd: residual I - M X and the update X + X R against numpy.longdouble (what the host polish used)"""
+    rng = numpy.random.default_rng(12)
+    n = 203
+    M = numpy.eye(n) + 0.05 * rng.standard_normal((n, n))
+    X = numpy.linalg.inv(M)
+    ML, XL = M.astype(numpy.longdouble), X.astype(numpy.longdouble)
+    RL = numpy.eye(n, dtype=numpy.longdouble) - ML @ XL
+    dM, dX = dev.upload(M), dev.upload(X)
+    R, out = dev.empty((n, n)), dev.empty((n, n))
+    dev.ctx.gemm_dd(n, n, n, dM, n, dX, n, None, 0, -1.0, R, n)
+    got = dev.download(R)
+    assert numpy.abs(got - RL.astype(numpy.float64)).max() <= 1e-19 * n * numpy.abs(X).max()     # plain FP64 would be ~1e-16
+    assert numpy.abs(got).max() < 1e-13
+    dev.ctx.gemm_dd(n, n, n, dX, n, R, n, dX, n, +1.0, out, n)
+    polished = (XL + XL @ RL).astype(numpy.float64)
+    assert numpy.abs(dev.download(out) - polished).max() <= 2e-16 * numpy.abs(X).max()
+    # rectangular, with leading dimensions and a C0 operand
+    A, B, C0 = rng.standard_normal((37, 60)), rng.standard_normal((50, 29)), rng.standard_normal((37, 31))
+    o = dev.zeros((37, 33))
+    dev.ctx.gemm_dd(37, 29, 50, dev.upload(A), 60, dev.upload(B), 29, dev.upload(C0), 31, -1.0, o, 33)
+    ref = (C0[:, :29].astype(numpy.longdouble) - A[:, :50].astype(numpy.longdouble) @ B.astype(numpy.longdouble)).astype(numpy.float64)
+    res = dev.download(o)
+    assert numpy.abs(res[:, :29] - ref).max() <= 1e-15 * numpy.abs(ref).max()
+    assert numpy.all(res[:, 29:] == 0)
 
 
 # ------------------------------------------------------------------------------- streamed dimers (cfg5 path)
