@@ -69,6 +69,9 @@ gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
         KT = KT - kt_begin < p.kt_per_split ? KT - kt_begin : p.kt_per_split;
     }
 
+    const int64_t k_last = (int64_t)(kt_begin + KT - 1) * TBK;            // first k of this CTA's last k-tile
+    const int last_ksteps = p.K - k_last >= TBK ? TBK / 4 : (int)((p.K - k_last + 3) / 4);
+
     if (tid == 0) {
         for (int s = 0; s < TSTAGES; ++s) mbar_init(&full[s], 1);
         fence_barrier_init();
@@ -99,8 +102,12 @@ gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
         if (tid == 0 && kt + TSTAGES - 1 < KT) issue(kt + TSTAGES - 1);
         const unsigned char* as = smem + (size_t)s * (TILE_A_BYTES + TILE_B_BYTES);
         const unsigned char* bs = as + TILE_A_BYTES;
+        // the last k-tile may hold fewer than 16 real k (K = 2n = 36 -> 32 + 4): skip the DMMA steps that would only
+        // multiply the zeros the TMA unit filled in (a quarter of all tensor work for the d=+-1 dimer classes)
+        const int ksteps = kt == KT - 1 ? last_ksteps : TBK / 4;
 #pragma unroll
         for (int ks = 0; ks < TBK / 4; ++ks) {
+            if (ks >= ksteps) break;
             double a[MI], b[NJ];
 #pragma unroll
             for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const double*>(as + swz(warp_m * 32 + i * 8 + g, ks * 4 + t));

@@ -95,15 +95,21 @@ def _offset_table(extents, strides):
     return table
 
 
+_TABLES = {}        # id(device) -> {(extents, strides): device int64 table}; pure functions of the shapes, kept across calls
+
+
 class Contractor(object):
     def __init__(self, dev=None):
         self.dev = dev or default_device()
-        self._tables = {}
+        self._tables = _TABLES.setdefault(id(self.dev), {"device": self.dev})
         self.flops = 0.0
 
     def _table(self, extents, strides):
         key = (tuple(extents), tuple(strides))
         if key not in self._tables:
+            if len(self._tables) > 4096:        # bound the cache (an optimiser loop reuses a few hundred shapes)
+                for stale in [k for k in self._tables if k != "device"]:
+                    del self._tables[stale]
             self._tables[key] = self.dev.upload(_offset_table(extents, strides), dtype=numpy.int64)
         return self._tables[key]
 
