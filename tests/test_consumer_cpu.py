@@ -61,3 +61,32 @@ def test_unequal_fragment_dimensions_host_logic():
         big.add((1, 0), H2[0][1])
     with pytest.raises(ValueError):
         big.add((0, 1), H2[0][2])
+
+
+@pytest.mark.parametrize("name", ["toy3", "toy5"])
+def test_matrix_free_operator_host_logic(name):
+    """y = Hmat.v from the class factors (never forming H2/H3) equals the reference's braket_loops matrix"""
+    from qodeapplications_b200 import synth
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    from qodeapplications_b200.general.operator import xr_operator
+    system = synth.make_system(name)
+    eng = build_matrix_elements(system["fragments"], system["symm"], system["nuc"], device=FakeDevice())
+    op = xr_operator(eng)
+    if name == "toy3":
+        ref = numpy.load(os.path.join(GOLDEN, "supersystem_hmat.npz"))["toy3"]
+    else:       # five charge states: the reference's blocks from the fixture, expanded by the oracle restatement
+        g = numpy.load(os.path.join(GOLDEN, "general_toy5.npz"))
+        H3 = numpy.zeros(tuple(g["H3_012_shape"]))
+        H3[g["H3_012_rows"], g["H3_012_cols"]] = g["H3_012_vals"]
+        H = ([g["H1_%d" % m] for m in range(3)], [[g["H2_%d%d" % (M, N)] if M < N else None for N in range(3)] for M in range(3)],
+             [[[H3 if (M, N, O) == (0, 1, 2) else None for O in range(3)] for N in range(3)] for M in range(3)])
+        ref = go.supersystem_matrix(op.dims, H)
+    got = op.dense().numpy()
+    assert numpy.abs(got - ref).max() <= 1e-10 * numpy.abs(ref).max()
+    # several vectors at once (trailing axis) and accumulation into a given output
+    import torch
+    rng = numpy.random.default_rng(3)
+    v = rng.standard_normal(tuple(op.dims) + (2,))
+    y = op.apply(torch.from_numpy(v)).numpy()
+    D = ref.shape[0]
+    assert numpy.abs(y.reshape(D, 2) - ref @ v.reshape(D, 2)).max() <= 1e-10 * numpy.abs(ref).max() * numpy.abs(v).max() * D ** 0.5
