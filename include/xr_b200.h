@@ -49,6 +49,24 @@ typedef double  Double;
 /* replaces general-XRCC/H_contractions.c:208 */ PyFloat trimer_2pls1min1min(PyInt n_orb1, PyInt n_orb2, PyInt n_orb3, Double* Raa1, Double* Rc2, Double* Rc3, Double* V);
 /* replaces general-XRCC/H_contractions.c:232 */ PyFloat trimer_Ex1min1pls(PyInt n_orb1, PyInt n_orb2, PyInt n_orb3, Double* Rca1, Double* Rc2, Double* Ra3, Double* V);
 
+/* (A') The eight entry points of the reference's general-XRCC/density_tensors.c (the step before the H build, bound by
+ * build_density_tensors.py:23 and called at :85-153), identical C signature: HOST pointers, z_list / configs /
+ * combinatorics are arrays of per-charge-sector pointers, `storage` [n_states[bra]*n_states[ket]*(2 n_orbs)^k] is added
+ * into.  `combinatorics` and `n_threads` are accepted and unused.  Errors (2*n_orbs > 64, CUDA failures) leave storage
+ * untouched and set xr_last_error(). */
+typedef int64_t BigInt;
+#define XR_DENSITY_ARGS Double storage[], PyInt bra_chg_idx, PyInt ket_chg_idx, BigInt n_elec[], BigInt n_states[], \
+                        Double* z_list[], BigInt n_configs[], BigInt* configs[], PyInt n_orbs, PyInt n_core,         \
+                        BigInt* combinatorics[], PyInt n_threads
+/* replaces general-XRCC/density_tensors.c:162 */ void a_tensor(XR_DENSITY_ARGS);
+/* replaces general-XRCC/density_tensors.c:199 */ void c_tensor(XR_DENSITY_ARGS);
+/* replaces general-XRCC/density_tensors.c:236 */ void ca_tensor(XR_DENSITY_ARGS);
+/* replaces general-XRCC/density_tensors.c:283 */ void aa_tensor(XR_DENSITY_ARGS);
+/* replaces general-XRCC/density_tensors.c:330 */ void cc_tensor(XR_DENSITY_ARGS);
+/* replaces general-XRCC/density_tensors.c:377 */ void caa_tensor(XR_DENSITY_ARGS);
+/* replaces general-XRCC/density_tensors.c:437 */ void cca_tensor(XR_DENSITY_ARGS);
+/* replaces general-XRCC/density_tensors.c:493 */ void ccaa_tensor(XR_DENSITY_ARGS);
+
 /* ------------------------------------------------------------------ (B) block-level ABI */
 typedef struct xr_ctx xr_ctx;
 
@@ -143,6 +161,20 @@ int xr_embed_add(xr_ctx* ctx, double* H, const double* src, int64_t ld, int64_t 
  * qode.math.precise_numpy_inverse (an extended-precision refinement of numpy's inverse). out must not alias A or B. */
 int xr_gemm_dd(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb,
                const double* C0, int64_t ldc0, double sign, double* out, int64_t ldo);
+
+/* Transition-density tensor of one operator string between two charge sectors (general-XRCC/density_tensors.c:142-556):
+ *
+ *     rho[(I*n_ket_states + J)*dim^k + index] += parity * z_bra[I*n_configs_bra + P] * z_ket[J*n_configs_ket + Q]
+ *
+ * for every ket configuration Q and orbital indices (i_0..i_{k-1}) (index row-major, dim = 2*n_orbs <= 64) for which
+ * |P> = parity * op_0(i_0) ... op_{k-1}(i_{k-1}) |Q> keeps the n_core core orbitals of both spins occupied; ops is a
+ * string of 'c'/'a' (k <= 4: "a","c","aa","cc","ca","caa","cca","ccaa").  ket_masks[Q] (device) is the occupation bit
+ * mask of ket configuration Q; the bra coefficients must span ALL C(2(n_orbs-n_core), n_elec_bra-2 n_core) valence
+ * configurations in find_config_index order (density_tensors.c:29-64).  Gather formulation, no atomics: the summation
+ * order over Q -- and therefore every bit of the result -- is the reference's.  All pointers are device pointers. */
+int xr_density_tensor(xr_ctx* ctx, const char* ops, double* rho, int64_t n_bra_states, int64_t n_ket_states,
+                      const double* z_bra, int64_t n_configs_bra, const double* z_ket, int64_t n_configs_ket,
+                      const uint64_t* ket_masks, int64_t n_elec_bra, int64_t n_elec_ket, int64_t n_orbs, int64_t n_core);
 
 /* Streamed three-factor contraction, the trimer classes of general-XRCC/build_H.py:103-188
  * after the rho x V precontraction:

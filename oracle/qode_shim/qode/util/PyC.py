@@ -40,6 +40,11 @@ class _function(object):
                 else:
                     arg = numpy.ascontiguousarray(arg, dtype=numpy.int64)
                     converted.append(arg.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+            elif isinstance(arg, (list, tuple)):      # list of per-sector arrays -> Double*[] / BigInt*[] (build_density_tensors.py:88)
+                arrays = [numpy.ascontiguousarray(a) for a in arg]
+                ctype = ctypes.c_double if arrays[0].dtype == numpy.float64 else ctypes.c_int64
+                self._keep = arrays
+                converted.append((ctypes.POINTER(ctype) * len(arrays))(*[a.ctypes.data_as(ctypes.POINTER(ctype)) for a in arrays]))
             elif isinstance(arg, (int, numpy.integer)):
                 converted.append(ctypes.c_int64(int(arg)))
             elif isinstance(arg, (float, numpy.floating)):

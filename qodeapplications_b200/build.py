@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libxr_b200.so")
-SOURCES = ["xr_api.cu", "xr_gemm.cu", "xr_gemm_tma.cu", "xr_trimer.cu", "xr_embed.cu", "xr_linalg.cu", "xr_scalar.cu"]
+SOURCES = ["xr_api.cu", "xr_gemm.cu", "xr_gemm_tma.cu", "xr_trimer.cu", "xr_embed.cu", "xr_linalg.cu", "xr_density.cu", "xr_scalar.cu"]
 HEADERS = [os.path.join(CSRC, "xr_common.cuh"), os.path.join(HERE, "..", "include", "xr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]

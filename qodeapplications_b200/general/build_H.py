@@ -311,7 +311,11 @@ class build_matrix_elements(object):
             N = info.n_states[ci]
             ca = self._rho(m, "ca", (ci, cj))
             ctx.gemm_scatter(N * N, 1, n * n, 1.0, ca, n * n, h, n * n, H, off.data_ptr() + 8 * row0, 0, None, False)
-            scal = self.dev.upload(numpy.asarray(rho[m]["ccaa"][(ci, cj)], dtype=numpy.float64).reshape(N * N, 1))
+            scal = rho[m]["ccaa"][(ci, cj)]
+            if isinstance(scal, torch.Tensor):      # device-resident (general.build_density_tensors(device_result=True))
+                scal = scal.reshape(N * N, 1)
+            else:
+                scal = self.dev.upload(numpy.asarray(scal, dtype=numpy.float64).reshape(N * N, 1))
             ctx.gemm_scatter(N * N, 1, 1, 1.0, scal, 1, one, 2, H, off.data_ptr() + 8 * row0, 0, None, True)
         diag = self._index(numpy.arange(info.dim, dtype=numpy.int64) * (info.dim + 1))
         ctx.scatter_const(H, diag, info.dim, float(nuc[m, m]), True)

@@ -23,6 +23,9 @@ LEGACY_SYMBOLS = {      # name -> (number of PyInt args, number of Double* args)
     "trimer_2min1pls1pls": (3, 4), "trimer_2pls1min1min": (3, 4), "trimer_Ex1min1pls": (3, 4),
 }
 
+# density_tensors.c ABI: (storage, bra, ket, n_elec[], n_states[], z_list[], n_configs[], configs[], n_orbs, n_core, combinatorics[], n_threads)
+LEGACY_DENSITY_SYMBOLS = ("a_tensor", "c_tensor", "ca_tensor", "aa_tensor", "cc_tensor", "caa_tensor", "cca_tensor", "ccaa_tensor")
+
 _PROTOTYPES = {
     "xr_last_error": (ctypes.c_char_p, []),
     "xr_version": (ctypes.c_char_p, []),
@@ -42,6 +45,7 @@ _PROTOTYPES = {
     "xr_gemm_reduce": (_int, [_ptr, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr]),
     "xr_copy2d_scaled": (_int, [_ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _dbl]),
     "xr_scatter_const": (_int, [_ptr, _ptr, _ptr, _i64, _dbl, _int]),
+    "xr_density_tensor": (_int, [_ptr, ctypes.c_char_p, _ptr, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64]),
     "xr_gemm_dd": (_int, [_ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _dbl, _ptr, _i64]),
     "xr_embed_add": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _int, _ptr, _int, _dbl]),
     "xr_permute_copy": (_int, [_ptr, _ptr, _ptr, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _dbl]),
@@ -81,6 +85,10 @@ def load():
         fn = getattr(lib, name)
         fn.restype = _dbl
         fn.argtypes = [_i64] * n_int + [_ptr] * n_ptr
+    for name in LEGACY_DENSITY_SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = None
+        fn.argtypes = [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _ptr, _i64]
     _lib = lib
     return lib
 
@@ -166,6 +174,12 @@ class Context(object):
         arr = _i64 * nd
         check(self.lib.xr_permute_copy(self.handle, _p(dst), _p(src), nd, arr(*[int(x) for x in shape]),
                                        arr(*[int(x) for x in src_strides]), float(alpha)), "xr_permute_copy")
+
+    def density_tensor(self, ops, rho, n_bra_states, n_ket_states, z_bra, n_configs_bra, z_ket, n_configs_ket, ket_masks,
+                       n_elec_bra, n_elec_ket, n_orbs, n_core):
+        check(self.lib.xr_density_tensor(self.handle, ops.encode(), _p(rho), n_bra_states, n_ket_states, _p(z_bra), n_configs_bra,
+                                         _p(z_ket), n_configs_ket, _p(ket_masks), n_elec_bra, n_elec_ket, n_orbs, n_core),
+              "xr_density_tensor")
 
     def gemm_dd(self, M, N, K, A, lda, B, ldb, C0, ldc0, sign, out, ldo):
         check(self.lib.xr_gemm_dd(self.handle, M, N, K, _p(A), lda, _p(B), ldb, _p(C0), ldc0, float(sign), _p(out), ldo), "xr_gemm_dd")

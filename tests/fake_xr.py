@@ -70,6 +70,27 @@ class FakeContext(object):
         D = numpy.lib.stride_tricks.as_strided(d, (rows, cols), (8 * dst_ld, 8))
         D[...] = alpha * S
 
+    def density_tensor(self, ops, rho, n_bra_states, n_ket_states, z_bra, n_configs_bra, z_ket, n_configs_ket, ket_masks,
+                       n_elec_bra, n_elec_ket, n_orbs, n_core):
+        """semantics of xr_density_tensor through the (test-only) Python restatement in oracle/density_oracle.py"""
+        import os, sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from oracle import density_oracle as do
+        self.launches += 1
+        assert 2 * n_orbs <= 64 and 1 <= len(ops) <= 4
+        dim = 2 * n_orbs
+
+        class states(object):
+            pass
+        bra, ket = states(), states()
+        bra.coeffs = _view(z_bra, n_bra_states * n_configs_bra).reshape(n_bra_states, n_configs_bra)
+        bra.configs = numpy.zeros((n_configs_bra, n_elec_bra), dtype=numpy.int64)
+        ket.coeffs = _view(z_ket, n_ket_states * n_configs_ket).reshape(n_ket_states, n_configs_ket)
+        masks = _view(ket_masks, n_configs_ket, numpy.int64)
+        ket.configs = numpy.array([[i for i in range(dim) if (int(m) >> i) & 1] for m in masks], dtype=numpy.int64).reshape(n_configs_ket, n_elec_ket)
+        out = do.tensor(ops, {"bra": bra, "ket": ket}, "bra", "ket", n_orbs, n_core)
+        _view(rho, out.size)[...] += out.reshape(-1)
+
     def gemm_dd(self, M, N, K, A, lda, B, ldb, C0, ldc0, sign, out, ldo):
         self.launches += 1
         if M <= 0 or N <= 0:

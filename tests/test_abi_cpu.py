@@ -24,7 +24,7 @@ def test_version_string():
 
 def test_prototypes_cover_header():
     declared = set(xr.declared_symbols())
-    bound = set(xr._PROTOTYPES) | set(xr.LEGACY_SYMBOLS)
+    bound = set(xr._PROTOTYPES) | set(xr.LEGACY_SYMBOLS) | set(xr.LEGACY_DENSITY_SYMBOLS)
     assert declared == bound, declared ^ bound
 
 
