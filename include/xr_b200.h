@@ -164,17 +164,29 @@ int xr_gemm_dd(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, in
 
 /* Transition-density tensor of one operator string between two charge sectors (general-XRCC/density_tensors.c:142-556):
  *
- *     rho[(I*n_ket_states + J)*dim^k + index] += parity * z_bra[I*n_configs_bra + P] * z_ket[J*n_configs_ket + Q]
+ *     rho[(I*n_ket_states + J)*dim^k + index] (+)= sum_Q parity * z_bra[I*n_configs_bra + P] * z_ket[J*n_configs_ket + Q]
  *
  * for every ket configuration Q and orbital indices (i_0..i_{k-1}) (index row-major, dim = 2*n_orbs <= 64) for which
  * |P> = parity * op_0(i_0) ... op_{k-1}(i_{k-1}) |Q> keeps the n_core core orbitals of both spins occupied; ops is a
  * string of 'c'/'a' (k <= 4: "a","c","aa","cc","ca","caa","cca","ccaa").  ket_masks[Q] (device) is the occupation bit
  * mask of ket configuration Q; the bra coefficients must span ALL C(2(n_orbs-n_core), n_elec_bra-2 n_core) valence
- * configurations in find_config_index order (density_tensors.c:29-64).  Gather formulation, no atomics: the summation
+ * configurations in find_config_index order (density_tensors.c:29-64).  accumulate = 0 overwrites rho (no need to clear
+ * it), 1 adds to what is there (the reference's `+=`).  Gather formulation, no atomics: the summation
  * order over Q -- and therefore every bit of the result -- is the reference's.  All pointers are device pointers. */
 int xr_density_tensor(xr_ctx* ctx, const char* ops, double* rho, int64_t n_bra_states, int64_t n_ket_states,
                       const double* z_bra, int64_t n_configs_bra, const double* z_ket, int64_t n_configs_ket,
-                      const uint64_t* ket_masks, int64_t n_elec_bra, int64_t n_elec_ket, int64_t n_orbs, int64_t n_core);
+                      const uint64_t* ket_masks, int64_t n_elec_bra, int64_t n_elec_ket, int64_t n_orbs, int64_t n_core,
+                      int accumulate);
+
+/* The same tensor contracted on the fly with weights[dim^k] (device), never stored:
+ *     out[I*n_ket_states + J] (+)= sum_index weights[index] * rho[I,J,index]
+ * general-XRCC/build_density_tensors.py:125-133 forms every ccaa tensor only to reduce it at once with the two-electron
+ * integrals (monomer_2e: weights[p,q,r,s] = V[p,q,s,r]); fused, the largest tensor of the density build never touches HBM.
+ * Fixed-order reductions (bit-reproducible); the summation order differs from monomer_2e's, the values agree to rounding. */
+int xr_density_contracted(xr_ctx* ctx, const char* ops, double* out, const double* weights, int64_t n_bra_states,
+                          int64_t n_ket_states, const double* z_bra, int64_t n_configs_bra, const double* z_ket,
+                          int64_t n_configs_ket, const uint64_t* ket_masks, int64_t n_elec_bra, int64_t n_elec_ket, int64_t n_orbs,
+                          int64_t n_core, int accumulate);
 
 /* Streamed three-factor contraction, the trimer classes of general-XRCC/build_H.py:103-188
  * after the rho x V precontraction:

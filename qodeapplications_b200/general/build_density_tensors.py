@@ -73,20 +73,21 @@ def build_density_tensors(z_lists, n_orbs, Vints, n_core, n_threads=1, device=No
             Nb, Nk = coeffs[bra].shape[0], coeffs[ket].shape[0]
             for op in _OPS_BY_DCHG.get(bra - ket, ()):
                 T = n ** len(op)
-                rho = dev.zeros((Nb * Nk, T))
-                ctx.density_tensor(op, rho, Nb, Nk, coeffs[bra], coeffs[bra].shape[1], coeffs[ket], coeffs[ket].shape[1],
-                                   masks[ket], n_elec[bra], n_elec[ket], n_orbs, n_core)
-                if op == "ccaa":        # build_density_tensors.py:125-133 keeps only sum V[p,q,r,s] ccaa[p,q,s,r]
+                args = (Nb, Nk, coeffs[bra], coeffs[bra].shape[1], coeffs[ket], coeffs[ket].shape[1], masks[ket], n_elec[bra],
+                        n_elec[ket], n_orbs, n_core)
+                if op == "ccaa":        # build_density_tensors.py:125-133 keeps only sum V[p,q,r,s] ccaa[p,q,s,r]: fused, never stored
                     if Vt is None:
                         V = numpy.asarray(Vints, dtype=numpy.float64).reshape(n, n, n, n)
-                        Vt = dev.upload(numpy.stack([V.transpose(0, 1, 3, 2).reshape(-1), numpy.zeros(T)]))
-                    scalars = dev.empty((Nb * Nk, 1))
-                    ctx.gemm_scatter(Nb * Nk, 1, T, 1.0, rho, T, Vt, T, scalars, None, 1, None, False)
-                    block, count = scalars.reshape(Nb, Nk), Nb * Nk
+                        Vt = dev.upload(V.transpose(0, 1, 3, 2).reshape(-1))
+                    scalars = dev.empty((Nb, Nk))
+                    ctx.density_contracted(op, scalars, Vt, *args)
+                    block, count = scalars, Nb * Nk
                     if not device_result:
                         host = dev.download(block)
                         block = [[float(host[i, j]) for j in range(Nk)] for i in range(Nb)]
                 else:
+                    rho = dev.empty((Nb * Nk, T))
+                    ctx.density_tensor(op, rho, *args)
                     block, count = rho.reshape((Nb, Nk) + (n,) * len(op)), Nb * Nk * T
                     if not device_result:
                         host = dev.download(block)

@@ -45,7 +45,8 @@ _PROTOTYPES = {
     "xr_gemm_reduce": (_int, [_ptr, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr]),
     "xr_copy2d_scaled": (_int, [_ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _dbl]),
     "xr_scatter_const": (_int, [_ptr, _ptr, _ptr, _i64, _dbl, _int]),
-    "xr_density_tensor": (_int, [_ptr, ctypes.c_char_p, _ptr, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64]),
+    "xr_density_tensor": (_int, [_ptr, ctypes.c_char_p, _ptr, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _int]),
+    "xr_density_contracted": (_int, [_ptr, ctypes.c_char_p, _ptr, _ptr, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _int]),
     "xr_gemm_dd": (_int, [_ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _dbl, _ptr, _i64]),
     "xr_embed_add": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _int, _ptr, _int, _dbl]),
     "xr_permute_copy": (_int, [_ptr, _ptr, _ptr, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _dbl]),
@@ -176,10 +177,17 @@ class Context(object):
                                        arr(*[int(x) for x in src_strides]), float(alpha)), "xr_permute_copy")
 
     def density_tensor(self, ops, rho, n_bra_states, n_ket_states, z_bra, n_configs_bra, z_ket, n_configs_ket, ket_masks,
-                       n_elec_bra, n_elec_ket, n_orbs, n_core):
+                       n_elec_bra, n_elec_ket, n_orbs, n_core, accumulate=False):
         check(self.lib.xr_density_tensor(self.handle, ops.encode(), _p(rho), n_bra_states, n_ket_states, _p(z_bra), n_configs_bra,
-                                         _p(z_ket), n_configs_ket, _p(ket_masks), n_elec_bra, n_elec_ket, n_orbs, n_core),
+                                         _p(z_ket), n_configs_ket, _p(ket_masks), n_elec_bra, n_elec_ket, n_orbs, n_core,
+                                         1 if accumulate else 0),
               "xr_density_tensor")
+
+    def density_contracted(self, ops, out, weights, n_bra_states, n_ket_states, z_bra, n_configs_bra, z_ket, n_configs_ket, ket_masks,
+                           n_elec_bra, n_elec_ket, n_orbs, n_core, accumulate=False):
+        check(self.lib.xr_density_contracted(self.handle, ops.encode(), _p(out), _p(weights), n_bra_states, n_ket_states, _p(z_bra),
+                                             n_configs_bra, _p(z_ket), n_configs_ket, _p(ket_masks), n_elec_bra, n_elec_ket, n_orbs,
+                                             n_core, 1 if accumulate else 0), "xr_density_contracted")
 
     def gemm_dd(self, M, N, K, A, lda, B, ldb, C0, ldc0, sign, out, ldo):
         check(self.lib.xr_gemm_dd(self.handle, M, N, K, _p(A), lda, _p(B), ldb, _p(C0), ldc0, float(sign), _p(out), ldo), "xr_gemm_dd")

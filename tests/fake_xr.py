@@ -71,7 +71,7 @@ class FakeContext(object):
         D[...] = alpha * S
 
     def density_tensor(self, ops, rho, n_bra_states, n_ket_states, z_bra, n_configs_bra, z_ket, n_configs_ket, ket_masks,
-                       n_elec_bra, n_elec_ket, n_orbs, n_core):
+                       n_elec_bra, n_elec_ket, n_orbs, n_core, accumulate=False):
         """semantics of xr_density_tensor through the (test-only) Python restatement in oracle/density_oracle.py"""
         import os, sys
         sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -89,7 +89,20 @@ class FakeContext(object):
         masks = _view(ket_masks, n_configs_ket, numpy.int64)
         ket.configs = numpy.array([[i for i in range(dim) if (int(m) >> i) & 1] for m in masks], dtype=numpy.int64).reshape(n_configs_ket, n_elec_ket)
         out = do.tensor(ops, {"bra": bra, "ket": ket}, "bra", "ket", n_orbs, n_core)
-        _view(rho, out.size)[...] += out.reshape(-1)
+        if accumulate:
+            _view(rho, out.size)[...] += out.reshape(-1)
+        else:
+            _view(rho, out.size)[...] = out.reshape(-1)
+
+    def density_contracted(self, ops, out, weights, n_bra_states, n_ket_states, z_bra, n_configs_bra, z_ket, n_configs_ket, ket_masks,
+                           n_elec_bra, n_elec_ket, n_orbs, n_core, accumulate=False):
+        T = (2 * n_orbs) ** len(ops)
+        rho = numpy.zeros(n_bra_states * n_ket_states * T)
+        self.density_tensor(ops, rho.ctypes.data, n_bra_states, n_ket_states, z_bra, n_configs_bra, z_ket, n_configs_ket, ket_masks,
+                            n_elec_bra, n_elec_ket, n_orbs, n_core)
+        res = rho.reshape(n_bra_states * n_ket_states, T) @ _view(weights, T)
+        o = _view(out, n_bra_states * n_ket_states)
+        o[...] = o + res if accumulate else res
 
     def gemm_dd(self, M, N, K, A, lda, B, ldb, C0, ldc0, sign, out, ldo):
         self.launches += 1

@@ -130,3 +130,30 @@ def test_ci_vectors_to_hamiltonian_blocks_without_leaving_the_gpu(dev):
     ref2 = go.block_dimer(host_frags, symm, nuc, 0, 1)
     assert numpy.abs(H1 - ref1).max() <= 1e-10 * numpy.abs(ref1).max()
     assert numpy.abs(H2 - ref2).max() <= 1e-10 * numpy.abs(ref2).max()
+
+
+def test_contracted_density_equals_tensor_times_weights(dev):
+    """xr_density_contracted (the ccaa tensor reduced with V without ever being stored) against the stored tensor"""
+    z_lists, V = inputs()
+    n_orbs, n_core, n = CASE["n_orbs"], CASE["n_core"], 2 * CASE["n_orbs"]
+    masks = {c: dev.upload(numpy.bitwise_or.reduce(numpy.left_shift(numpy.uint64(1), z_lists[c].configs.astype(numpy.uint64)), axis=1)
+                           .view(numpy.int64), numpy.int64) for c in z_lists}
+    z = {c: dev.upload(z_lists[c].coeffs) for c in z_lists}
+    for op, bra, ket in (("ccaa", 0, 0), ("ccaa", -1, -1), ("ca", 1, 1), ("caa", 0, -1)):
+        T = n ** len(op)
+        w = numpy.random.default_rng(len(op) + bra).standard_normal(T)
+        Nb, Nk = z[bra].shape[0], z[ket].shape[0]
+        args = (Nb, Nk, z[bra], z[bra].shape[1], z[ket], z[ket].shape[1], masks[ket], z_lists[bra].configs.shape[1],
+                z_lists[ket].configs.shape[1], n_orbs, n_core)
+        rho = dev.empty((Nb * Nk, T))
+        dev.ctx.density_tensor(op, rho, *args)
+        want = dev.download(rho) @ w
+        out = dev.upload(numpy.full(Nb * Nk, 0.5))
+        dev.ctx.density_contracted(op, out, dev.upload(w), *args, accumulate=True)
+        got = dev.download(out)
+        assert numpy.abs(got - 0.5 - want).max() <= 1e-13 * max(1.0, numpy.abs(want).max())
+        again = dev.empty((Nb * Nk,))
+        dev.ctx.density_contracted(op, again, dev.upload(w), *args)
+        twice = dev.empty((Nb * Nk,))
+        dev.ctx.density_contracted(op, twice, dev.upload(w), *args)
+        assert numpy.array_equal(dev.download(again), dev.download(twice)), "fixed-order reduction must be reproducible"
