@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(256) density_hits_kernel(const DensityParams p
 }
 
 __global__ void __launch_bounds__(256) density_fill_kernel(const DensityParams p, int64_t chunks, const long long* __restrict__ offsets,
-                                                           const unsigned long long* __restrict__ hitmasks, uint2* __restrict__ entries) {
+                                                           const unsigned long long* __restrict__ hitmasks, uint2* __restrict__ entries,
+                                                           const double* __restrict__ weights, double* __restrict__ entry_weights) {
     const int64_t total = p.T * chunks;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t idx = t % p.T, chunk = t / p.T;
@@ -121,7 +122,9 @@ __global__ void __launch_bounds__(256) density_fill_kernel(const DensityParams p
             unsigned long long mask = p.ket_masks[Q];
             int flips;
             apply_string(p, orb, mask, flips);
-            entries[at++] = make_uint2((unsigned)config_rank(mask, p) | ((unsigned)(flips & 1) << 31), (unsigned)Q);
+            entries[at] = make_uint2((unsigned)config_rank(mask, p) | ((unsigned)(flips & 1) << 31), (unsigned)Q);
+            if (entry_weights) entry_weights[at] = (flips & 1) ? -weights[idx] : weights[idx];       // parity * weights[index]
+            ++at;
         }
     }
 }
@@ -183,15 +186,17 @@ __global__ void __launch_bounds__(256) density_apply_kernel(const DensityParams 
 }
 
 // Phase 2, contracted: out[I,J] (+)= sum_index weights[index] * rho[I,J,index] without ever storing rho (the reference forms
-// the ccaa tensor only to reduce it with V at once, build_density_tensors.py:125-133).  blockIdx.y = (bra tile, ket tile);
-// every thread folds its tensor indices in order, then a fixed shuffle/shared-memory tree and a fixed-order second pass
-// over the blocks: bit-reproducible.
+// the ccaa tensor only to reduce it with V at once, build_density_tensors.py:125-133).  No per-index structure is needed any
+// more: out = sum over ALL couplings e of (parity_e weights[index_e]) z_bra[:,P_e] (x) z_ket[:,Q_e] -- a flat, perfectly
+// balanced walk of the coupling list with coalesced entry loads.  blockIdx.y = (bra tile, ket tile); every thread folds
+// its couplings in order, then a fixed shuffle/shared-memory tree and a fixed-order second pass over the blocks:
+// bit-reproducible.
 constexpr int CONTRACT_BLOCKS = 512;
 
-__global__ void __launch_bounds__(256) density_contract_kernel(const DensityParams p, const long long* __restrict__ offsets,
-                                                               const uint2* __restrict__ entries, const double* __restrict__ zT_bra,
-                                                               const double* __restrict__ zT_ket, int64_t nb_pad, int64_t nk_pad, int64_t chunks,
-                                                               const double* __restrict__ weights, double* __restrict__ partials) {
+__global__ void __launch_bounds__(256) density_contract_kernel(const DensityParams p, long long nnz, const uint2* __restrict__ entries,
+                                                               const double* __restrict__ entry_weights, const double* __restrict__ zT_bra,
+                                                               const double* __restrict__ zT_ket, int64_t nb_pad, int64_t nk_pad,
+                                                               double* __restrict__ partials) {
     const int64_t itiles = nb_pad / IT;
     const int64_t I0 = (blockIdx.y % itiles) * IT, J0 = (blockIdx.y / itiles) * JT;
     double sum[IT][JT];
@@ -199,18 +204,18 @@ __global__ void __launch_bounds__(256) density_contract_kernel(const DensityPara
     for (int i = 0; i < IT; ++i)
 #pragma unroll
         for (int j = 0; j < JT; ++j) sum[i][j] = 0.0;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < p.T; idx += (int64_t)gridDim.x * blockDim.x) {
-        double acc[IT][JT];
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x) {
+        const uint2 entry = entries[e];
+        const double w = entry_weights[e];
+        const double4 b4 = *reinterpret_cast<const double4*>(zT_bra + (size_t)(entry.x & 0x7fffffffu) * nb_pad + I0);
+        const double4 k0 = *reinterpret_cast<const double4*>(zT_ket + (size_t)entry.y * nk_pad + J0);
+        const double4 k1 = *reinterpret_cast<const double4*>(zT_ket + (size_t)entry.y * nk_pad + J0 + 4);
+        const double left[IT] = {w * b4.x, w * b4.y, w * b4.z, w * b4.w};
+        const double zk[JT] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
 #pragma unroll
         for (int i = 0; i < IT; ++i)
 #pragma unroll
-            for (int j = 0; j < JT; ++j) acc[i][j] = 0.0;
-        sum_list(acc, offsets[idx * chunks], offsets[(idx + 1) * chunks], entries, zT_bra, zT_ket, nb_pad, nk_pad, I0, J0);
-        const double w = weights[idx];
-#pragma unroll
-        for (int i = 0; i < IT; ++i)
-#pragma unroll
-            for (int j = 0; j < JT; ++j) sum[i][j] = fma(w, acc[i][j], sum[i][j]);
+            for (int j = 0; j < JT; ++j) sum[i][j] = fma(left[i], zk[j], sum[i][j]);
     }
     __shared__ double red[8][IT * JT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -347,8 +352,10 @@ int density_run(xr_ctx* ctx, const char* what, const char* ops, double* rho, con
     XR_CUDA(cudaMemcpyAsync(&nnz, offsets + cells, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     XR_CUDA(cudaStreamSynchronize(ctx->stream));
     uint2* entries = nullptr;
+    double* entry_weights = nullptr;
     XR_CUDA(tmp.get(&entries, (size_t)nnz));
-    density_fill_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, chunks, offsets, hitmasks, entries);
+    if (!rho) XR_CUDA(tmp.get(&entry_weights, (size_t)nnz));
+    density_fill_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, chunks, offsets, hitmasks, entries, weights, entry_weights);
     XR_CUDA(cudaGetLastError());
 
     // phase 2
@@ -369,12 +376,13 @@ int density_run(xr_ctx* ctx, const char* what, const char* ops, double* rho, con
         ctx->launches += 5;
     } else {
         XR_REQUIRE(tiles < 65536, "%s: too many state tiles (%lld)", what, (long long)tiles);
-        int bx = (int)((p.T + 255) / 256);
+        int bx = (int)((nnz + 255) / 256);
         if (bx > CONTRACT_BLOCKS) bx = CONTRACT_BLOCKS;
+        if (bx < 1) bx = 1;
         double* partials = nullptr;
         XR_CUDA(tmp.get(&partials, (size_t)tiles * bx * IT * JT));
-        density_contract_kernel<<<dim3((unsigned)bx, (unsigned)tiles), 256, 0, ctx->stream>>>(p, offsets, entries, zT_bra, zT_ket, nb_pad, nk_pad,
-                                                                                             chunks, weights, partials);
+        density_contract_kernel<<<dim3((unsigned)bx, (unsigned)tiles), 256, 0, ctx->stream>>>(p, nnz, entries, entry_weights, zT_bra, zT_ket, nb_pad,
+                                                                                             nk_pad, partials);
         XR_CUDA(cudaGetLastError());
         density_contract_finish_kernel<<<(unsigned)((tiles * IT * JT + 255) / 256), 256, 0, ctx->stream>>>(p, partials, tiles, bx, nb_pad, out, accumulate);
         XR_CUDA(cudaGetLastError());
