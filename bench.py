@@ -264,18 +264,29 @@ def run_xr(args):
             key = ((hi - lo) * dims[m2], dims[m1] * dims[m2])
             if key not in host_out:
                 host_out[key] = torch.empty(key, dtype=torch.float64, pin_memory=True)
+        side = torch.cuda.Stream(device=dev.torch_device)
+        copied = [0]
+        def read_back_dimers():
+            # the dimer blocks are final once their launches are queued: read them back on a second stream while the
+            # trimer phase (99.9 % of the step) runs on the main one
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                for m1, m2 in dimers:
+                    mine = build.my_rows(m1, m2)
+                    host_out[tuple(mine.shape)].copy_(mine, non_blocking=True)
+                    copied[0] += mine.numel() * 8
         def e2e_step():
             eng.drop_caches(densities=True)
             dev.h2d_bytes = dev.d2h_bytes = 0
-            step()
-            d2h = 0
+            copied[0] = 0
+            build.step(gather=True, after_dimers=read_back_dimers)
+            d2h = copied[0]
             for m in range(F):
                 d2h += build.H1[m].numel() * 8
                 build.H1[m].cpu()
-            for m1, m2 in dimers:
-                mine = build.my_rows(m1, m2)
-                host_out[tuple(mine.shape)].copy_(mine, non_blocking=True)
-                d2h += mine.numel() * 8
+            side.synchronize()
             for ms_ in trimers:
                 d2h += build.H3_moments[ms_].numel() * 8
                 build.H3_moments[ms_].cpu()
@@ -298,7 +309,7 @@ def run_xr(args):
         e2e = {"value": total_flops * e2e_steps / (float(tms.item()) * 1e-3) / 1e12, "unit": UNIT,
                "h2d_bytes_per_step": int(byt[0].item()), "d2h_bytes_per_step": int(byt[1].item()),
                "seconds_per_step": float(tms.item()) * 1e-3 / e2e_steps, "steps": e2e_steps,
-               "note": "host wall clock (max over ranks) around upload + build + download of every H1, H2 slab and H3 moment"}
+               "note": "host wall clock (max over ranks) around upload + build + download of every H1, H2 slab and H3 moment; the H2 slabs are read back on a second stream while the trimer phase runs"}
 
     if rank != 0:
         if world > 1:

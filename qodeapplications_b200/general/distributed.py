@@ -53,7 +53,10 @@ class sharded_build(object):
         """the assembled H2[m1][m2] (valid on every rank after step(gather=True))"""
         return self.H2[(m1, m2)][:self.dims[m1] * self.dims[m2]]
 
-    def step(self, gather=True):
+    def step(self, gather=True, after_dimers=None):
+        """One build.  after_dimers(), if given, is called once every H1/H2 launch (and all-gather) of the step has been
+        queued and before the trimer streams are: the point where a caller can start reading the assembled dimer blocks
+        back on a second stream while the (much longer) trimer phase runs."""
         eng, rank, world = self.eng, self.rank, self.world
         for m in range(len(self.dims)):
             self.H1[m] = eng.H1_device(m)
@@ -64,6 +67,8 @@ class sharded_build(object):
                 d2 = self.dims[m2]
                 full = self.H2[(m1, m2)]
                 dist.all_gather_into_tensor(full, full[rank * per * d2:(rank + 1) * per * d2], group=self.group)
+        if after_dimers is not None:
+            after_dimers()
         for ms in self.trimers:
             self.H3_moments[ms] = eng.H3_moments_device(*ms, shard=(rank, world))
 
