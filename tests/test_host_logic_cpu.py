@@ -156,3 +156,26 @@ def test_general_streamed_dimer_moments_host_logic(name):
     s, q = eng.H2_moments(0, 1)
     assert abs(q - (ref ** 2).sum()) <= 1e-11 * (ref ** 2).sum()
     assert abs(s - ref.sum()) <= 1e-10 * numpy.abs(ref).sum()
+
+
+def test_tensornet_backend_function_table():
+    """hermitian/meta_backend.py: the table XRbase/meta_backend.py:27-72 hands to tensornet.primitive_tensor_factory"""
+    from qodeapplications_b200.hermitian import meta_backend as mb
+    from qodeapplications_b200.hermitian import tensor as xt
+    dev = FakeDevice()
+    wrap = lambda a: mb.xr_wrapper(xt.DeviceTensor(dev.upload(a), dev))
+    rng = numpy.random.default_rng(2)
+    A, B, S = rng.standard_normal((3, 4, 5, 6)), rng.standard_normal((2, 6)), rng.standard_normal((5, 7))
+    f = mb.xr_functions
+    out = f.contract((wrap(A), 0, 1, "p", "q"), 2.0, (wrap(B), 2, "q"), (wrap(S), "p", 3))
+    assert f.shape(out) == (3, 4, 2, 7)
+    assert numpy.allclose(out.host(), 2.0 * numpy.einsum("abpq,cq,pd->abcd", A, B, S), rtol=1e-13, atol=1e-13)
+    t = f.mult(-0.5, wrap(A))
+    assert numpy.array_equal(t.host(), -0.5 * A)
+    c = f.copy_data(t)
+    f.increment(c, wrap(A))
+    assert numpy.allclose(c.host(), 0.5 * A) and numpy.array_equal(t.host(), -0.5 * A)
+    assert f.element(wrap(A), (1, 2, 3, 4)) == A[1, 2, 3, 4]
+    s = f.contract((wrap(B), "x", "y"), (wrap(B), "x", "y"))
+    assert abs(f.scalar_value(s) - (B * B).sum()) < 1e-12 and f.shape(s) == ()
+    assert isinstance(f.str(s), str)
