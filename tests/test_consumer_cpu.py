@@ -90,3 +90,30 @@ def test_matrix_free_operator_host_logic(name):
     y = op.apply(torch.from_numpy(v)).numpy()
     D = ref.shape[0]
     assert numpy.abs(y.reshape(D, 2) - ref @ v.reshape(D, 2)).max() <= 1e-10 * numpy.abs(ref).max() * numpy.abs(v).max() * D ** 0.5
+
+
+def test_hermitian_full_matrix_host_logic():
+    """H2 + H1 (x) 1 + 1 (x) H1 restricted to charge-diagonal monomer blocks: hermitian-XRCC/mains/workflow.py:214-226 restated"""
+    from qodeapplications_b200.hermitian.full_matrix import full_matrix
+    rng = numpy.random.default_rng(6)
+    charges = [[0, 1, -1], [0, -1]]
+    state_dict = [{0: 3, 1: 2, -1: 2}, {0: 2, -1: 3}]
+    n = [sum(state_dict[m][c] for c in charges[m]) for m in (0, 1)]
+    H1 = [rng.standard_normal((n[0], n[0])), rng.standard_normal((n[1], n[1]))]
+    H2 = rng.standard_normal((n[0] * n[1], n[0] * n[1]))
+    slices = []
+    for m in (0, 1):
+        at, sl = 0, {}
+        for c in charges[m]:
+            sl[c] = slice(at, at + state_dict[m][c])
+            at += state_dict[m][c]
+        slices.append(sl)
+    ref = H2.copy().reshape(n[0], n[1], n[0], n[1])
+    for c0 in charges[0]:
+        for c1 in charges[1]:
+            ref[slices[0][c0], slices[1][c1], slices[0][c0], slices[1][c1]] += \
+                numpy.einsum("ij,kl->ikjl", H1[0][slices[0][c0], slices[0][c0]], numpy.eye(state_dict[1][c1])) + \
+                numpy.einsum("ij,kl->ikjl", numpy.eye(state_dict[0][c0]), H1[1][slices[1][c1], slices[1][c1]])
+    ref = ref.reshape(n[0] * n[1], n[0] * n[1])
+    got = full_matrix(H1, H2, state_dict, charges, device=FakeDevice())
+    assert numpy.abs(got - ref).max() <= 1e-14 * numpy.abs(ref).max()
