@@ -25,6 +25,7 @@ class Device(object):
         self.ctx = _lib.Context(self.index, stream)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._ring, self._ring_at = None, 0      # pinned staging ring for small pageable uploads
 
     def empty(self, shape, dtype=torch.float64):
         return torch.empty(shape, dtype=dtype, device=self.torch_device)
@@ -32,14 +33,30 @@ class Device(object):
     def zeros(self, shape, dtype=torch.float64):
         return torch.zeros(shape, dtype=dtype, device=self.torch_device)
 
+    STAGING_BYTES = 64 << 20
+
     def upload(self, array, dtype=numpy.float64):
-        """host ndarray -> device tensor on the current stream"""
+        """host ndarray -> device tensor on the current stream.  Pinned sources (bench.py pins its inputs) are copied
+        asynchronously as they are; small pageable ones (integral blocks, offset tables: hundreds per get_xr_H call) are
+        staged through a pinned ring so the host never waits for the stream; large pageable ones go through the driver's
+        own staging."""
         array = numpy.ascontiguousarray(array, dtype=dtype)
         host = torch.from_numpy(array)
         self.h2d_bytes += array.nbytes
-        # pinned sources (bench.py pins its inputs) go asynchronously; pageable ones are copied by the driver's
-        # own staging -- allocating a pinned bounce buffer per call costs more than it saves
-        return host.to(self.torch_device, non_blocking=host.is_pinned())
+        if host.is_pinned():
+            return host.to(self.torch_device, non_blocking=True)
+        if array.nbytes == 0 or array.nbytes > self.STAGING_BYTES // 4:
+            return host.to(self.torch_device)
+        if self._ring is None:
+            self._ring = torch.empty(self.STAGING_BYTES, dtype=torch.uint8, pin_memory=True)
+        size = (array.nbytes + 255) & ~255
+        if self._ring_at + size > self.STAGING_BYTES:
+            torch.cuda.current_stream(self.index).synchronize()      # every copy staged so far has left the ring
+            self._ring_at = 0
+        staged = self._ring[self._ring_at:self._ring_at + array.nbytes].view(host.dtype).reshape(host.shape)
+        self._ring_at += size
+        staged.copy_(host)
+        return staged.to(self.torch_device, non_blocking=True)
 
     def download(self, tensor):
         self.d2h_bytes += tensor.numel() * tensor.element_size()
