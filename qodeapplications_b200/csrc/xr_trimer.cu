@@ -23,6 +23,15 @@ namespace {
 
 constexpr int TA = 8, TB = 16, ROWS = TA * TB;
 
+// The first moment is LINEAR in the tile, so it does not need the stream: sum_abc T = sum_a sum_rs W[a,rs] (sum_b beta[b,r])
+// (sum_c gamma[c,s]), three tiny reductions (trimer_sum_kernel).  Only the second moment is accumulated element by element:
+// one FP64 instruction per element on the pipe the DMMAs share instead of two (+4 % on the whole kernel).  Set to 1 to
+// accumulate the sum from the streamed elements as well (the two agree to rounding; tests/test_general_gpu.py).
+#ifndef XR_TRIMER_STREAM_SUM
+#define XR_TRIMER_STREAM_SUM 0
+#endif
+constexpr bool STREAM_SUM = XR_TRIMER_STREAM_SUM != 0;
+
 struct TrimerParams {
     int n;
     int64_t Pb, Pc;
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
                 for (int i = 0; i < MI; ++i)
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
-                        s1p[j] += acc[i][j][0] + acc[i][j][1];
+                        if (STREAM_SUM) s1p[j] += acc[i][j][0] + acc[i][j][1];
                         s2p[j] = fma(acc[i][j][0], acc[i][j][0], s2p[j]);
                     }
 #pragma unroll
@@ -266,6 +275,49 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
             p.partials[2 * blockIdx.x + 1] = t2;
         }
     }
+}
+
+// sum of all T[a,b,c], a in [a_begin, a_end), from the factor sums (one block; fixed assignment and trees: reproducible)
+__global__ void __launch_bounds__(256) trimer_sum_kernel(int n, int64_t Pb, int64_t Pc, double alpha, const double* __restrict__ W,
+                                                         int64_t ldw, const double* __restrict__ beta, int64_t ldbeta,
+                                                         const double* __restrict__ gamma, int64_t ldgamma, int64_t a_begin,
+                                                         int64_t a_end, double* __restrict__ moments) {
+    __shared__ double colsum[2][48];
+    __shared__ double outer[48 * 48];
+    __shared__ double red[256];
+    const int tid = threadIdx.x;
+    for (int which = 0; which < 2; ++which) {
+        const double* M = which ? gamma : beta;
+        const int64_t rows = which ? Pc : Pb, ld = which ? ldgamma : ldbeta;
+        for (int c = 0; c < n; ++c) {
+            double s = 0.0;
+            for (int64_t r = tid; r < rows; r += 256) s += M[r * ld + c];
+            red[tid] = s;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if (tid < o) red[tid] += red[tid + o];
+                __syncthreads();
+            }
+            if (tid == 0) colsum[which][c] = red[0];
+            __syncthreads();
+        }
+    }
+    for (int e = tid; e < n * n; e += 256) outer[e] = colsum[0][e / n] * colsum[1][e % n];
+    __syncthreads();
+    double s = 0.0;
+    for (int64_t a = a_begin + tid; a < a_end; a += 256) {
+        const double* w = W + a * ldw;
+        double d = 0.0;
+        for (int e = 0; e < n * n; ++e) d = fma(w[e], outer[e], d);
+        s += d;
+    }
+    red[tid] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) moments[0] += alpha * red[0];
 }
 
 __global__ void trimer_finalize_kernel(const double* partials, int count, double alpha, double* moments) {
@@ -329,6 +381,12 @@ int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbet
         trimer_finalize_kernel<<<1, 32, 0, ctx->stream>>>(partials, grid, p.alpha, moments);
         XR_CUDA(cudaGetLastError());
         ctx->launches++;
+        if (!STREAM_SUM) {
+            trimer_sum_kernel<<<1, 256, 0, ctx->stream>>>(p.n, p.Pb, p.Pc, p.alpha, p.W, p.ldw, beta, ldbeta, gamma, ldgamma, p.a_begin,
+                                                          p.a_end, moments);
+            XR_CUDA(cudaGetLastError());
+            ctx->launches++;
+        }
     }
     return XR_OK;
 }
