@@ -344,7 +344,7 @@ def run_xr(args):
     if not args.no_cpu_baseline and world == 1:
         from oracle import cpu_baseline
         kind = cpu_baseline.prepare(system)
-        per_class = args.sample or 2500
+        per_class = args.sample or 20000        # ~15 s of CPU at ~90 us per element
         sample = cpu_baseline.make_sample(system, per_class)
         secs = cpu_baseline.time_sample(sample, 1)
         full_seconds = cpu_baseline.extrapolate(secs, sample, counts)

@@ -196,7 +196,9 @@ int xr_density_contracted(xr_ctx* ctx, const char* ops, double* out, const doubl
  * for a in [a_begin, a_end), b < Pb, c < Pc.  The Pa*Pb*Pc elements are formed tile by tile in
  * registers by FP64 DMMA and handed to a consumer, because at the benchmark sizes they cannot
  * be stored (1e13 elements per trimer):
- *   XR_TRIMER_REDUCE      moments[0] += sum T, moments[1] += sum T^2   (device doubles, caller zeroes)
+ *   XR_TRIMER_REDUCE      moments[0] += sum T, moments[1] += sum T^2   (device doubles, caller zeroes).  The second moment
+ *                         is accumulated element by element from the streamed tiles; the first is linear in T and is taken
+ *                         from the factor sums (sum_a sum_rs W[a,rs] (sum_b beta[b,r]) (sum_c gamma[c,s])), same value to rounding
  *   XR_TRIMER_MATERIALIZE C[offA[a] + offB[b] + offC[c]] = T[a,b,c]    (device int64 tables)
  * n <= 48. */
 enum xr_trimer_mode { XR_TRIMER_REDUCE = 0, XR_TRIMER_MATERIALIZE = 1 };

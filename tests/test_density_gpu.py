@@ -157,3 +157,29 @@ def test_contracted_density_equals_tensor_times_weights(dev):
         twice = dev.empty((Nb * Nk,))
         dev.ctx.density_contracted(op, twice, dev.upload(w), *args)
         assert numpy.array_equal(dev.download(again), dev.download(twice)), "fixed-order reduction must be reproducible"
+
+
+def test_argument_errors_are_loud(dev):
+    """bad arguments come back as XRError with a message (no silent fallback, no partial result)"""
+    from qodeapplications_b200.lib import XRError
+    z_lists, _ = inputs()
+    n_orbs, n_core = CASE["n_orbs"], CASE["n_core"]
+    z0 = dev.upload(z_lists[0].coeffs)
+    m0 = dev.upload(numpy.zeros(z_lists[0].configs.shape[0], dtype=numpy.int64), numpy.int64)
+    rho = dev.zeros((9 * 64,))
+    good = (3, 3, z0, 15, z0, 15, m0, 4, 4, n_orbs, n_core)
+    with pytest.raises(XRError, match="must consist of c and a"):
+        dev.ctx.density_tensor("cx", rho, *good)
+    with pytest.raises(XRError, match="does not connect"):
+        dev.ctx.density_tensor("a", rho, *good)
+    with pytest.raises(XRError, match="is not C"):
+        dev.ctx.density_tensor("ca", rho, 3, 3, z0, 14, z0, 15, m0, 4, 4, n_orbs, n_core)
+    with pytest.raises(XRError, match="2\\*n_orbs <= 64"):
+        dev.ctx.density_tensor("ca", rho, 3, 3, z0, 15, z0, 15, m0, 4, 4, 40, n_core)
+    with pytest.raises(XRError, match="sign must be"):
+        dev.ctx.gemm_dd(2, 2, 2, rho, 2, rho, 2, None, 0, 0.5, dev.zeros((4,)), 2)
+    with pytest.raises(XRError, match="spectator offset table"):
+        t = dev.upload(numpy.zeros(4, dtype=numpy.int64), numpy.int64)
+        dev.ctx.embed_add(rho, rho, 2, 2, 2, 3, t, t, None)
+    with pytest.raises(XRError, match="do not multiply"):
+        dev.ctx.embed_add(rho, rho, 4, 4, 4, 1, t, t, None, dims_sub=[3, 2], min_transitions=2)
