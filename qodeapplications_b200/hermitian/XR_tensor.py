@@ -7,7 +7,13 @@ The expression syntax of qode.math.tensornet that the reference's diagram files 
     2.0 * raw( A(0, 1, "p") @ B(2, 3, "q") @ S("p", "q") )   strings = contracted labels (each appears twice)
 
 but the product is evaluated on the GPU: the operands are uploaded once (tensor.DeviceStore) and contracted
-pairwise by xr_gemm_scatter (tensor.Contractor.multi_contract).
+pairwise by xr_gemm_scatter (tensor.Contractor.multi_contract).  Sums of such products are supported the way the
+reference's density code writes them (frag-states/compress_frags.py:91-99):
+
+    temp = XR_tensor.zeros()                      # takes its shape from the summed terms
+    temp += rho(0, 1, 2, 3);  temp -= rho(1, 0, 2, 3)
+    raw(temp)  /  temp(0, 1, "p", "q") @ ...      # the terms are accumulated into ONE buffer by the GEMM epilogues
+
 """
 import numpy
 
@@ -37,7 +43,65 @@ class _product(object):
         return _product(self.factors, -self.scalar)
 
 
+class _sum(object):
+    """sum of tensornet expressions with the same free (integer) labels; evaluated into one device buffer"""
+    def __init__(self, terms):
+        self.terms = list(terms)
+    def __add__(self, other):
+        return _sum(self.terms + _terms(other))
+    __iadd__ = __add__
+    def __sub__(self, other):
+        return _sum(self.terms + [-t for t in _terms(other)])
+    __isub__ = __sub__
+    def __mul__(self, scalar):
+        return _sum([t * scalar for t in self.terms])
+    __rmul__ = __mul__
+    def __neg__(self):
+        return _sum([-t for t in self.terms])
+    def __call__(self, *labels):
+        """index the (evaluated) sum like a primitive tensor, to use it inside a further product"""
+        return _device_tensor(evaluate(self))(*labels)
+    def __matmul__(self, other):
+        return self(*range(len(_free(self.terms[0])))) @ other
+
+
+def _terms(expr):
+    if isinstance(expr, _sum):
+        return list(expr.terms)
+    if isinstance(expr, xr_tensor):
+        return [] if expr.is_empty_sum else [expr(*range(len(expr.shape)))]
+    return [expr]
+
+
+def _free(product):
+    return sorted({l for _, labels in product.factors for l in labels if isinstance(l, (int, numpy.integer))})
+
+
+_product.__add__ = lambda self, other: _sum([self] + _terms(other))
+_product.__sub__ = lambda self, other: _sum([self] + [-t for t in _terms(other)])
+
+
+class _device_tensor(object):
+    """an evaluated expression (tensor.DeviceTensor) that can be indexed again"""
+    def __init__(self, device_tensor):
+        self.device_tensor = device_tensor
+    @property
+    def shape(self):
+        return self.device_tensor.shape
+    def __call__(self, *labels):
+        if len(labels) != len(self.shape):
+            raise ValueError("tensor of rank %d indexed with %d labels" % (len(self.shape), len(labels)))
+        return _product([(self.device_tensor, tuple(labels))])
+
+
 class xr_tensor(object):
+    is_empty_sum = False
+    def __add__(self, other):
+        return _sum(_terms(self) + _terms(other))
+    __iadd__ = __add__
+    def __sub__(self, other):
+        return _sum(_terms(self) + [-t for t in _terms(other)])
+    __isub__ = __sub__
     def __init__(self, array):
         self.array = numpy.ascontiguousarray(array, dtype=numpy.float64)
     @property
@@ -56,11 +120,25 @@ def init(raw_tensor):
 
 
 def zeros():
-    return xr_tensor(numpy.zeros(()))
+    """the empty sum: takes its shape from the terms added to it (XRbase/XR_tensor.py:55-56)"""
+    out = xr_tensor(numpy.zeros(()))
+    out.is_empty_sum = True
+    return out
 
 
 def evaluate(expr, engine=None):
     """device tensor of an expression; free (int) labels in ascending order"""
+    if isinstance(expr, _sum):
+        if not expr.terms:
+            raise ValueError("cannot evaluate an empty sum")
+        out = evaluate(expr.terms[0], engine)
+        store, contractor = engine or _default_engine()
+        for term in expr.terms[1:]:
+            if _free(term) != _free(expr.terms[0]):
+                raise ValueError("terms of a sum must have the same free indices")
+            factors = [(store.get(tensor), list(labels)) for tensor, labels in term.factors]
+            contractor.multi_contract(factors, _free(term), alpha=term.scalar, out=out, accumulate=True)
+        return out
     store, contractor = engine or _default_engine()
     factors, free = [], set()
     for tensor, labels in expr.factors:
@@ -72,8 +150,10 @@ def evaluate(expr, engine=None):
 
 
 def raw(tensor, engine=None):
-    if isinstance(tensor, _product):
+    if isinstance(tensor, (_product, _sum)):
         return evaluate(tensor, engine).host()
+    if isinstance(tensor, _device_tensor):
+        return tensor.device_tensor.host()
     if isinstance(tensor, DeviceTensor):
         return tensor.host()
     return as_host(tensor)

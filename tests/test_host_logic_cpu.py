@@ -179,3 +179,23 @@ def test_tensornet_backend_function_table():
     s = f.contract((wrap(B), "x", "y"), (wrap(B), "x", "y"))
     assert abs(f.scalar_value(s) - (B * B).sum()) < 1e-12 and f.shape(s) == ()
     assert isinstance(f.str(s), str)
+
+
+def test_xr_tensor_sums_of_products():
+    """XR_tensor: `temp = zeros(); temp += A(...); temp -= A(permuted)` as frag-states/compress_frags.py:91-99 writes it"""
+    from qodeapplications_b200.hermitian import XR_tensor
+    from qodeapplications_b200.hermitian.tensor import Contractor, DeviceStore
+    dev = FakeDevice()
+    engine = (DeviceStore(dev), Contractor(dev))
+    rng = numpy.random.default_rng(4)
+    a, b = rng.standard_normal((3, 3, 4)), rng.standard_normal((4, 5))
+    A, B = XR_tensor.init(a), XR_tensor.init(b)
+    temp = XR_tensor.zeros()
+    temp += A(0, 1, 2)
+    temp -= A(1, 0, 2)
+    assert numpy.allclose(XR_tensor.raw(temp, engine), a - a.transpose(1, 0, 2), atol=1e-15)
+    expr = 0.5 * (A(0, 1, "p") @ B("p", 2)) + A(1, 0, "p") @ B("p", 2) - 2.0 * (A(0, 1, "q") @ B("q", 2))
+    want = 0.5 * numpy.einsum("abp,pc->abc", a, b) + numpy.einsum("bap,pc->abc", a, b) - 2.0 * numpy.einsum("abq,qc->abc", a, b)
+    assert numpy.allclose(XR_tensor.raw(expr, engine), want, rtol=1e-13, atol=1e-13)
+    with pytest.raises(ValueError):
+        XR_tensor.raw(A(0, 1, 2) + B(0, 1), engine)
