@@ -219,7 +219,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
 
     # general-XRCC: 2-fragment toy (all dimer branches) and 3-fragment toy (all 12 trimer branches)
-    for name in ("toy", "toy3", "toy5", "toyh"):
+    for name in ("toy", "toy3", "toy5", "toyh", "toyh3"):
         system = synth.make_system(name)
         H1, H2, H3 = reference_general(system, trimers=True)
         payload = {"config": name, "seed": synth.SEEDS[name], "input_sha256": input_checksum(system)}

@@ -503,18 +503,25 @@ class build_matrix_elements(object):
             if pos in carries:
                 return lambda chg: _parity(f[pos].n_elec_ref, chg)
             return None
-        ldw = _even(nb * nc)
+        # the tile kernel takes ONE orbital count: fragments with different counts are padded to n = max(n_b, n_c) with zero
+        # rows of the (transposed) integral block, i.e. zero columns of W, beta and gamma
+        n = max(nb, nc)
+        def padded(block):          # [n_b, n_c, n_k*n_k] -> [n*n, n_k*n_k]
+            out = numpy.zeros((n, n, nk * nk))
+            out[:nb, :nc] = block
+            return out.reshape(n * n, nk * nk)
+        ldw = _even(n * n)
         W = self.dev.zeros((ck.P, ldw))
         if cl["kind"] == "2min":      # 2 sum V[k,k,b,c][p,q,r,s] cc_k[q,p]
-            Vt = self._ints(("t2min", mk, mb, mc), lambda: V[mk, mk, mb, mc].transpose(2, 3, 1, 0).reshape(nb * nc, nk * nk))
+            Vt = self._ints(("t2min", mk, mb, mc), lambda: padded(V[mk, mk, mb, mc].transpose(2, 3, 1, 0).reshape(nb, nc, nk * nk)))
             self._fill_contracted(W, ldw, 0, mk, "cc", ck, Vt, scale=2.0, sign=sign_of(k))
             op_b = op_c = "a"
         elif cl["kind"] == "2pls":    # 2 sum V[b,c,k,k][r,s,p,q] aa_k[q,p]
-            Vt = self._ints(("t2pls", mk, mb, mc), lambda: V[mb, mc, mk, mk].transpose(0, 1, 3, 2).reshape(nb * nc, nk * nk))
+            Vt = self._ints(("t2pls", mk, mb, mc), lambda: padded(V[mb, mc, mk, mk].transpose(0, 1, 3, 2).reshape(nb, nc, nk * nk)))
             self._fill_contracted(W, ldw, 0, mk, "aa", ck, Vt, scale=2.0, sign=sign_of(k))
             op_b = op_c = "c"
         else:                         # 4 sum V[k,cre,k,ann][p,r,q,s] ca_k[p,q] + delta_k U[k,cre,ann][r,s]
-            Vt = self._ints(("tex", mk, mb, mc), lambda: V[mk, mb, mk, mc].transpose(1, 3, 0, 2).reshape(nb * nc, nk * nk))
+            Vt = self._ints(("tex", mk, mb, mc), lambda: padded(V[mk, mb, mk, mc].transpose(1, 3, 0, 2).reshape(nb, nc, nk * nk)))
             self._fill_contracted(W, ldw, 0, mk, "ca", ck, Vt, scale=4.0, sign=sign_of(k))
             # delta(i_k, j_k) * U[k,cre,ann][r,s] on the diagonal rows: rank-1 update through the same kernel
             drows = ck.diagonal_rows(f[k])
@@ -525,15 +532,19 @@ class build_matrix_elements(object):
                     if ci == cj:
                         i = numpy.arange(i_lo, i_hi)
                         dvec[off + (i - i_lo) * f[k].n_states[cj] + i, 0] = 1.0 if sg is None else sg(ci)
-                Uv = self._ints(("tU", mk, mb, mc), lambda: numpy.stack([U[mk, mb, mc].reshape(nb * nc), numpy.zeros(nb * nc)], axis=1))
-                self.dev.ctx.gemm_scatter(ck.P, nb * nc, 1, 1.0, self.dev.upload(dvec), 2, Uv, 2, W, None, ldw, None, True)
+                def padded_U():
+                    out = numpy.zeros((n, n))
+                    out[:nb, :nc] = U[mk, mb, mc]
+                    return numpy.stack([out.reshape(n * n), numpy.zeros(n * n)], axis=1)
+                Uv = self._ints(("tU", mk, mb, mc), padded_U)
+                self.dev.ctx.gemm_scatter(ck.P, n * n, 1, 1.0, self.dev.upload(dvec), 2, Uv, 2, W, None, ldw, None, True)
             op_b, op_c = "c", "a"
-        beta = self.dev.zeros((cb.P, _even(nb)))
-        gamma = self.dev.zeros((cc.P, _even(nc)))
-        self._fill_raw(beta, _even(nb), 0, mb, op_b, cb, sign=sign_of(b))
-        self._fill_raw(gamma, _even(nc), 0, mc, op_c, cc, sign=sign_of(c))
+        beta = self.dev.zeros((cb.P, _even(n)))
+        gamma = self.dev.zeros((cc.P, _even(n)))
+        self._fill_raw(beta, _even(n), 0, mb, op_b, cb, sign=sign_of(b))
+        self._fill_raw(gamma, _even(n), 0, mc, op_c, cc, sign=sign_of(c))
         alpha = -1.0 if cl["flip"] else 1.0
-        return dict(W=W, ldw=ldw, beta=beta, gamma=gamma, ck=ck, cb=cb, cc=cc, alpha=alpha, n=nb, k=k, b=b, c=c)
+        return dict(W=W, ldw=ldw, beta=beta, gamma=gamma, ck=ck, cb=cb, cc=cc, alpha=alpha, n=n, k=k, b=b, c=c)
 
     def H3(self, m1, m2, m3):
         """H3[m1][m2][m3] dense (host ndarray), test_H.py:113-126 ordering.  Only for sizes that fit."""
@@ -552,8 +563,6 @@ class build_matrix_elements(object):
             fac = self._trimer_factors(ms, cl)
             if fac is None:
                 continue
-            if fac["n"] != f[cl["c"]].n_orb:
-                raise NotImplementedError("fragments with different orbital counts in one trimer")
             offs = []
             for role, cls in ((cl["k"], fac["ck"]), (cl["b"], fac["cb"]), (cl["c"], fac["cc"])):
                 offs.append(self._index(cls.offsets(f[role], stride[role] * D, stride[role])))

@@ -76,7 +76,7 @@ class xr_operator(object):
                 roles = [cl["k"], cl["b"], cl["c"]]
                 xk, xb, xc = (xs[r] for r in roles)
                 fk, fb, fc = (self.info[x] for x in (xk, xb, xc))
-                nb, nc = fb.n_orb, fc.n_orb
+                nb = nc = fac["n"]          # both padded to the larger orbital count by _trimer_factors
                 ldb, ldc = fac["beta"].shape[1], fac["gamma"].shape[1]
                 for cik, cjk, lok, hik, offk in fac["ck"].sectors:
                     Njk = fk.n_states[cjk]

@@ -27,6 +27,7 @@ CONFIGS = {
     "toy5": dict(n_frag=3, n_orb=4,  n_states={0: 2, +1: 2, -1: 2, +2: 1, -2: 1}),   # five charge states (general-XRCC/Be631g.py:73)
     "toy4": dict(n_frag=2, n_orb=5,  n_states={0: 3,   +1: 2,   -1: 2}),               # S-orders 3-4 (8-operator densities)
     "toyh": dict(n_frag=2, n_orb=[6, 4], n_states={0: 3, +1: 2, -1: 2}),             # fragments with different orbital counts
+    "toyh3": dict(n_frag=3, n_orb=[5, 4, 3], n_states={0: 2, +1: 2, -1: 2}),         # ... and in one trimer
     "mid":  dict(n_frag=2, n_orb=8,  n_states={0: 5,   +1: 3,   -1: 4}),
     "herm49":  dict(n_frag=2, n_orb=18, n_states={0: 24, +1: 8,  -1: 17}),           # hermitian path at larger state counts
     "herm100": dict(n_frag=2, n_orb=18, n_states={0: 48, +1: 17, -1: 35}),           # (cfg4's 96:34:70 halved; order-0 densities 7 GB)
@@ -36,7 +37,7 @@ CONFIGS = {
     "cfg4": dict(n_frag=4, n_orb=18, n_states={0: 96,  +1: 34,  -1: 70}),
     "cfg5": dict(n_frag=2, n_orb=48, n_states={0: 478, +1: 174, -1: 348}),
 }
-SEEDS = {"toy": 11, "toy3": 13, "mid": 17, "toy5": 19, "toyh": 29, "toy4": 31, "cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5, "herm49": 41, "herm100": 43}
+SEEDS = {"toy": 11, "toy3": 13, "mid": 17, "toy5": 19, "toyh": 29, "toy4": 31, "cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5, "herm49": 41, "herm100": 43, "toyh3": 37}
 N_ELEC_REF = 4
 
 OPS_ORDER0 = ("a", "c", "aa", "cc", "ca", "caa", "cca", "ccaa")

@@ -63,7 +63,7 @@ def test_unequal_fragment_dimensions_host_logic():
         big.add((0, 1), H2[0][2])
 
 
-@pytest.mark.parametrize("name", ["toy3", "toy5"])
+@pytest.mark.parametrize("name", ["toy3", "toy5", "toyh3"])
 def test_matrix_free_operator_host_logic(name):
     """y = Hmat.v from the class factors (never forming H2/H3) equals the reference's braket_loops matrix"""
     from qodeapplications_b200 import synth
@@ -74,8 +74,8 @@ def test_matrix_free_operator_host_logic(name):
     op = xr_operator(eng)
     if name == "toy3":
         ref = numpy.load(os.path.join(GOLDEN, "supersystem_hmat.npz"))["toy3"]
-    else:       # five charge states: the reference's blocks from the fixture, expanded by the oracle restatement
-        g = numpy.load(os.path.join(GOLDEN, "general_toy5.npz"))
+    else:       # five charge states / unequal orbital counts: the reference's blocks from the fixture, expanded by the oracle restatement
+        g = numpy.load(os.path.join(GOLDEN, "general_%s.npz" % name))
         H3 = numpy.zeros(tuple(g["H3_012_shape"]))
         H3[g["H3_012_rows"], g["H3_012_cols"]] = g["H3_012_vals"]
         H = ([g["H1_%d" % m] for m in range(3)], [[g["H2_%d%d" % (M, N)] if M < N else None for N in range(3)] for M in range(3)],

@@ -134,7 +134,7 @@ def test_legacy_scalar_abi(dev):
 
 # ------------------------------------------------------------------------------ H blocks
 
-@pytest.mark.parametrize("name", ["toy", "toy3", "toy5", "toyh"])
+@pytest.mark.parametrize("name", ["toy", "toy3", "toy5", "toyh", "toyh3"])
 def test_blocks_match_reference_golden(dev, name):
     g = numpy.load(os.path.join(GOLDEN, "general_%s.npz" % name))
     system = synth.make_system(name)

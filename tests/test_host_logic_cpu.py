@@ -19,7 +19,7 @@ def _close(a, b, tol=1e-10):
     assert numpy.abs(a - b).max() <= tol * scale, (numpy.abs(a - b).max(), scale)
 
 
-@pytest.mark.parametrize("name", ["toy", "toy3", "toy5", "toyh"])
+@pytest.mark.parametrize("name", ["toy", "toy3", "toy5", "toyh", "toyh3"])
 def test_general_blocks_host_logic(name):
     from qodeapplications_b200.general.build_H import build_matrix_elements
     g = numpy.load(os.path.join(GOLDEN, "general_%s.npz" % name))

@@ -28,7 +28,7 @@ def _close(a, b, tol=1e-10):
     assert numpy.abs(a - b).max() <= tol * scale, (numpy.abs(a - b).max(), scale)
 
 
-@pytest.mark.parametrize("name", ["toy", "toy3", "toy5", "toyh"])
+@pytest.mark.parametrize("name", ["toy", "toy3", "toy5", "toyh", "toyh3"])
 def test_block_oracle_matches_reference_golden(name):
     g = _load("general_%s.npz" % name)
     system = synth.make_system(name)
