@@ -12,6 +12,10 @@
 // Warp-specialised: a producer warpgroup (one elected lane) streams gamma tiles into a SLOTS-deep
 // ring with full/empty mbarriers per slot; the 8 consumer warps never meet at a block-wide barrier
 // inside the tile loop.  setmaxnreg moves the producer warpgroup's registers to the consumers.
+// The same lane also prefetches the NEXT work item's operands (TA rows of W, TB rows of beta) into a
+// staging buffer by bulk TMA while the current item's tiles are consumed, so forming X at an item
+// boundary reads shared memory only (the global-load version of that step -- 18 dependent L2 round
+// trips per output -- left the FP64 pipe idle for ~8 % of the kernel: stall_barrier in profiles/r01j).
 //
 // Roofline: FP64 pipe (DMMA.8x8x4 and DFMA share it on sm_100: 64 FMA/clk/SM, 37.2 TFLOP/s measured).
 // Algorithmic flops are 2*n per element.  k = n is split as 4*KS (DMMA k-steps) + TAIL (0..2 leftover
@@ -31,6 +35,43 @@ constexpr int TA = 8, TB = 16, ROWS = TA * TB;
 #define XR_TRIMER_STREAM_SUM 0
 #endif
 constexpr bool STREAM_SUM = XR_TRIMER_STREAM_SUM != 0;
+// Development switches (tools/trimer_variants.py builds one library per setting and times them on the GPU):
+//   XR_TRIMER_PREFETCH  wait for the NEXT gamma tile and load its first B fragments before the moment/store epilogue of the
+//                       current one, so the barrier poll and the shared-memory latency sit under FP64 work
+//   XR_TRIMER_MODE_T    compile the consumer (reduce / materialize) in as a template parameter instead of a uniform branch
+#ifndef XR_TRIMER_PREFETCH
+#define XR_TRIMER_PREFETCH 0
+#endif
+#ifndef XR_TRIMER_MODE_T
+#define XR_TRIMER_MODE_T 0
+#endif
+//   XR_TRIMER_SEP_TAIL  keep the DFMA k-tail in its own basic block (a run-time-true branch), so ptxas cannot interleave it
+//                       with the last DMMAs of the tile
+//   XR_TRIMER_TAIL_FIRST  start every accumulator from the DFMA k-tail and let the DMMA k-steps accumulate on top
+//   XR_TRIMER_NOSQ / XR_TRIMER_DIAG16  timing diagnostics only (wrong moments / n = 16 without a tail)
+#ifndef XR_TRIMER_SEP_TAIL
+#define XR_TRIMER_SEP_TAIL 1
+#endif
+#ifndef XR_TRIMER_TAIL_FIRST
+#define XR_TRIMER_TAIL_FIRST 0
+#endif
+#ifndef XR_TRIMER_NOSQ
+#define XR_TRIMER_NOSQ 0
+#endif
+#ifndef XR_TRIMER_DIAG16
+#define XR_TRIMER_DIAG16 0
+#endif
+#ifndef XR_TRIMER_SYNC
+#define XR_TRIMER_SYNC 0
+#endif
+#ifndef XR_TRIMER_PRETAIL
+#define XR_TRIMER_PRETAIL 0
+#endif
+#ifndef XR_TRIMER_CHAINS16
+#define XR_TRIMER_CHAINS16 0
+#endif
+constexpr bool PREFETCH = XR_TRIMER_PREFETCH != 0;
+constexpr bool SEP_TAIL = XR_TRIMER_SEP_TAIL != 0, TAIL_FIRST = XR_TRIMER_TAIL_FIRST != 0, NOSQ = XR_TRIMER_NOSQ != 0;
 
 struct TrimerParams {
     int n;
@@ -50,6 +91,7 @@ struct TrimerParams {
     const int64_t* offC;
     int64_t tiles_b, n_items;
     int c_tiles;
+    int staged;             // W rows are 16-byte aligned: the producer stages each item's W/beta rows by bulk TMA
 };
 
 // WN = consumer warps along c: 2 -> 8 warps, each 32 rows x 64 columns (128-column gamma tiles, 240 registers);
@@ -65,8 +107,11 @@ struct TrimerCfg {
     static constexpr int GS = (KP % 16 == 4 || KP % 16 == 12) ? KP : KP + 4;       // conflict-free fragment stride
     static constexpr bool AREG = KS <= 5;                                         // A fragments live in registers
     static constexpr int SLOTS = KS <= 5 ? 4 : 2;                                 // gamma ring depth (shared memory bound)
+    static constexpr bool STAGE = KS <= 5;                                        // item operands prefetched into shared memory
+    static constexpr int WS = STAGE ? (KP * KP + 1) / 2 * 2 : 0;                  // staged W row (n*n <= KP*KP doubles, even)
+    static constexpr int STAGE_DOUBLES = STAGE ? TA * WS + TB * KP : 0;
     static constexpr size_t SMEM = (size_t)(ROWS + SLOTS * CT) * GS * sizeof(double) + (size_t)SLOTS * CT * 2 * sizeof(double) +
-                                   2 * SLOTS * sizeof(uint64_t) + 64;
+                                   (size_t)STAGE_DOUBLES * sizeof(double) + (2 * SLOTS + 1) * sizeof(uint64_t) + 64;
 };
 
 template <int CONSUMER_THREADS>
@@ -77,30 +122,82 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int KS, int TAIL, int WN>
+// X[(a,b), s] = sum_r W[a, r*n + s] * beta[b, r] for one work item, r ascending (one rounding order for both sources).
+// Consumer warp w forms the TB rows of a = a0 + w; lane <-> s.  SMEM_SRC: W rows and beta rows come from the staging
+// buffer the producer filled by bulk TMA; otherwise straight from global memory with the r loop unrolled so that the
+// loads of several r are in flight together.
+template <bool SMEM_SRC, int KP, int GS>
+__device__ __forceinline__ void build_item_X(double* __restrict__ Xs, const double* __restrict__ Wsrc, int64_t w_row_stride,
+                                             const double* __restrict__ Bsrc, int n, int warp, int lane, int na, int nb) {
+    for (int al = warp; al < TA; al += 8) {
+        for (int s = lane; s < KP; s += 32) {
+            double acc[TB];
+#pragma unroll
+            for (int b = 0; b < TB; ++b) acc[b] = 0.0;
+            if (al < na && s < n) {
+                const double* w = Wsrc + (int64_t)al * w_row_stride + s;
+                if (SMEM_SRC) {
+                    for (int r = 0; r < n; ++r) {
+                        const double wv = w[r * n];
+#pragma unroll
+                        for (int b = 0; b < TB; ++b) acc[b] = fma(wv, Bsrc[b * KP + r], acc[b]);
+                    }
+                } else {
+                    constexpr int U = 6;
+                    for (int r0 = 0; r0 < n; r0 += U) {
+                        double wv[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) wv[u] = r0 + u < n ? __ldg(w + (int64_t)(r0 + u) * n) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            if (r0 + u < n) {
+#pragma unroll
+                                for (int b = 0; b < TB; ++b) {
+                                    const double bv = b < nb ? __ldg(Bsrc + b * KP + r0 + u) : 0.0;
+                                    acc[b] = fma(wv[u], bv, acc[b]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < TB; ++b) Xs[(al * TB + b) * GS + s] = b < nb ? acc[b] : 0.0;
+        }
+    }
+}
+
+template <int KS, int TAIL, int WN, int MODE>      // MODE < 0: the consumer is chosen at run time (p.mode)
 __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_stream_kernel(const TrimerParams p) {
     using Cfg = TrimerCfg<KS, TAIL, WN>;
+    const int mode = MODE < 0 ? p.mode : MODE;
     constexpr int KP = Cfg::KP, GS = Cfg::GS, SLOTS = Cfg::SLOTS, CT = Cfg::CT;
     constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS, CONSUMER_THREADS = Cfg::CONSUMER_THREADS;
-    constexpr bool AREG = Cfg::AREG;
-    constexpr int MI = 4, NJ = Cfg::NJ, WCOLS = NJ * 8;
+    constexpr bool AREG = Cfg::AREG, STAGE = Cfg::STAGE;
+    constexpr int MI = 4, NJ = Cfg::NJ, WCOLS = NJ * 8, WS = Cfg::WS;
+    static_assert(CONSUMER_WARPS >= 8, "build_item_X spreads the TA rows of W over 8 consumer warps");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* Gs = reinterpret_cast<double*>(smem_raw);                  // [SLOTS][CT][GS]  (bulk-copy destinations: 16B aligned)
     double* Gt = Gs + SLOTS * CT * GS;                                  // [SLOTS][CT][2]   tail columns, compact
     double* Xs = Gt + SLOTS * CT * 2;                                   // [ROWS][GS]
-    uint64_t* full = reinterpret_cast<uint64_t*>(Xs + ROWS * GS);       // [SLOTS]
+    double* Wst = Xs + ROWS * GS;                                       // [TA][WS]   next item's W rows   (STAGE only)
+    double* Bst = Wst + TA * WS;                                        // [TB][KP]   next item's beta rows (STAGE only)
+    uint64_t* full = reinterpret_cast<uint64_t*>(Xs + ROWS * GS + Cfg::STAGE_DOUBLES);   // [SLOTS]
     uint64_t* empty = full + SLOTS;                                     // [SLOTS]
+    uint64_t* wfull = empty + SLOTS;                                    // staging buffer filled (one phase per work item)
     __shared__ double red[2][CONSUMER_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr uint32_t TILE_BYTES = CT * GS * sizeof(double);
     constexpr uint32_t TAIL_BYTES = TAIL ? CT * 2 * sizeof(double) : 0;
+    const bool staged = STAGE && p.staged;
 
     if (tid == 0) {
         for (int s = 0; s < SLOTS; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], CONSUMER_WARPS);
         }
+        mbar_init(wfull, 1);
         fence_barrier_init();
     }
     __syncthreads();
@@ -112,16 +209,50 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
     if (warp >= CONSUMER_WARPS) {
         // -------------------------------------------------- producer warpgroup (one lane works)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::PRODUCER_REGS));     // hand registers to the consumers
-        if (warp == CONSUMER_WARPS && lane == 0) {
+        if (warp == CONSUMER_WARPS && lane == 0 && my_items > 0) {
+            // coordinates of the next item to stage; items advance by gridDim.x
+            int64_t ia = (int64_t)blockIdx.x / p.tiles_b, ib = (int64_t)blockIdx.x % p.tiles_b;
+            const uint32_t row_bytes = (uint32_t)(((p.n * p.n + 1) / 2 * 2) * sizeof(double));
+            auto stage_item = [&]() {
+                const int64_t a0 = p.a_begin + ia * TA, b0 = ib * TB;
+                const int na = (int)(p.a_end - a0 < TA ? p.a_end - a0 : TA);
+                const int nb = (int)(p.Pb - b0 < TB ? p.Pb - b0 : TB);
+                const uint32_t beta_bytes = (uint32_t)(nb * KP * sizeof(double));
+                mbar_expect_tx(wfull, (uint32_t)na * row_bytes + beta_bytes);
+                for (int i = 0; i < na; ++i) bulk_copy_g2s(Wst + i * WS, p.W + (a0 + i) * p.ldw, row_bytes, wfull);
+                bulk_copy_g2s(Bst, p.betaP + b0 * KP, beta_bytes, wfull);
+                ib += gridDim.x;
+                while (ib >= p.tiles_b) {
+                    ib -= p.tiles_b;
+                    ++ia;
+                }
+            };
+            int64_t staged_items = 0, next_stage_q = SLOTS;
+            if (staged) {
+                stage_item();
+                staged_items = 1;
+            }
             int ct = 0;
-            for (int64_t q = 0; q < total_tiles; ++q) {
+            // Item it+1 is staged once tile (it, 0) has been released by every consumer warp -- they all built X(it)
+            // from the staging buffer before touching that tile -- i.e. just before global tile it*c_tiles + SLOTS is
+            // issued.  The loop runs SLOTS steps past the last tile so that rule also covers c_tiles < SLOTS.
+            for (int64_t q = 0; q < total_tiles + SLOTS; ++q) {
                 const int slot = (int)(q % SLOTS);
                 const uint32_t round = (uint32_t)(q / SLOTS);
                 mbar_wait(&empty[slot], (round & 1) ^ 1);     // passes at once on the first lap
-                mbar_expect_tx(&full[slot], TILE_BYTES + TAIL_BYTES);
-                bulk_copy_g2s(Gs + (size_t)slot * CT * GS, p.gammaP + (size_t)ct * CT * GS, TILE_BYTES, &full[slot]);
-                if (TAIL) bulk_copy_g2s(Gt + (size_t)slot * CT * 2, p.gammaT + (size_t)ct * CT * 2, TAIL_BYTES, &full[slot]);
-                if (++ct == p.c_tiles) ct = 0;
+                if (q == next_stage_q) {
+                    if (staged && staged_items < my_items) {
+                        stage_item();
+                        ++staged_items;
+                    }
+                    next_stage_q += p.c_tiles;
+                }
+                if (q < total_tiles) {
+                    mbar_expect_tx(&full[slot], TILE_BYTES + TAIL_BYTES);
+                    bulk_copy_g2s(Gs + (size_t)slot * CT * GS, p.gammaP + (size_t)ct * CT * GS, TILE_BYTES, &full[slot]);
+                    if (TAIL) bulk_copy_g2s(Gt + (size_t)slot * CT * 2, p.gammaT + (size_t)ct * CT * 2, TAIL_BYTES, &full[slot]);
+                    if (++ct == p.c_tiles) ct = 0;
+                }
             }
         }
         return;
@@ -136,23 +267,23 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
     for (int j = 0; j < NJ; ++j) s1p[j] = s2p[j] = 0.0;
     const int n = p.n;
     int64_t q = 0;
+    uint32_t item_parity = 0;
+    double bnext[PREFETCH ? NJ : 1];     // first-k-step B fragments of the next gamma tile
+    int nosq_bits = 0;
 
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int64_t a0 = p.a_begin + (item / p.tiles_b) * TA;
         const int64_t b0 = (item % p.tiles_b) * TB;
+        const int na = (int)(p.a_end - a0 < TA ? p.a_end - a0 : TA);
+        const int nb = (int)(p.Pb - b0 < TB ? p.Pb - b0 : TB);
 
         consumer_barrier<CONSUMER_THREADS>();    // every consumer is done with the previous item's Xs
-        // X[(a,b), s] = sum_r W[a, r*n + s] * beta[b, r]
-        for (int idx = tid; idx < ROWS * KP; idx += CONSUMER_THREADS) {
-            const int row = idx / KP, s = idx - row * KP;
-            const int64_t a = a0 + row / TB, b = b0 + row % TB;
-            double v = 0.0;
-            if (a < p.a_end && b < p.Pb && s < n) {
-                const double* w = p.W + a * p.ldw + s;
-                const double* be = p.betaP + b * KP;
-                for (int r = 0; r < n; ++r) v = fma(__ldg(w + (int64_t)r * n), __ldg(be + r), v);
-            }
-            Xs[row * GS + s] = v;
+        if (STAGE && staged) {
+            mbar_wait(wfull, item_parity);
+            item_parity ^= 1;
+            build_item_X<true, KP, GS>(Xs, Wst, WS, Bst, n, warp, lane, na, nb);
+        } else {
+            build_item_X<false, KP, GS>(Xs, p.W + a0 * p.ldw, p.ldw, p.betaP + b0 * KP, n, warp, lane, na, nb);
         }
         consumer_barrier<CONSUMER_THREADS>();
 
@@ -174,29 +305,69 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
 
         for (int ct = 0; ct < p.c_tiles; ++ct, ++q) {
             const int slot = (int)(q % SLOTS);
-            mbar_wait(&full[slot], (uint32_t)(q / SLOTS) & 1);
-
-            double acc[MI][NJ][2];
             const double* gtile = Gs + (size_t)slot * CT * GS;
             const double* gs = gtile + (WCOLS * wn + g) * GS + t;
+#if XR_TRIMER_SYNC == 1
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + (warp & 3)) : "memory");     // the two warps of one scheduler start the tile together
+#elif XR_TRIMER_SYNC == 2
+            consumer_barrier<CONSUMER_THREADS>();
+#endif
+            if (!PREFETCH || q == 0) {
+                mbar_wait(&full[slot], (uint32_t)(q / SLOTS) & 1);
+                if (PREFETCH) {
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) bnext[j] = gs[j * 8 * GS];
+                }
+            }
+
+            double acc[MI][NJ][2];
+            if (TAIL && TAIL_FIRST && SEP_TAIL && p.n <= 4 * KS) {      // never taken (TAIL > 0 means n > 4*KS): keeps the tail a basic block
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            } else if (TAIL && TAIL_FIRST) {
+                const double2* gt = reinterpret_cast<const double2*>(Gt + (size_t)slot * CT * 2) + WCOLS * wn + 2 * t;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double2 v = gt[8 * j + e];
+#pragma unroll
+                        for (int i = 0; i < MI; ++i) {
+                            acc[i][j][e] = atail[i][0] * v.x;
+                            if (TAIL == 2) acc[i][j][e] = fma(atail[i][TAIL - 1], v.y, acc[i][j][e]);
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 double b[NJ];
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) b[j] = gs[j * 8 * GS + 4 * ks];
+                for (int j = 0; j < NJ; ++j) b[j] = (PREFETCH && ks == 0) ? bnext[j] : gs[j * 8 * GS + 4 * ks];
 #pragma unroll
                 for (int i = 0; i < MI; ++i) {
                     const double a = AREG ? areg[AREG ? i : 0][AREG ? ks : 0] : xs[i * 8 * GS + 4 * ks];
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
-                        if (ks == 0)
+                        if (ks == 0 && !(TAIL && TAIL_FIRST))
                             dmma_m8n8k4_zero(acc[i][j][0], acc[i][j][1], a, b[j]);
                         else
                             dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a, b[j]);
                     }
                 }
             }
-            if (TAIL) {
+#if XR_TRIMER_PRETAIL
+            // the first tail operands are fetched in the DMMA block, so the DFMA block does not start on a shared-memory round trip
+            double2 vpre[XR_TRIMER_PRETAIL];
+            if (TAIL && !TAIL_FIRST) {
+                const double2* gtp = reinterpret_cast<const double2*>(Gt + (size_t)slot * CT * 2) + WCOLS * wn + 2 * t;
+#pragma unroll
+                for (int u = 0; u < XR_TRIMER_PRETAIL; ++u) vpre[u] = gtp[8 * (u >> 1) + (u & 1)];
+            }
+#endif
+            if (TAIL && !TAIL_FIRST && (!SEP_TAIL || p.n > 4 * KS)) {
                 // leftover k (n - 4*KS <= 2) on the accumulator layout: lane owns rows 8i+g, columns 8j+2t+{0,1}.
                 // The tail columns come from the compact [c][2] copy: a quad's four 32-byte reads cover 128
                 // contiguous bytes (no bank conflicts; the strided [c][GS] rows would give 2-way conflicts).
@@ -205,7 +376,11 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
                 for (int j = 0; j < NJ; ++j) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
+#if XR_TRIMER_PRETAIL
+                        const double2 v = (2 * j + e < XR_TRIMER_PRETAIL) ? vpre[(2 * j + e) % XR_TRIMER_PRETAIL] : gt[8 * j + e];
+#else
                         const double2 v = gt[8 * j + e];
+#endif
 #pragma unroll
                         for (int i = 0; i < MI; ++i) {
                             acc[i][j][e] = fma(atail[i][0], v.x, acc[i][j][e]);
@@ -216,19 +391,38 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);      // this warp no longer reads the slot
+            if (PREFETCH && q + 1 < total_tiles) {
+                // gamma tiles do not depend on the work item, so this also runs across item boundaries
+                const int nslot = (int)((q + 1) % SLOTS);
+                mbar_wait(&full[nslot], (uint32_t)((q + 1) / SLOTS) & 1);
+                const double* gn = Gs + (size_t)nslot * CT * GS + (WCOLS * wn + g) * GS + t;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) bnext[j] = gn[j * 8 * GS];
+            }
 
-            if (p.mode == XR_TRIMER_REDUCE) {
+            if (mode == XR_TRIMER_REDUCE) {
 #pragma unroll
                 for (int i = 0; i < MI; ++i)
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
                         if (STREAM_SUM) s1p[j] += acc[i][j][0] + acc[i][j][1];
-                        s2p[j] = fma(acc[i][j][0], acc[i][j][0], s2p[j]);
+                        if (NOSQ)
+                            nosq_bits ^= __double2hiint(acc[i][j][0]) ^ __double2hiint(acc[i][j][1]);
+                        else
+                            s2p[j] = fma(acc[i][j][0], acc[i][j][0], s2p[j]);
                     }
+                if (!NOSQ) {
 #pragma unroll
-                for (int i = 0; i < MI; ++i)
+                    for (int i = 0; i < MI; ++i)
 #pragma unroll
-                    for (int j = 0; j < NJ; ++j) s2p[j] = fma(acc[i][j][1], acc[i][j][1], s2p[j]);
+                        for (int j = 0; j < NJ; ++j) {
+#if XR_TRIMER_CHAINS16
+                            s1p[j] = fma(acc[i][j][1], acc[i][j][1], s1p[j]);      // (s1p is free when the sum is not streamed)
+#else
+                            s2p[j] = fma(acc[i][j][1], acc[i][j][1], s2p[j]);
+#endif
+                        }
+                }
             } else {
                 const int64_t c_base = (int64_t)ct * CT + WCOLS * wn + 2 * t;
 #pragma unroll
@@ -248,11 +442,15 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
         }
     }
 
-    if (p.mode == XR_TRIMER_REDUCE) {
-        double s1 = 0.0, s2 = 0.0;
+    if (mode == XR_TRIMER_REDUCE) {
+        double s1 = 0.0, s2 = NOSQ ? (double)nosq_bits : 0.0;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
+#if XR_TRIMER_CHAINS16
+            s2 += s1p[j];
+#else
             s1 += s1p[j];
+#endif
             s2 += s2p[j];
         }
 #pragma unroll
@@ -371,8 +569,15 @@ int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbet
     p.gammaP = gammaP;
     p.gammaT = gammaT;
     p.partials = partials;
+    // bulk TMA needs 16-byte aligned sources: every W row is, when the base is and ldw is even (build_H pads ldw to even)
+    p.staged = Cfg::STAGE && (reinterpret_cast<uintptr_t>(p.W) % 16 == 0) && (p.ldw % 2 == 0);
 
-    auto kernel = trimer_stream_kernel<KS, TAIL, WN>;
+#if XR_TRIMER_MODE_T
+    auto kernel = p.mode == XR_TRIMER_REDUCE ? trimer_stream_kernel<KS, TAIL, WN, XR_TRIMER_REDUCE>
+                                             : trimer_stream_kernel<KS, TAIL, WN, XR_TRIMER_MATERIALIZE>;
+#else
+    auto kernel = trimer_stream_kernel<KS, TAIL, WN, -1>;
+#endif
     XR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     kernel<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(p);
     XR_CUDA(cudaGetLastError());
@@ -432,6 +637,9 @@ extern "C" int xr_trimer_stream(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int6
     if (n <= 8) return launch_trimer<2, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
     // (WN = 3, i.e. 12 consumer warps with 32x32 warp tiles, was measured too: 29.1 vs 29.9 TFLOP/s for WN = 2 at
     //  n = 18 on B200 -- the kernel is bound by its DMMA:DFMA instruction mix, not by warp-level latency hiding)
+#if XR_TRIMER_DIAG16
+    if (n == 16) return launch_trimer<4, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+#endif
     if (n == 18) return launch_trimer<4, 2>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
     if (n <= 20) return launch_trimer<5, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
     return launch_trimer<12, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);

@@ -9,7 +9,8 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libxr_b200.so")
+# XR_B200_LIB: load another BUILD of the same library (tools/trimer_variants.py compiles kernel variants side by side)
+LIB_PATH = os.environ.get("XR_B200_LIB") or os.path.join(HERE, "libxr_b200.so")
 HEADER_PATH = os.path.join(HERE, "..", "include", "xr_b200.h")
 
 _i64 = ctypes.c_int64

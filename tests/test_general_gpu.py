@@ -75,31 +75,45 @@ def test_gemm_scatter_offset_tables(dev):
     _close(dev.download(dC), ref, 1e-13)
 
 
-@pytest.mark.parametrize("n,Pa,Pb,Pc", [(5, 3, 4, 7), (6, 20, 33, 130), (18, 9, 17, 257), (18, 40, 50, 1000), (48, 5, 18, 140)])
-def test_trimer_stream(dev, n, Pa, Pb, Pc):
+@pytest.mark.parametrize("n,Pa,Pb,Pc,pad", [(5, 3, 4, 7, 0), (6, 20, 33, 130, 0), (18, 9, 17, 257, 0), (18, 40, 50, 1000, 0),
+                                            (48, 5, 18, 140, 0),
+                                            # several work items per persistent CTA (items = ceil(Pa/8)*ceil(Pb/16) > 148), with
+                                            # fewer gamma tiles per item than ring slots (1, 3) and more (6): the producer
+                                            # stages item i+1's W/beta rows while item i streams
+                                            (6, 400, 200, 40, 0), (18, 130, 330, 300, 0), (18, 70, 530, 700, 0),
+                                            # odd leading dimension of W: rows are not 16-byte aligned, no TMA staging
+                                            (18, 130, 330, 300, 1), (6, 400, 200, 40, 3), (20, 9, 40, 129, 0), (48, 30, 100, 140, 0)])
+def test_trimer_stream(dev, n, Pa, Pb, Pc, pad):
     from qodeapplications_b200 import lib as xr
     rng = numpy.random.default_rng(n + Pa + Pb + Pc)
-    W, beta, gamma = rng.standard_normal((Pa, n * n)), rng.standard_normal((Pb, n)), rng.standard_normal((Pc, n))
+    ldw = n * n + pad
+    Wp = rng.standard_normal((Pa, ldw))
+    W, beta, gamma = numpy.ascontiguousarray(Wp[:, :n * n]), rng.standard_normal((Pb, n)), rng.standard_normal((Pc, n))
     ref = -1.5 * numpy.einsum("ars,br,cs->abc", W.reshape(Pa, n, n), beta, gamma, optimize=True)
-    dW, dB, dG = dev.upload(W), dev.upload(beta), dev.upload(gamma)
+    dW, dB, dG = dev.upload(Wp), dev.upload(beta), dev.upload(gamma)
     # materialise with a permuted layout [c, a, b]
     offA = numpy.arange(Pa, dtype=numpy.int64) * Pb
     offB = numpy.arange(Pb, dtype=numpy.int64)
     offC = numpy.arange(Pc, dtype=numpy.int64) * (Pa * Pb)
     dC = dev.zeros((Pc, Pa, Pb))
-    dev.ctx.trimer_stream(n, Pa, Pb, Pc, -1.5, dW, n * n, dB, n, dG, n, 0, Pa, xr.TRIMER_MATERIALIZE, None, dC,
+    dev.ctx.trimer_stream(n, Pa, Pb, Pc, -1.5, dW, ldw, dB, n, dG, n, 0, Pa, xr.TRIMER_MATERIALIZE, None, dC,
                           dev.upload(offA, numpy.int64), dev.upload(offB, numpy.int64), dev.upload(offC, numpy.int64))
     _close(dev.download(dC), ref.transpose(2, 0, 1), 1e-13 * n)
-    # reduce, in two shards
+    # reduce, in two shards (the second one starts at an a that is not a multiple of the 8-row item height)
     mom = dev.zeros((2,))
-    split = Pa // 2
+    split = Pa // 2 + (1 if Pa > 20 else 0)
     for lo, hi in ((0, split), (split, Pa)):
-        dev.ctx.trimer_stream(n, Pa, Pb, Pc, -1.5, dW, n * n, dB, n, dG, n, lo, hi, xr.TRIMER_REDUCE, mom, None, None, None, None)
+        dev.ctx.trimer_stream(n, Pa, Pb, Pc, -1.5, dW, ldw, dB, n, dG, n, lo, hi, xr.TRIMER_REDUCE, mom, None, None, None, None)
     got = dev.download(mom)
     assert abs(got[0] - ref.sum()) <= 1e-11 * numpy.abs(ref).sum()
     assert abs(got[1] - (ref ** 2).sum()) <= 1e-12 * (ref ** 2).sum()
     total, sumsq = go.trimer_class_moments(W.reshape(Pa, n, n), beta, gamma)
     assert abs(got[1] - 2.25 * sumsq) <= 1e-11 * 2.25 * sumsq
+    # bit-reproducible: the same launch twice gives the same moments
+    mom2 = dev.zeros((2,))
+    for lo, hi in ((0, split), (split, Pa)):
+        dev.ctx.trimer_stream(n, Pa, Pb, Pc, -1.5, dW, ldw, dB, n, dG, n, lo, hi, xr.TRIMER_REDUCE, mom2, None, None, None, None)
+    assert numpy.array_equal(dev.download(mom2), got)
 
 
 def test_legacy_scalar_abi(dev):
