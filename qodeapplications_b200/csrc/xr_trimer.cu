@@ -35,43 +35,15 @@ constexpr int TA = 8, TB = 16, ROWS = TA * TB;
 #define XR_TRIMER_STREAM_SUM 0
 #endif
 constexpr bool STREAM_SUM = XR_TRIMER_STREAM_SUM != 0;
-// Development switches (tools/trimer_variants.py builds one library per setting and times them on the GPU):
-//   XR_TRIMER_PREFETCH  wait for the NEXT gamma tile and load its first B fragments before the moment/store epilogue of the
-//                       current one, so the barrier poll and the shared-memory latency sit under FP64 work
-//   XR_TRIMER_MODE_T    compile the consumer (reduce / materialize) in as a template parameter instead of a uniform branch
-#ifndef XR_TRIMER_PREFETCH
-#define XR_TRIMER_PREFETCH 0
-#endif
-#ifndef XR_TRIMER_MODE_T
-#define XR_TRIMER_MODE_T 0
-#endif
-//   XR_TRIMER_SEP_TAIL  keep the DFMA k-tail in its own basic block (a run-time-true branch), so ptxas cannot interleave it
-//                       with the last DMMAs of the tile
-//   XR_TRIMER_TAIL_FIRST  start every accumulator from the DFMA k-tail and let the DMMA k-steps accumulate on top
-//   XR_TRIMER_NOSQ / XR_TRIMER_DIAG16  timing diagnostics only (wrong moments / n = 16 without a tail)
+// XR_TRIMER_SEP_TAIL keeps the DFMA k-tail of a tile in its own basic block (behind a branch that is always taken when
+// TAIL > 0), so that ptxas does not interleave the 64-128 DFMAs with the last DMMAs of the tile: interleaved, the two
+// instruction kinds contend for the one FP64 pipe in an order that leaves issue slots empty (31.5 -> 32.9 TFLOP/s at
+// n = 18 on B200).  tools/trimer_variants.py builds one library per -D setting and times them in one GPU call; what was
+// tried and rejected is listed in DESIGN.md (trimer kernel, "variants measured").
 #ifndef XR_TRIMER_SEP_TAIL
 #define XR_TRIMER_SEP_TAIL 1
 #endif
-#ifndef XR_TRIMER_TAIL_FIRST
-#define XR_TRIMER_TAIL_FIRST 0
-#endif
-#ifndef XR_TRIMER_NOSQ
-#define XR_TRIMER_NOSQ 0
-#endif
-#ifndef XR_TRIMER_DIAG16
-#define XR_TRIMER_DIAG16 0
-#endif
-#ifndef XR_TRIMER_SYNC
-#define XR_TRIMER_SYNC 0
-#endif
-#ifndef XR_TRIMER_PRETAIL
-#define XR_TRIMER_PRETAIL 0
-#endif
-#ifndef XR_TRIMER_CHAINS16
-#define XR_TRIMER_CHAINS16 0
-#endif
-constexpr bool PREFETCH = XR_TRIMER_PREFETCH != 0;
-constexpr bool SEP_TAIL = XR_TRIMER_SEP_TAIL != 0, TAIL_FIRST = XR_TRIMER_TAIL_FIRST != 0, NOSQ = XR_TRIMER_NOSQ != 0;
+constexpr bool SEP_TAIL = XR_TRIMER_SEP_TAIL != 0;
 
 struct TrimerParams {
     int n;
@@ -167,10 +139,10 @@ __device__ __forceinline__ void build_item_X(double* __restrict__ Xs, const doub
     }
 }
 
-template <int KS, int TAIL, int WN, int MODE>      // MODE < 0: the consumer is chosen at run time (p.mode)
+template <int KS, int TAIL, int WN>
 __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_stream_kernel(const TrimerParams p) {
     using Cfg = TrimerCfg<KS, TAIL, WN>;
-    const int mode = MODE < 0 ? p.mode : MODE;
+    const int mode = p.mode;
     constexpr int KP = Cfg::KP, GS = Cfg::GS, SLOTS = Cfg::SLOTS, CT = Cfg::CT;
     constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS, CONSUMER_THREADS = Cfg::CONSUMER_THREADS;
     constexpr bool AREG = Cfg::AREG, STAGE = Cfg::STAGE;
@@ -268,8 +240,6 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
     const int n = p.n;
     int64_t q = 0;
     uint32_t item_parity = 0;
-    double bnext[PREFETCH ? NJ : 1];     // first-k-step B fragments of the next gamma tile
-    int nosq_bits = 0;
 
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int64_t a0 = p.a_begin + (item / p.tiles_b) * TA;
@@ -307,67 +277,27 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
             const int slot = (int)(q % SLOTS);
             const double* gtile = Gs + (size_t)slot * CT * GS;
             const double* gs = gtile + (WCOLS * wn + g) * GS + t;
-#if XR_TRIMER_SYNC == 1
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + (warp & 3)) : "memory");     // the two warps of one scheduler start the tile together
-#elif XR_TRIMER_SYNC == 2
-            consumer_barrier<CONSUMER_THREADS>();
-#endif
-            if (!PREFETCH || q == 0) {
-                mbar_wait(&full[slot], (uint32_t)(q / SLOTS) & 1);
-                if (PREFETCH) {
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) bnext[j] = gs[j * 8 * GS];
-                }
-            }
+            mbar_wait(&full[slot], (uint32_t)(q / SLOTS) & 1);
 
             double acc[MI][NJ][2];
-            if (TAIL && TAIL_FIRST && SEP_TAIL && p.n <= 4 * KS) {      // never taken (TAIL > 0 means n > 4*KS): keeps the tail a basic block
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-            } else if (TAIL && TAIL_FIRST) {
-                const double2* gt = reinterpret_cast<const double2*>(Gt + (size_t)slot * CT * 2) + WCOLS * wn + 2 * t;
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const double2 v = gt[8 * j + e];
-#pragma unroll
-                        for (int i = 0; i < MI; ++i) {
-                            acc[i][j][e] = atail[i][0] * v.x;
-                            if (TAIL == 2) acc[i][j][e] = fma(atail[i][TAIL - 1], v.y, acc[i][j][e]);
-                        }
-                    }
-                }
-            }
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 double b[NJ];
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) b[j] = (PREFETCH && ks == 0) ? bnext[j] : gs[j * 8 * GS + 4 * ks];
+                for (int j = 0; j < NJ; ++j) b[j] = gs[j * 8 * GS + 4 * ks];
 #pragma unroll
                 for (int i = 0; i < MI; ++i) {
                     const double a = AREG ? areg[AREG ? i : 0][AREG ? ks : 0] : xs[i * 8 * GS + 4 * ks];
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
-                        if (ks == 0 && !(TAIL && TAIL_FIRST))
+                        if (ks == 0)
                             dmma_m8n8k4_zero(acc[i][j][0], acc[i][j][1], a, b[j]);
                         else
                             dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a, b[j]);
                     }
                 }
             }
-#if XR_TRIMER_PRETAIL
-            // the first tail operands are fetched in the DMMA block, so the DFMA block does not start on a shared-memory round trip
-            double2 vpre[XR_TRIMER_PRETAIL];
-            if (TAIL && !TAIL_FIRST) {
-                const double2* gtp = reinterpret_cast<const double2*>(Gt + (size_t)slot * CT * 2) + WCOLS * wn + 2 * t;
-#pragma unroll
-                for (int u = 0; u < XR_TRIMER_PRETAIL; ++u) vpre[u] = gtp[8 * (u >> 1) + (u & 1)];
-            }
-#endif
-            if (TAIL && !TAIL_FIRST && (!SEP_TAIL || p.n > 4 * KS)) {
+            if (TAIL && (!SEP_TAIL || p.n > 4 * KS)) {      // always taken when TAIL > 0 (n > 4*KS): see SEP_TAIL
                 // leftover k (n - 4*KS <= 2) on the accumulator layout: lane owns rows 8i+g, columns 8j+2t+{0,1}.
                 // The tail columns come from the compact [c][2] copy: a quad's four 32-byte reads cover 128
                 // contiguous bytes (no bank conflicts; the strided [c][GS] rows would give 2-way conflicts).
@@ -376,11 +306,7 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
                 for (int j = 0; j < NJ; ++j) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-#if XR_TRIMER_PRETAIL
-                        const double2 v = (2 * j + e < XR_TRIMER_PRETAIL) ? vpre[(2 * j + e) % XR_TRIMER_PRETAIL] : gt[8 * j + e];
-#else
                         const double2 v = gt[8 * j + e];
-#endif
 #pragma unroll
                         for (int i = 0; i < MI; ++i) {
                             acc[i][j][e] = fma(atail[i][0], v.x, acc[i][j][e]);
@@ -391,38 +317,18 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);      // this warp no longer reads the slot
-            if (PREFETCH && q + 1 < total_tiles) {
-                // gamma tiles do not depend on the work item, so this also runs across item boundaries
-                const int nslot = (int)((q + 1) % SLOTS);
-                mbar_wait(&full[nslot], (uint32_t)((q + 1) / SLOTS) & 1);
-                const double* gn = Gs + (size_t)nslot * CT * GS + (WCOLS * wn + g) * GS + t;
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) bnext[j] = gn[j * 8 * GS];
-            }
-
             if (mode == XR_TRIMER_REDUCE) {
 #pragma unroll
                 for (int i = 0; i < MI; ++i)
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
                         if (STREAM_SUM) s1p[j] += acc[i][j][0] + acc[i][j][1];
-                        if (NOSQ)
-                            nosq_bits ^= __double2hiint(acc[i][j][0]) ^ __double2hiint(acc[i][j][1]);
-                        else
-                            s2p[j] = fma(acc[i][j][0], acc[i][j][0], s2p[j]);
+                        s2p[j] = fma(acc[i][j][0], acc[i][j][0], s2p[j]);
                     }
-                if (!NOSQ) {
 #pragma unroll
-                    for (int i = 0; i < MI; ++i)
+                for (int i = 0; i < MI; ++i)
 #pragma unroll
-                        for (int j = 0; j < NJ; ++j) {
-#if XR_TRIMER_CHAINS16
-                            s1p[j] = fma(acc[i][j][1], acc[i][j][1], s1p[j]);      // (s1p is free when the sum is not streamed)
-#else
-                            s2p[j] = fma(acc[i][j][1], acc[i][j][1], s2p[j]);
-#endif
-                        }
-                }
+                    for (int j = 0; j < NJ; ++j) s2p[j] = fma(acc[i][j][1], acc[i][j][1], s2p[j]);
             } else {
                 const int64_t c_base = (int64_t)ct * CT + WCOLS * wn + 2 * t;
 #pragma unroll
@@ -443,14 +349,10 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
     }
 
     if (mode == XR_TRIMER_REDUCE) {
-        double s1 = 0.0, s2 = NOSQ ? (double)nosq_bits : 0.0;
+        double s1 = 0.0, s2 = 0.0;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-#if XR_TRIMER_CHAINS16
-            s2 += s1p[j];
-#else
             s1 += s1p[j];
-#endif
             s2 += s2p[j];
         }
 #pragma unroll
@@ -572,12 +474,7 @@ int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbet
     // bulk TMA needs 16-byte aligned sources: every W row is, when the base is and ldw is even (build_H pads ldw to even)
     p.staged = Cfg::STAGE && (reinterpret_cast<uintptr_t>(p.W) % 16 == 0) && (p.ldw % 2 == 0);
 
-#if XR_TRIMER_MODE_T
-    auto kernel = p.mode == XR_TRIMER_REDUCE ? trimer_stream_kernel<KS, TAIL, WN, XR_TRIMER_REDUCE>
-                                             : trimer_stream_kernel<KS, TAIL, WN, XR_TRIMER_MATERIALIZE>;
-#else
-    auto kernel = trimer_stream_kernel<KS, TAIL, WN, -1>;
-#endif
+    auto kernel = trimer_stream_kernel<KS, TAIL, WN>;
     XR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     kernel<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(p);
     XR_CUDA(cudaGetLastError());
@@ -637,9 +534,6 @@ extern "C" int xr_trimer_stream(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int6
     if (n <= 8) return launch_trimer<2, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
     // (WN = 3, i.e. 12 consumer warps with 32x32 warp tiles, was measured too: 29.1 vs 29.9 TFLOP/s for WN = 2 at
     //  n = 18 on B200 -- the kernel is bound by its DMMA:DFMA instruction mix, not by warp-level latency hiding)
-#if XR_TRIMER_DIAG16
-    if (n == 16) return launch_trimer<4, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
-#endif
     if (n == 18) return launch_trimer<4, 2>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
     if (n <= 20) return launch_trimer<5, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
     return launch_trimer<12, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);

@@ -3,7 +3,8 @@
     python tools/trimer_variants.py build            # here (nvcc cross-compiles)
     python tools/trimer_variants.py run [Pa]         # on the GPU box: parity test + timing of every variant
 
-Variants are compile-time switches of csrc/xr_trimer.cu (see its header); "head" is the file as committed at HEAD.
+Variants are the compile-time switches of csrc/xr_trimer.cu (see its header).  The switches that lost on B200
+(profiles/r01q_trimer_variants.jsonl) were removed from the kernel again.
 """
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,12 +13,9 @@ from qodeapplications_b200 import build as xr_build
 
 OUT = os.path.join(ROOT, "tools", "variants")
 VARIANTS = {
-    "sep": [],
-    "sep_pairsync": ["-DXR_TRIMER_SYNC=1"],
-    "sep_allsync": ["-DXR_TRIMER_SYNC=2"],
-    "sep_pretail4": ["-DXR_TRIMER_PRETAIL=4"],
-    "sep_pretail8": ["-DXR_TRIMER_PRETAIL=8"],
-    "sep_chains16": ["-DXR_TRIMER_CHAINS16=1"],
+    "sep": [],                                  # shipped: DFMA k-tail in its own basic block
+    "nosep": ["-DXR_TRIMER_SEP_TAIL=0"],        # ptxas free to interleave the tail with the DMMAs
+    "stream_sum": ["-DXR_TRIMER_STREAM_SUM=1"],  # first moment accumulated element by element as well
 }
 SHAPES = {}
 ONLY_TRIMER_CU = True     # the variants differ in xr_trimer.cu only: compile that file per variant, link the rest once
