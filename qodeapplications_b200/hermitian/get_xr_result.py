@@ -108,3 +108,29 @@ def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False
     else:
         raise NotImplementedError("xr order %r is not implemented" % (xr_order,))
     return H1, H2
+
+
+def get_xr_S(ints, dens, xr_order, monomer_charges, device=None):
+    """Dimer overlap matrix of the orbital solver -- hermitian-XRCC/get_xr_result.py:357-422 (called at
+    StateSpaceOptimizer/orbital_solver.py:512,517), same arguments.  xr_order 0: the identity diagram; xr_order 1: the
+    first-order ``s01`` diagram alone (:375-391); anything else raises NotImplementedError like the reference (:393).
+
+    Returned in the (global state of fragment 0, global state of fragment 1) ordering of get_xr_H.  The reference MEANS to
+    return exactly this, but its reorder loop stores into the diagram dictionary (``D.S2[i,j] = ...``, :421) and hands back
+    the zero matrix it allocated; the matrix it built up to that point is pinned in tests/golden/hermitian_toy_S.npz.
+    """
+    symm_ints = ints[0]
+    if xr_order == 0:
+        active = {0: D.S0[0], 2: []}
+    elif xr_order == 1:
+        active = {0: [], 2: D.S2[1]}
+    else:
+        raise NotImplementedError("only xr in zeroth and first order are implemented")
+    dev = device or default_device()
+    store, contractor = DeviceStore(dev), Contractor(dev)
+    precon_timer = timer()
+    contract_cache = precontract(dens, symm_ints.S, precon_timer, store=store, contractor=contractor)
+    S_blocks = diagrammatic_expansion.blocks(densities=dens, integrals=symm_ints.S, diagrams=S_diagrams, contract_cache=contract_cache,
+                                             timings=timer(), precon_timings=precon_timer)
+    all_dimer_charges = [(c0, c1) for c0 in monomer_charges[0] for c1 in monomer_charges[1]]
+    return XR_term.dimer_matrix(S_blocks, active, (0, 1), all_dimer_charges, timer(), ordering="final")

@@ -81,6 +81,17 @@ def test_get_xr_H_matches_reference_golden(dev, order, ops):
     _close(H2, g["H2"], 1e-9 if order else 1e-10)
 
 
+@pytest.mark.parametrize("order", [0, 1])
+def test_get_xr_S_matches_reference_golden(dev, order):
+    """get_xr_S (get_xr_result.py:357-422, orbital solver): golden = the reference's own charge-blocked matrix"""
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_S
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_S.npz"))
+    system = synth.make_system("toy", ops=synth.OPS_ORDER1, with_bior=True)
+    charges = system["charges"]
+    S2 = get_xr_S((system["symm"], system["bior"], system["nuc"]), system["densities"][:2], order, [charges, charges], device=dev)
+    _close(S2, ho.reorder(g["S2_blocked_order%d" % order], system["densities"], [charges, charges]))
+
+
 def test_cfg1_order0_against_oracle(dev):
     """Be2 / 6-31G shapes (n = 18, N = 11/4/8): get_xr_H(order 0) against the NumPy oracle"""
     from qodeapplications_b200.hermitian.get_xr_result import get_xr_H

@@ -115,6 +115,24 @@ def test_hermitian_get_xr_H_host_logic(order, ops):
     _close(H2, g["H2"], 1e-9 if order else 1e-10)
 
 
+@pytest.mark.parametrize("order", [0, 1])
+def test_hermitian_get_xr_S_host_logic(order):
+    """get_xr_S (get_xr_result.py:357-422): the overlap matrix the reference builds (charge-blocked, from its own modules)
+    in the final ordering it meant to return"""
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_S
+    from oracle import hermitian_oracle as ho
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_S.npz"))
+    system = synth.make_system("toy", ops=synth.OPS_ORDER1, with_bior=True)
+    charges = system["charges"]
+    S2 = get_xr_S((system["symm"], system["bior"], system["nuc"]), system["densities"][:2], order, [charges, charges],
+                  device=FakeDevice())
+    _close(S2, ho.reorder(g["S2_blocked_order%d" % order], system["densities"], [charges, charges]))
+    if order == 0:
+        assert numpy.array_equal(S2, numpy.eye(S2.shape[0]))
+    with pytest.raises(NotImplementedError):
+        get_xr_S((system["symm"], system["bior"], system["nuc"]), system["densities"][:2], 2, [charges, charges], device=FakeDevice())
+
+
 def test_hermitian_dimer_matrix_blocked_ordering(toy1):
     """XR_term.dimer_matrix keeps the reference's charge-blocked ordering by default"""
     from qodeapplications_b200.hermitian import XR_term
