@@ -78,6 +78,10 @@ enum xr_status {
     XR_ERR_UNSUPPORTED = -4
 };
 
+/* Conventions of every block-level call below: returns an xr_status; asynchronous on the context's stream; a call whose
+ * output has a zero extent (an empty charge sector: M, N, rows, count, Pa.. = 0, or an empty a range) is a no-op that
+ * returns XR_OK without launching anything, and its buffers may then be NULL. */
+
 /* Thread-local message of the last failure in the calling thread. */
 const char* xr_last_error(void);
 

@@ -219,7 +219,7 @@ __global__ void permute_copy_kernel(double* __restrict__ dst, const double* __re
 
 extern "C" int xr_permute_copy(xr_ctx* ctx, double* dst, const double* src, int nd, const int64_t* shape,
                                const int64_t* src_strides, double alpha) {
-    XR_REQUIRE(ctx && dst && src && shape && src_strides, "xr_permute_copy: null argument");
+    XR_REQUIRE(ctx && shape && src_strides, "xr_permute_copy: null argument");
     XR_REQUIRE(nd >= 1 && nd <= 12, "xr_permute_copy: nd=%d unsupported (1..12)", nd);
     PermuteParams p{};
     p.nd = nd;
@@ -230,7 +230,8 @@ extern "C" int xr_permute_copy(xr_ctx* ctx, double* dst, const double* src, int 
         p.stride[d] = src_strides[d];
         p.total *= shape[d];
     }
-    if (p.total == 0) return XR_OK;
+    if (p.total == 0) return XR_OK;      // an empty charge sector: nothing to copy, and the buffers may be null
+    XR_REQUIRE(dst && src, "xr_permute_copy: null buffer");
     int64_t blocks = (p.total + 255) / 256;
     int64_t cap = (int64_t)ctx->sm_count * 32;
     if (blocks > cap) blocks = cap;

@@ -344,3 +344,39 @@ def test_streamed_dimer_from_device_resident_bra_slabs(dev):
         with pytest.raises(ValueError):
             eng.H2_device(0, 1)                                     # needs bra states this engine does not hold
     assert numpy.allclose(acc, whole, rtol=1e-12, atol=1e-12 * numpy.abs(whole).max())
+
+
+RAGGED = [{0: 2, +1: 1, -1: 0}, {0: 1, +1: 1, -1: 1}, {0: 3, +1: 0, -1: 0}, {0: 2, +1: 0, -1: 2}, {0: 1}]
+
+
+@pytest.mark.parametrize("n_states", RAGGED, ids=lambda d: "-".join("%+d:%d" % kv for kv in d.items()))
+def test_ragged_and_empty_charge_sectors(dev, n_states):
+    """charge sectors with no states, one state, or a missing charge: zero-size factor matrices reach the library"""
+    system = synth.make_system(n_frag=3, n_orb=4, n_states=n_states, seed=77)
+    fr, ints, nuc = system["fragments"], system["symm"], system["nuc"]
+    eng = _engine(system, dev)
+    for m in range(3):
+        _close(eng.H1(m), go.block_monomer(fr, ints, nuc, m), 1e-12)
+    for m1, m2 in itertools.combinations(range(3), 2):
+        _close(eng.H2(m1, m2), go.block_dimer(fr, ints, nuc, m1, m2), 1e-12)
+    ref = go.block_trimer(fr, ints, (0, 1, 2))
+    _close(eng.H3(0, 1, 2), ref, 1e-12)
+    s, q = eng.H3_moments(0, 1, 2)
+    assert abs(q - (ref ** 2).sum()) <= 1e-10 * (ref ** 2).sum() and abs(s - ref.sum()) <= 1e-10 * max(numpy.abs(ref).sum(), 1.0)
+
+
+def test_zero_size_arguments_are_no_ops(dev):
+    """every block-level entry point returns XR_OK without touching memory when an extent is zero (null buffers allowed)"""
+    from qodeapplications_b200 import lib as xr
+    c = dev.ctx
+    before = c.launch_count()
+    c.gemm_scatter(0, 5, 3, 1.0, None, 3, None, 3, None, None, 5)
+    c.gemm_scatter(5, 0, 3, 1.0, None, 3, None, 3, None, None, 1)
+    c.gemm_reduce(0, 4, 2, 1.0, None, 2, None, 2, None)
+    c.copy2d_scaled(None, 4, None, 4, 0, 4)
+    c.permute_copy(None, None, (3, 0, 2), (0, 2, 1))
+    c.scatter_const(None, None, 0, 1.0)
+    c.trimer_stream(4, 3, 0, 5, 1.0, None, 16, None, 4, None, 4, 0, 3, xr.TRIMER_REDUCE, None)
+    c.trimer_stream(4, 3, 2, 5, 1.0, None, 16, None, 4, None, 4, 2, 2, xr.TRIMER_REDUCE, None)
+    c.embed_add(None, None, 1, 0, 0, 1, None, None)
+    assert c.launch_count() == before

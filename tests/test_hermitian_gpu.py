@@ -180,3 +180,18 @@ def test_det_variants_match_reference_golden(dev, which):
     _close(H1[0], g["H1_0"])
     _close(H1[1], g["H1_1"])
     _close(H2, g["H2"])
+
+
+@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1)])
+@pytest.mark.parametrize("n_states", [{0: 2, +1: 1, -1: 0}, {0: 1, +1: 1, -1: 1}, {0: 2, +1: 0, -1: 2}],
+                         ids=lambda d: "-".join("%+d:%d" % kv for kv in d.items()))
+def test_ragged_and_empty_charge_sectors(dev, order, ops, n_states):
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    system = synth.make_system(n_frag=2, n_orb=4, n_states=n_states, seed=78, ops=ops, with_bior=True)
+    ch = system["charges"]
+    args = (system["densities"][:2], order, [ch, ch])
+    H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), *args, device=dev)
+    R1, R2 = ho.get_xr_H(system["symm"], system["bior"], *args)
+    _close(H1[0], R1[0])
+    _close(H1[1], R1[1])
+    _close(H2, R2, 1e-9 if order else 1e-10)

@@ -217,3 +217,39 @@ def test_xr_tensor_sums_of_products():
     assert numpy.allclose(XR_tensor.raw(expr, engine), want, rtol=1e-13, atol=1e-13)
     with pytest.raises(ValueError):
         XR_tensor.raw(A(0, 1, 2) + B(0, 1), engine)
+
+
+RAGGED = [{0: 2, +1: 1, -1: 0}, {0: 1, +1: 1, -1: 1}, {0: 3, +1: 0, -1: 0}, {0: 2, +1: 0, -1: 2}, {0: 1}]
+
+
+@pytest.mark.parametrize("n_states", RAGGED, ids=lambda d: "-".join("%+d:%d" % kv for kv in d.items()))
+def test_general_ragged_and_empty_sectors_host_logic(n_states):
+    """charge sectors with no states, one state, or a missing charge: every H1/H2/H3 element against the element-level port"""
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    from oracle import general_oracle as go
+    system = synth.make_system(n_frag=3, n_orb=4, n_states=n_states, seed=77)
+    fr, ints, nuc = system["fragments"], system["symm"], system["nuc"]
+    eng = build_matrix_elements(fr, ints, nuc, device=FakeDevice())
+    for m in range(3):
+        _close(eng.H1(m), go.block_monomer(fr, ints, nuc, m), 1e-12)
+    for m1, m2 in itertools.combinations(range(3), 2):
+        _close(eng.H2(m1, m2), go.block_dimer(fr, ints, nuc, m1, m2), 1e-12)
+    ref = go.block_trimer(fr, ints, (0, 1, 2))
+    _close(eng.H3(0, 1, 2), ref, 1e-12)
+    s, q = eng.H3_moments(0, 1, 2)
+    assert abs(q - (ref ** 2).sum()) <= 1e-10 * (ref ** 2).sum() and abs(s - ref.sum()) <= 1e-10 * max(numpy.abs(ref).sum(), 1.0)
+
+
+@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1)])
+@pytest.mark.parametrize("n_states", RAGGED[:2] + RAGGED[3:4], ids=lambda d: "-".join("%+d:%d" % kv for kv in d.items()))
+def test_hermitian_ragged_and_empty_sectors_host_logic(order, ops, n_states):
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    from oracle import hermitian_oracle as ho
+    system = synth.make_system(n_frag=2, n_orb=4, n_states=n_states, seed=78, ops=ops, with_bior=True)
+    ch = system["charges"]
+    args = (system["densities"][:2], order, [ch, ch])
+    H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), *args, device=FakeDevice())
+    R1, R2 = ho.get_xr_H(system["symm"], system["bior"], *args)
+    _close(H1[0], R1[0])
+    _close(H1[1], R1[1])
+    _close(H2, R2, 1e-9 if order else 1e-10)
