@@ -377,57 +377,85 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
     }
 }
 
-// sum of all T[a,b,c], a in [a_begin, a_end), from the factor sums (one block; fixed assignment and trees: reproducible)
-__global__ void __launch_bounds__(256) trimer_sum_kernel(int n, int64_t Pb, int64_t Pc, double alpha, const double* __restrict__ W,
-                                                         int64_t ldw, const double* __restrict__ beta, int64_t ldbeta,
-                                                         const double* __restrict__ gamma, int64_t ldgamma, int64_t a_begin,
-                                                         int64_t a_end, double* __restrict__ moments) {
-    __shared__ double colsum[2][48];
-    __shared__ double outer[48 * 48];
-    __shared__ double red[256];
-    const int tid = threadIdx.x;
-    for (int which = 0; which < 2; ++which) {
-        const double* M = which ? gamma : beta;
-        const int64_t rows = which ? Pc : Pb, ld = which ? ldgamma : ldbeta;
-        for (int c = 0; c < n; ++c) {
-            double s = 0.0;
-            for (int64_t r = tid; r < rows; r += 256) s += M[r * ld + c];
-            red[tid] = s;
-            __syncthreads();
-            for (int o = 128; o > 0; o >>= 1) {
-                if (tid < o) red[tid] += red[tid + o];
-                __syncthreads();
-            }
-            if (tid == 0) colsum[which][c] = red[0];
-            __syncthreads();
+// First moment from the factor sums:  sum_{a in [a_begin,a_end), b, c} T[a,b,c] = alpha * sum_a sum_{rs} W[a,rs] * bsum[r] * gsum[s],
+// bsum = column sums of beta, gsum = column sums of gamma.  Every assignment of work to threads and every reduction tree
+// below is fixed by the sizes alone, so the result is bit-reproducible.
+constexpr int SUM_THREADS = 256, SUM_WARPS = SUM_THREADS / 32, MAX_N = 48;
+
+// block 0: bsum, block 1: gsum -> colsum[which][0..n).  A thread owns rows tid, tid + 256, ... and adds up whole rows.
+__global__ void __launch_bounds__(SUM_THREADS) trimer_colsum_kernel(int n, int64_t Pb, int64_t Pc, const double* __restrict__ beta,
+                                                                    int64_t ldbeta, const double* __restrict__ gamma, int64_t ldgamma,
+                                                                    double* __restrict__ colsum) {
+    __shared__ double part[SUM_WARPS][MAX_N];
+    const int which = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* M = which ? gamma : beta;
+    const int64_t rows = which ? Pc : Pb, ld = which ? ldgamma : ldbeta;
+    double acc[MAX_N];
+#pragma unroll
+    for (int c = 0; c < MAX_N; ++c) acc[c] = 0.0;
+    for (int64_t r = tid; r < rows; r += SUM_THREADS) {
+        const double* row = M + r * ld;
+#pragma unroll
+        for (int c = 0; c < MAX_N; ++c)
+            if (c < n) acc[c] += row[c];
+    }
+#pragma unroll
+    for (int c = 0; c < MAX_N; ++c) {
+        if (c < n) {
+            double v = acc[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) part[warp][c] = v;
         }
     }
-    for (int e = tid; e < n * n; e += 256) outer[e] = colsum[0][e / n] * colsum[1][e % n];
     __syncthreads();
-    double s = 0.0;
-    for (int64_t a = a_begin + tid; a < a_end; a += 256) {
-        const double* w = W + a * ldw;
-        double d = 0.0;
-        for (int e = 0; e < n * n; ++e) d = fma(w[e], outer[e], d);
-        s += d;
+    if (tid < n) {
+        double v = 0.0;
+        for (int w = 0; w < SUM_WARPS; ++w) v += part[w][tid];
+        colsum[which * MAX_N + tid] = v;
     }
-    red[tid] = s;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (tid < o) red[tid] += red[tid + o];
-        __syncthreads();
-    }
-    if (tid == 0) moments[0] += alpha * red[0];
 }
 
-__global__ void trimer_finalize_kernel(const double* partials, int count, double alpha, double* moments) {
+// block b: rows [a_begin + b*rows_per_block, ...) of W; thread <-> flat index rs (coalesced).  wpart[b] = its share of the sum.
+__global__ void __launch_bounds__(SUM_THREADS) trimer_wsum_kernel(int n, const double* __restrict__ W, int64_t ldw, int64_t a_begin,
+                                                                  int64_t a_end, int64_t rows_per_block,
+                                                                  const double* __restrict__ colsum, double* __restrict__ wpart) {
+    __shared__ double cs[2][MAX_N];
+    __shared__ double red[SUM_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 2 * MAX_N) cs[tid / MAX_N][tid % MAX_N] = (tid % MAX_N) < n ? colsum[tid] : 0.0;
+    __syncthreads();
+    const int64_t r0 = a_begin + (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < a_end ? r0 + rows_per_block : a_end;
+    double d = 0.0;
+    for (int e = tid; e < n * n; e += SUM_THREADS) {
+        const double o = cs[0][e / n] * cs[1][e % n];
+        double colw = 0.0;
+        for (int64_t a = r0; a < r1; ++a) colw += W[a * ldw + e];
+        d = fma(colw, o, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0) red[warp] = d;
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0.0;
+        for (int w = 0; w < SUM_WARPS; ++w) v += red[w];
+        wpart[blockIdx.x] = v;
+    }
+}
+
+// moments += (alpha * (sum of streamed partial sums + sum of wpart), alpha^2 * sum of streamed partial squares)
+__global__ void trimer_finalize_kernel(const double* partials, int count, const double* wpart, int wcount, double alpha,
+                                       double* moments) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double t1 = 0.0, t2 = 0.0;
+        double t1 = 0.0, t2 = 0.0, tw = 0.0;
         for (int i = 0; i < count; ++i) {   // fixed order: bit-reproducible
             t1 += partials[2 * i];
             t2 += partials[2 * i + 1];
         }
-        moments[0] += alpha * t1;
+        for (int i = 0; i < wcount; ++i) tw += wpart[i];
+        moments[0] += alpha * (t1 + tw);
         moments[1] += alpha * alpha * t2;
     }
 }
@@ -451,13 +479,21 @@ int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbet
     const size_t tail_bytes = (size_t)p.c_tiles * CT * 2 * sizeof(double);
     const size_t tail_off = gamma_off + (gamma_bytes + 255) / 256 * 256;
     const size_t part_off = tail_off + (tail_bytes + 255) / 256 * 256;
-    int rc = xr_ensure_scratch(ctx, part_off + (size_t)grid * 2 * sizeof(double) + 256);
+    // first-moment scratch (reduce mode): column sums of beta and gamma, then one partial per trimer_wsum_kernel block
+    const int64_t wblocks_cap = (int64_t)ctx->sm_count * 4;
+    const int64_t rows_per_block = (n_a + wblocks_cap - 1) / wblocks_cap;
+    const int wblocks = (int)((n_a + rows_per_block - 1) / rows_per_block);
+    const size_t colsum_off = part_off + ((size_t)grid * 2 * sizeof(double) + 255) / 256 * 256;
+    const size_t wpart_off = colsum_off + (2 * MAX_N * sizeof(double) + 255) / 256 * 256;
+    int rc = xr_ensure_scratch(ctx, wpart_off + (size_t)wblocks * sizeof(double) + 256);
     if (rc != XR_OK) return rc;
     char* base = static_cast<char*>(ctx->scratch);
     double* betaP = reinterpret_cast<double*>(base + beta_off);
     double* gammaP = reinterpret_cast<double*>(base + gamma_off);
     double* gammaT = reinterpret_cast<double*>(base + tail_off);
     double* partials = reinterpret_cast<double*>(base + part_off);
+    double* colsum = reinterpret_cast<double*>(base + colsum_off);
+    double* wpart = reinterpret_cast<double*>(base + wpart_off);
     XR_CUDA(cudaMemsetAsync(base, 0, part_off, ctx->stream));
     rc = xr_copy2d_scaled(ctx, betaP, Cfg::KP, beta, ldbeta, p.Pb, p.n, 1.0);
     if (rc != XR_OK) return rc;
@@ -480,15 +516,17 @@ int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbet
     XR_CUDA(cudaGetLastError());
     ctx->launches++;
     if (p.mode == XR_TRIMER_REDUCE) {
-        trimer_finalize_kernel<<<1, 32, 0, ctx->stream>>>(partials, grid, p.alpha, moments);
+        if (!STREAM_SUM) {
+            trimer_colsum_kernel<<<2, SUM_THREADS, 0, ctx->stream>>>(p.n, p.Pb, p.Pc, beta, ldbeta, gamma, ldgamma, colsum);
+            XR_CUDA(cudaGetLastError());
+            trimer_wsum_kernel<<<wblocks, SUM_THREADS, 0, ctx->stream>>>(p.n, p.W, p.ldw, p.a_begin, p.a_end, rows_per_block, colsum,
+                                                                         wpart);
+            XR_CUDA(cudaGetLastError());
+            ctx->launches += 2;
+        }
+        trimer_finalize_kernel<<<1, 32, 0, ctx->stream>>>(partials, grid, wpart, STREAM_SUM ? 0 : wblocks, p.alpha, moments);
         XR_CUDA(cudaGetLastError());
         ctx->launches++;
-        if (!STREAM_SUM) {
-            trimer_sum_kernel<<<1, 256, 0, ctx->stream>>>(p.n, p.Pb, p.Pc, p.alpha, p.W, p.ldw, beta, ldbeta, gamma, ldgamma, p.a_begin,
-                                                          p.a_end, moments);
-            XR_CUDA(cudaGetLastError());
-            ctx->launches++;
-        }
     }
     return XR_OK;
 }
@@ -527,14 +565,28 @@ extern "C" int xr_trimer_stream(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int6
     p.offA = offA;
     p.offB = offB;
     p.offC = offC;
-    // k = n is covered by 4*KS DMMA k-steps + TAIL DFMA k (smallest instantiated cover)
-    if (n <= 4) return launch_trimer<1, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
-    if (n == 5) return launch_trimer<1, 1>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
-    if (n == 6) return launch_trimer<1, 2>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
-    if (n <= 8) return launch_trimer<2, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+    // k = n is covered by 4*KS DMMA k-steps + TAIL DFMA k: exactly for n <= 20 (n mod 4 = 3 rounds up to the next DMMA
+    // step), in steps of 4/8 beyond (A fragments then come from shared memory, no tail).
     // (WN = 3, i.e. 12 consumer warps with 32x32 warp tiles, was measured too: 29.1 vs 29.9 TFLOP/s for WN = 2 at
     //  n = 18 on B200 -- the kernel is bound by its DMMA:DFMA instruction mix, not by warp-level latency hiding)
-    if (n == 18) return launch_trimer<4, 2>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
-    if (n <= 20) return launch_trimer<5, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+#define XR_TRIMER_CASE(COND, KS, TAIL) \
+    if (COND) return launch_trimer<KS, TAIL>(ctx, p, beta, ldbeta, gamma, ldgamma, moments)
+    XR_TRIMER_CASE(n <= 4, 1, 0);
+    XR_TRIMER_CASE(n == 5, 1, 1);
+    XR_TRIMER_CASE(n == 6, 1, 2);
+    XR_TRIMER_CASE(n <= 8, 2, 0);
+    XR_TRIMER_CASE(n == 9, 2, 1);
+    XR_TRIMER_CASE(n == 10, 2, 2);
+    XR_TRIMER_CASE(n <= 12, 3, 0);
+    XR_TRIMER_CASE(n == 13, 3, 1);
+    XR_TRIMER_CASE(n == 14, 3, 2);
+    XR_TRIMER_CASE(n <= 16, 4, 0);
+    XR_TRIMER_CASE(n == 17, 4, 1);
+    XR_TRIMER_CASE(n == 18, 4, 2);
+    XR_TRIMER_CASE(n <= 20, 5, 0);
+    XR_TRIMER_CASE(n <= 24, 6, 0);
+    XR_TRIMER_CASE(n <= 32, 8, 0);
+    XR_TRIMER_CASE(n <= 40, 10, 0);
+#undef XR_TRIMER_CASE
     return launch_trimer<12, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
 }

@@ -16,6 +16,11 @@ Extra keyword arguments (defaults reproduce the reference):
   device_result=False          -- return the device tensor instead of a host ndarray;
   into=None, scale=1.0         -- accumulate scale * (this term) into an existing device matrix instead of a
       fresh zero one (how get_xr_H sums and subtracts terms without any elementwise pass).
+
+Bra slabs (multi-GPU row sharding, hermitian/distributed.py): a density dict that holds only the bra states [lo, hi) of
+every charge sector says so with ``rho["bra_offset"] = {chg: lo}`` (and ``n_states_bra`` = the slab sizes).  The rows
+of the matrix are then the slab's states and the Kronecker deltas of spectator fragments (XR_term.py:69-80) connect
+local bra state i with ket state lo + i.
 """
 import numpy
 
@@ -109,6 +114,13 @@ def dimer_matrix(op_blocks, active_diagrams, subsys_indices, charge_blocks, timi
     cols = _layout(rho1, rho2, "n_states", charge_blocks, ordering)
     n_j = lambda x, chg: op_blocks.densities[m[x]]["n_states"][chg]
 
+    def delta_range(x, chg):
+        """(first ket state, count) of the states of fragment x that a Kronecker delta pairs with its local bra states"""
+        rho = op_blocks.densities[m[x]]
+        if "bra_offset" in rho:
+            return rho["bra_offset"].get(chg, 0), rho["n_states_bra"][chg]
+        return 0, n_j(x, chg)
+
     for chg_i in charge_blocks:
         for chg_j in charge_blocks:
             subsys_charges = [(chg_i[0], chg_j[0]), (chg_i[1], chg_j[1])]
@@ -140,17 +152,19 @@ def dimer_matrix(op_blocks, active_diagrams, subsys_indices, charge_blocks, timi
                             # diagram value (1 for "identity") on the diagonal of the block (XR_term.py:69-80)
                             value = entry[label]
                             if value is not None:
-                                n0, n1 = n_j(0, chg_j[0]), n_j(1, chg_j[1])
+                                (lo0, n0), (lo1, n1) = delta_range(0, chg_j[0]), delta_range(1, chg_j[1])
                                 a = numpy.arange(n0, dtype=numpy.int64)[:, None]
                                 b = numpy.arange(n1, dtype=numpy.int64)[None, :]
-                                idx = base + a * (slot[("i", 0)] + slot[("j", 0)]) + b * (slot[("i", 1)] + slot[("j", 1)])
+                                idx = (base + lo0 * slot[("j", 0)] + lo1 * slot[("j", 1)]
+                                       + a * (slot[("i", 0)] + slot[("j", 0)]) + b * (slot[("i", 1)] + slot[("j", 1)]))
                                 idx = dev.upload(idx.reshape(-1), dtype=numpy.int64)
                                 dev.ctx.scatter_const(Matrix, idx, n0 * n1, scale * float(value), True)
                         elif frag_order == 1:
                             x, o = frags[0], others[0]
+                            lo, count = delta_range(o, chg_j[o])
                             strides = {("i", 0): slot[("i", x)], ("j", 0): slot[("j", x)],
-                                       "delta": slot[("i", o)] + slot[("j", o)], "n_delta": n_j(o, chg_j[o])}
-                            entry.accumulate(label, Matrix, base, strides, scale)
+                                       "delta": slot[("i", o)] + slot[("j", o)], "n_delta": count}
+                            entry.accumulate(label, Matrix, base + lo * slot[("j", o)], strides, scale)
                         else:
                             entry.accumulate(label, Matrix, base, slot, scale)
                         timings.record("block evaluation")

@@ -72,6 +72,9 @@ class frag_resolve(object):
         self._storage["Dchg"] = _indexable(lambda m: self._chgs[m][0] - self._chgs[m][1])
         self._storage["n_states"] = _indexable(lambda m: (dens[self._frags[m]]["n_states_bra"][self._chgs[m][0]],
                                                           dens[self._frags[m]]["n_states"][self._chgs[m][1]]))
+        # first bra state held of diagram fragment m when its densities are a bra slab (hermitian/distributed.py), else None
+        self._storage["bra_offset"] = _indexable(lambda m: dens[self._frags[m]]["bra_offset"].get(self._chgs[m][0], 0)
+                                                 if "bra_offset" in dens[self._frags[m]] else None)
 
     # absolute fragment / charges of diagram fragment m
     def fragment(self, m):
@@ -88,7 +91,7 @@ class frag_resolve(object):
     def __getattr__(self, attr):
         if attr.startswith("_"):
             raise AttributeError(attr)
-        if attr[:3] == "n_j" or attr in ("Dchg", "n_states"):
+        if attr[:3] == "n_j" or attr in ("Dchg", "n_states", "bra_offset"):
             return self._storage[attr]
         if attr in self._storage:
             return self._storage[attr]

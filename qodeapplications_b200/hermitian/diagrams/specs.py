@@ -232,14 +232,23 @@ def _u100_pieces(X, special_processing):
     return res, K, which
 
 
+def _delta_range(X, m):
+    """(first ket state, count) that the Kronecker delta on diagram fragment m pairs with its bra states 0, 1, ...: the
+    whole sector, or -- when the fragment's densities are a bra slab [lo, hi) -- ket states lo, lo + 1, ..."""
+    n_bra, n_ket = X.n_states[m]
+    lo = X.bra_offset[m]
+    return (0, min(n_bra, n_ket)) if lo is None else (lo, n_bra)
+
+
 def u100(X, special_processing=None):
     """delta(i1,j1) * sum_pq ca0[i0,j0,p,q] U[frag1, frag0, frag0][p,q]   (SU_2mer_0.py:26-96)"""
     (i0s, j0s), (i1s, j1s) = X.n_states[0], X.n_states[1]
     if special_processing is None:
         block = X.ca0pq_U1pq.host()
         result = numpy.zeros((i0s, i1s, j0s, j1s))
-        for i1 in range(min(i1s, j1s)):
-            result[:, i1, :, i1] = block
+        lo, n_delta = _delta_range(X, 1)
+        for i1 in range(n_delta):
+            result[:, i1, :, lo + i1] = block
         return result
     if special_processing not in (0, 1, 2, 3):
         raise ValueError("special processing %r can not be handled" % (special_processing,))
@@ -258,11 +267,10 @@ def u100(X, special_processing=None):
 def _u100_accumulate(X, phase, out, offset, strides, special_processing=None):
     C = _contractor(X)
     if special_processing is None:
-        (i0s, j0s), (i1s, j1s) = X.n_states[0], X.n_states[1]
-        n_delta = min(i1s, j1s)
+        lo, n_delta = _delta_range(X, 1)
         ones = C.dev.upload(numpy.ones((n_delta, 1)))
         C.contract(X.ca0pq_U1pq, ["i0", "j0"], DeviceTensor(ones, C.dev), ["d", "one"], ["i0", "j0", "d", "one"], alpha=phase,
-                   out=out, out_offset=offset,
+                   out=out, out_offset=offset + lo * strides["j1"],
                    out_strides={"i0": strides["i0"], "j0": strides["j0"], "d": strides["i1"] + strides["j1"], "one": 0},
                    accumulate=True)
         return True

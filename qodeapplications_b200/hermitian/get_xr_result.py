@@ -39,47 +39,84 @@ def precise_inverse(M, dev):
     return DeviceTensor(out, dev)
 
 
-def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False, device=None):
+def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False, device=None, shard=None):
+    """shard=(rank, world[, process group]): one process per GPU, each building the rows of its slab of fragment 0's bra
+    states; every rank returns the assembled (H1, H2) after one all-gather per matrix (hermitian/distributed.py)."""
     if bra_det and ket_det:
         raise NotImplementedError("bra_det and ket_det together")
     if (bra_det or ket_det) and xr_order != 0:
         raise NotImplementedError("bra_det / ket_det are built for xr_order 0 (two-fragment diagrams) only")
+    if (bra_det or ket_det) and shard is not None:
+        raise NotImplementedError("bra_det / ket_det with row sharding")
     diag_timer, precon_timer, matrix_timer = timer(), timer(), timer()
     symm_ints, bior_ints, nuc_rep = ints
     dev = device or default_device()
     store, contractor = DeviceStore(dev), Contractor(dev)
+    full_dens = dens
+    rows = None
+    if shard is not None:
+        from .distributed import row_shard
+        rows = row_shard(dens[0], monomer_charges[0], *shard)
+        dens = [rows.densities0, dens[1]]
     contract_cache = precontract(dens, symm_ints.S, precon_timer, store=store, contractor=contractor)
 
-    def make(integrals, diagrams):
-        return diagrammatic_expansion.blocks(densities=dens, integrals=integrals, diagrams=diagrams,
-                                             contract_cache=contract_cache, timings=diag_timer, precon_timings=precon_timer,
+    def make(integrals, diagrams, densities=None, cache=None):
+        return diagrammatic_expansion.blocks(densities=densities or dens, integrals=integrals, diagrams=diagrams,
+                                             contract_cache=cache or contract_cache, timings=diag_timer, precon_timings=precon_timer,
                                              bra_det=bra_det and diagrams is not S_diagrams, ket_det=ket_det and diagrams is not S_diagrams)
     S = symm_ints.S
-    S_blocks = make(S, S_diagrams)
+    if rows is None:
+        S_blocks = make(S, S_diagrams)
+    else:       # the overlap matrix is inverted, so every rank builds all of it (K = n contractions only)
+        S_blocks = make(S, S_diagrams, full_dens, precontract(full_dens, S, precon_timer, store=store, contractor=contractor))
     ST_symm, SU_symm, SV_symm = make(struct(S=S, T=symm_ints.T), ST_diagrams), make(struct(S=S, U=symm_ints.U), SU_diagrams), make(struct(S=S, V=symm_ints.V), SV_diagrams)
     ST_bior, SU_bior, SV_bior = make(struct(S=S, T=bior_ints.T), ST_diagrams), make(struct(S=S, U=bior_ints.U), SU_diagrams), make(struct(S=S, V=bior_ints.V), SV_diagrams)
 
     all_dimer_charges = [(c0, c1) for c0 in monomer_charges[0] for c1 in monomer_charges[1]]
+    dims = [sum(full_dens[m]["n_states"][c] for c in monomer_charges[m]) for m in (0, 1)]
+    dim1_bra = sum(full_dens[1].get("n_states_bra", full_dens[1]["n_states"])[c] for c in monomer_charges[1])
 
     def monomers(ST, SU, SV):
         H1 = []
         for m in (0, 1):
-            M = None
+            M = full = None
+            if rows is not None and m == 0:
+                full, M = rows.buffer(dev, 1, dims[0])
             for b, lst in ((ST, D.ST1), (SU, D.SU1), (SV, D.SV1)):
                 M = XR_term.monomer_matrix(b, {1: lst[0]}, m, monomer_charges[m], matrix_timer, device_result=True, into=M)
-            H1.append(M.host())
+            H1.append(M.host() if full is None else dev.download(rows.gather(full, 1)))
         return H1
 
     def dimer_sum(terms, into=None, scale=1.0):
-        """sum of dimer matrices, each term accumulated in place by its own GEMM epilogues"""
+        """sum of dimer matrices, each term accumulated in place by its own GEMM epilogues; with row sharding ``into`` is
+        this rank's slab of a padded full matrix and the result stays a slab until ``assembled`` gathers it"""
+        full = None
+        if rows is not None and into is None:
+            full, into = rows.buffer(dev, dim1_bra, dims[0] * dims[1])
         for op_blocks, active in terms:
             into = XR_term.dimer_matrix(op_blocks, active, (0, 1), all_dimer_charges, matrix_timer, bra_det=bra_det,
                                         ket_det=ket_det, ordering="final", device_result=True, into=into, scale=scale)
-        return into
+        return (full, into) if rows is not None else into
+
+    def assembled(result):
+        """device tensor of the whole matrix (row sharding: all-gather of the slabs, in place)"""
+        if rows is None:
+            return result
+        return DeviceTensor(rows.gather(result[0], dim1_bra), dev)
+
+    def apply_S2inv(S2inv, S2H2, out):
+        """out += S2inv @ S2H2 -- with row sharding only this rank's rows of the product, then the gather"""
+        if rows is None:
+            contractor.contract(S2inv, ["a", "k"], S2H2, ["k", "b"], ["a", "b"], out=out, accumulate=True)
+            return out
+        full, mine = out
+        mine_rows = DeviceTensor(S2inv.buf[rows.lo * dim1_bra:rows.hi * dim1_bra], dev)
+        contractor.contract(mine_rows, ["a", "k"], assembled(S2H2), ["k", "b"], ["a", "b"], out=mine, accumulate=True)
+        return assembled(out)
 
     if xr_order == 0:                                   # get_xr_result.py:86-132
         H1 = monomers(ST_bior, SU_bior, SV_bior)
-        H2 = dimer_sum([(ST_bior, {2: D.ST2[0]}), (SU_bior, {2: D.SU2[0]}), (SV_bior, {2: D.SV2[0]})]).host()
+        H2 = assembled(dimer_sum([(ST_bior, {2: D.ST2[0]}), (SU_bior, {2: D.SU2[0]}), (SV_bior, {2: D.SV2[0]})])).host()
     elif xr_order == 1:                                 # get_xr_result.py:133-213
         SV_diff = make(struct(S=S, V=bior_ints.V_diff), SV_diagrams)
         H1 = monomers(ST_symm, SU_symm, SV_symm)
@@ -91,8 +128,7 @@ def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False
         # H2 = S2inv @ S2H2 - (monomer terms in the dimer basis): the subtraction is accumulated first, with
         # scale -1, and the matrix product is then added on top by the GEMM epilogue
         out = dimer_sum([(ST_symm, {1: D.ST1[0]}), (SU_symm, {1: D.SU1[0]}), (SV_symm, {1: D.SV1[0]})], scale=-1.0)
-        contractor.contract(S2inv, ["a", "k"], S2H2, ["k", "b"], ["a", "b"], out=out, accumulate=True)
-        H2 = out.host()
+        H2 = apply_S2inv(S2inv, S2H2, out).host()
     elif xr_order == 2:                                 # get_xr_result.py:214-296
         SV_diff = make(struct(S=S, V=bior_ints.V_diff), SV_diagrams)
         H1 = monomers(ST_symm, SU_symm, SV_symm)
@@ -103,12 +139,10 @@ def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False
                           (ST_bior, {2: D.ST2[2]}), (SU_bior, {2: D.SU2[2]}),
                           (SV_symm, {1: D.SV1[0], 2: D.SV2[0]}), (SV_diff, {2: D.SV2[1]}), (SV_bior, {2: D.SV2[2]})])
         out = dimer_sum([(ST_symm, {1: D.ST1[0]}), (SU_symm, {1: D.SU1[0]}), (SV_symm, {1: D.SV1[0]})], scale=-1.0)
-        contractor.contract(S2inv, ["a", "k"], S2H2, ["k", "b"], ["a", "b"], out=out, accumulate=True)
-        H2 = out.host()
+        H2 = apply_S2inv(S2inv, S2H2, out).host()
     else:
         raise NotImplementedError("xr order %r is not implemented" % (xr_order,))
     return H1, H2
-
 
 def get_xr_S(ints, dens, xr_order, monomer_charges, device=None):
     """Dimer overlap matrix of the orbital solver -- hermitian-XRCC/get_xr_result.py:357-422 (called at

@@ -86,3 +86,39 @@ def test_two_rank_sharded_build_matches_reference(tmp_path):
         assert abs(out["dimer_moments"][0] - ref2.sum()) <= 1e-10 * numpy.abs(ref2).sum()
         assert numpy.allclose(out["dimer_moments_held"], out["dimer_moments"], rtol=1e-12, atol=0)
         assert numpy.allclose(out["dimer_moments_sector"], out["dimer_moments"], rtol=1e-12, atol=0)
+
+
+def _hermitian_worker(rank, world, port, out_dir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fake_xr import FakeDevice
+    from qodeapplications_b200 import synth
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    payload = {}
+    for order, ops in ((0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1), (2, synth.OPS_ORDER2)):
+        system = synth.make_system("toy", ops=ops, with_bior=True)
+        charges = system["charges"]
+        H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), system["densities"][:2], order, [charges, charges],
+                          device=FakeDevice(), shard=(rank, world))
+        payload["H1_0_order%d" % order], payload["H1_1_order%d" % order], payload["H2_order%d" % order] = H1[0], H1[1], H2
+    numpy.savez(os.path.join(out_dir, "rank%d.npz" % rank), **payload)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_sharded_get_xr_H_matches_reference(tmp_path, world):
+    """hermitian path, one process per rank over gloo: every rank builds the rows of its slab of fragment 0's bra states
+    (3 ranks over 7 states: slabs cut through charge sectors, the last one is short) and ends up with the reference's
+    H1 and H2 after the all-gathers"""
+    mp.spawn(_hermitian_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for order in (0, 1, 2):
+        g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_order%d.npz" % order))
+        for rank in range(world):
+            out = numpy.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+            for key in ("H1_0", "H1_1", "H2"):
+                got, ref = out["%s_order%d" % (key, order)], g[key]
+                assert got.shape == ref.shape
+                assert numpy.abs(got - ref).max() <= (1e-9 if order else 1e-10) * numpy.abs(ref).max(), (order, rank, key)

@@ -82,7 +82,12 @@ def test_gemm_scatter_offset_tables(dev):
                                             # stages item i+1's W/beta rows while item i streams
                                             (6, 400, 200, 40, 0), (18, 130, 330, 300, 0), (18, 70, 530, 700, 0),
                                             # odd leading dimension of W: rows are not 16-byte aligned, no TMA staging
-                                            (18, 130, 330, 300, 1), (6, 400, 200, 40, 3), (20, 9, 40, 129, 0), (48, 30, 100, 140, 0)])
+                                            (18, 130, 330, 300, 1), (6, 400, 200, 40, 3), (20, 9, 40, 129, 0), (48, 30, 100, 140, 0),
+                                            # every (DMMA k-steps, DFMA tail) cover the dispatcher instantiates: n = 4*KS + TAIL
+                                            (9, 12, 20, 150, 0), (10, 9, 33, 140, 0), (12, 17, 18, 129, 0), (13, 8, 16, 128, 0),
+                                            (13, 20, 40, 130, 1), (14, 10, 30, 200, 0), (16, 24, 40, 260, 0), (17, 9, 17, 130, 0),
+                                            (19, 9, 17, 130, 0), (24, 9, 20, 140, 0), (30, 10, 18, 130, 0), (36, 9, 17, 129, 0),
+                                            (44, 8, 16, 200, 0)])
 def test_trimer_stream(dev, n, Pa, Pb, Pc, pad):
     from qodeapplications_b200 import lib as xr
     rng = numpy.random.default_rng(n + Pa + Pb + Pc)

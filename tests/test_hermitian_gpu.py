@@ -195,3 +195,36 @@ def test_ragged_and_empty_charge_sectors(dev, order, ops, n_states):
     _close(H1[0], R1[0])
     _close(H1[1], R1[1])
     _close(H2, R2, 1e-9 if order else 1e-10)
+
+
+@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1)])
+def test_row_sharded_get_xr_H_single_rank(dev, order, ops):
+    """shard=(0, 1): the row-sharded code path (slab buffers, slab rows of S2inv) without a collective"""
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_order%d.npz" % order))
+    system = synth.make_system("toy", ops=ops, with_bior=True)
+    charges = system["charges"]
+    H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), system["densities"][:2], order, [charges, charges], device=dev,
+                      shard=(0, 1))
+    _close(H1[0], g["H1_0"])
+    _close(H1[1], g["H1_1"])
+    _close(H2, g["H2"], 1e-9 if order else 1e-10)
+
+
+@pytest.mark.parametrize("rank", [0, 1, 2])
+def test_row_sharded_get_xr_H_own_rows(dev, rank, monkeypatch):
+    """each of 3 ranks' slabs of the order-0 build (bra offsets in the spectator deltas, a short last slab) computed on
+    this GPU with the all-gather stubbed out: the rank's own rows must be the reference's"""
+    import torch.distributed as dist
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    from qodeapplications_b200.general.distributed import slab_bounds
+    monkeypatch.setattr(dist, "all_gather_into_tensor", lambda out, inp, group=None: None)
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_order0.npz"))
+    system = synth.make_system("toy", ops=synth.OPS_ORDER0, with_bior=True)
+    charges = system["charges"]
+    H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), system["densities"][:2], 0, [charges, charges], device=dev,
+                      shard=(rank, 3))
+    dim = g["H1_0"].shape[0]
+    lo, hi, per = slab_bounds(dim, rank, 3)
+    _close(H1[0][lo:hi], g["H1_0"][lo:hi])
+    _close(H2[lo * dim:hi * dim], g["H2"][lo * dim:hi * dim])
