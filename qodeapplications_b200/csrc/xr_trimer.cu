@@ -566,7 +566,7 @@ extern "C" int xr_trimer_stream(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int6
     p.offB = offB;
     p.offC = offC;
     // k = n is covered by 4*KS DMMA k-steps + TAIL DFMA k: exactly for n <= 20 (n mod 4 = 3 rounds up to the next DMMA
-    // step), in steps of 4/8 beyond (A fragments then come from shared memory, no tail).
+    // step), in steps of 4 beyond (A fragments then come from shared memory, no tail).
     // (WN = 3, i.e. 12 consumer warps with 32x32 warp tiles, was measured too: 29.1 vs 29.9 TFLOP/s for WN = 2 at
     //  n = 18 on B200 -- the kernel is bound by its DMMA:DFMA instruction mix, not by warp-level latency hiding)
 #define XR_TRIMER_CASE(COND, KS, TAIL) \
@@ -585,8 +585,11 @@ extern "C" int xr_trimer_stream(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int6
     XR_TRIMER_CASE(n == 18, 4, 2);
     XR_TRIMER_CASE(n <= 20, 5, 0);
     XR_TRIMER_CASE(n <= 24, 6, 0);
+    XR_TRIMER_CASE(n <= 28, 7, 0);
     XR_TRIMER_CASE(n <= 32, 8, 0);
+    XR_TRIMER_CASE(n <= 36, 9, 0);
     XR_TRIMER_CASE(n <= 40, 10, 0);
+    XR_TRIMER_CASE(n <= 44, 11, 0);
 #undef XR_TRIMER_CASE
     return launch_trimer<12, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
 }

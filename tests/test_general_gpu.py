@@ -87,7 +87,8 @@ def test_gemm_scatter_offset_tables(dev):
                                             (9, 12, 20, 150, 0), (10, 9, 33, 140, 0), (12, 17, 18, 129, 0), (13, 8, 16, 128, 0),
                                             (13, 20, 40, 130, 1), (14, 10, 30, 200, 0), (16, 24, 40, 260, 0), (17, 9, 17, 130, 0),
                                             (19, 9, 17, 130, 0), (24, 9, 20, 140, 0), (30, 10, 18, 130, 0), (36, 9, 17, 129, 0),
-                                            (44, 8, 16, 200, 0)])
+                                            (44, 8, 16, 200, 0), (26, 9, 17, 130, 0), (28, 8, 16, 129, 0), (34, 9, 17, 130, 0),
+                                            (42, 9, 20, 140, 0)])
 def test_trimer_stream(dev, n, Pa, Pb, Pc, pad):
     from qodeapplications_b200 import lib as xr
     rng = numpy.random.default_rng(n + Pa + Pb + Pc)
