@@ -11,6 +11,8 @@ multiprocessing.Pool like general-XRCC/test_H.py:131.
 The full workload cannot be run on a CPU (cfg4 is ~1e6 core-hours), so a fixed random sample of
 charge-allowed elements of every class is timed and the whole-workload time is extrapolated with
 the exact per-class element counts.
+
+`factored_numpy` is the second, best-effort CPU figure: the factored algorithm of the GPU path in NumPy/BLAS on all cores.
 """
 import itertools
 import os
@@ -126,3 +128,28 @@ def extrapolate(seconds, sample, counts):
 def make_pool(cores):
     ctx = multiprocessing.get_context("fork")      # workers inherit the prepared oracle (no CUDA in this process)
     return ctx.Pool(cores)
+
+
+def factored_numpy(n_states, n_orb, seconds=5.0, seed=0):
+    """Best-effort CPU figure beside the reference-faithful one: the FACTORED trimer-class algorithm the GPU
+    path uses -- X = beta . W[a] (GEMM), T = X . gamma^T (GEMM), sum of T^2 -- in NumPy/BLAS on all host cores, on factors
+    of the workload's own class shape (Pb = P(-1), Pc = P(+1) pair counts; random values: timing only), for about `seconds`
+    of wall clock.  Returns (algorithmic TFLOP/s = 2 n Pb Pc per row of W, rows done, seconds)."""
+    P = lambda d: sum(n_states[c] * n_states[c - d] for c in n_states if (c - d) in n_states)
+    Pb, Pc = P(-1), P(+1)
+    rng = numpy.random.default_rng(seed)
+    W = rng.standard_normal((8, n_orb, n_orb))
+    beta, gamma_t = rng.standard_normal((Pb, n_orb)), numpy.ascontiguousarray(rng.standard_normal((Pc, n_orb)).T)
+    chunk = 2048
+    T = numpy.empty((chunk, Pc))
+    rows, moment, t0 = 0, 0.0, time.perf_counter()
+    while True:
+        X = beta @ W[rows % 8]
+        for b0 in range(0, Pb, chunk):
+            t = numpy.matmul(X[b0:b0 + chunk], gamma_t, out=T[:min(chunk, Pb - b0)])
+            moment += float(numpy.vdot(t, t))
+        rows += 1
+        elapsed = time.perf_counter() - t0
+        if elapsed >= seconds:
+            break
+    return 2.0 * n_orb * Pb * Pc * rows / elapsed / 1e12, rows, elapsed
