@@ -14,6 +14,12 @@ reference's density code writes them (frag-states/compress_frags.py:91-99):
     temp += rho(0, 1, 2, 3);  temp -= rho(1, 0, 2, 3)
     raw(temp)  /  temp(0, 1, "p", "q") @ ...      # the terms are accumulated into ONE buffer by the GEMM epilogues
 
+Expressions stay LAZY, as in tensornet: calling a product or a sum with labels re-indexes its free axes (free axis k, in
+ascending order of the current integer labels, gets labels[k]) without evaluating anything, and `@` distributes over sums.
+That is what lets the decomposed high-rank densities of frag-states/decomps.py:71-166 -- antisymmetrised sums of OUTER
+products such as  anti(caC(p,u) @ cccaV(i,j,q,r,s,t), ...)  -- be handed to the diagram engine as they are: a density or
+integral entry may be such an expression, and every diagram then contracts its factors directly (tensor.FactoredTensor);
+the n^6..n^8 tensors they stand for are never formed.
 """
 import numpy
 
@@ -29,18 +35,46 @@ def _default_engine():
     return _engine[dev]
 
 
+_unique = [0]
+
+
+def _relabelled(factors, free, labels):
+    """factors with free axis free[k] renamed to labels[k]; the product's own contracted (string) labels are made unique
+    so that they cannot collide with string labels the caller brings"""
+    if len(labels) != len(free):
+        raise ValueError("expression with %d free axes indexed with %d labels" % (len(free), len(labels)))
+    _unique[0] += 1
+    rename = dict(zip(free, labels))
+    def new(l):
+        if isinstance(l, (int, numpy.integer)):
+            return rename[l]
+        return l if str(l).startswith("_x") else "_x%d_%s" % (_unique[0], l)
+    return [(tensor, tuple(new(l) for l in ls)) for tensor, ls in factors]
+
+
 class _product(object):
     """scalar * product of index-labelled tensors (a tensornet expression)"""
     def __init__(self, factors, scalar=1.0):
         self.factors, self.scalar = factors, scalar
     def __matmul__(self, other):
         other = other() if isinstance(other, xr_tensor) else other
+        if isinstance(other, _sum):
+            return _sum([self @ t for t in other.terms])
         return _product(self.factors + other.factors, self.scalar * other.scalar)
     def __mul__(self, scalar):
         return _product(self.factors, self.scalar * scalar)
     __rmul__ = __mul__
     def __neg__(self):
         return _product(self.factors, -self.scalar)
+    def __call__(self, *labels):
+        """the same product with its free axes re-indexed (lazy, like a tensornet tensor)"""
+        return _product(_relabelled(self.factors, _free(self), labels), self.scalar)
+    @property
+    def shape(self):
+        extent = {}
+        for tensor, labels in self.factors:
+            extent.update(zip(labels, tensor.shape))
+        return tuple(extent[l] for l in _free(self))
 
 
 class _sum(object):
@@ -59,10 +93,14 @@ class _sum(object):
     def __neg__(self):
         return _sum([-t for t in self.terms])
     def __call__(self, *labels):
-        """index the (evaluated) sum like a primitive tensor, to use it inside a further product"""
-        return _device_tensor(evaluate(self))(*labels)
+        """the same sum with the free axes of every term re-indexed (lazy)"""
+        return _sum([t(*labels) for t in self.terms])
     def __matmul__(self, other):
-        return self(*range(len(_free(self.terms[0])))) @ other
+        other = other() if isinstance(other, xr_tensor) else other
+        return _sum([t @ other for t in self.terms])
+    @property
+    def shape(self):
+        return self.terms[0].shape
 
 
 def _terms(expr):

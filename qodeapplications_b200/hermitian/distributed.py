@@ -29,6 +29,8 @@ def bra_slab(rho, held):
         sliced = {}
         for (ci, cj), t in val.items():
             lo, hi = held.get(ci, (0, 0))
+            if hasattr(t, "terms") or hasattr(t, "factors"):
+                raise NotImplementedError("row sharding of factored (lazy expression) densities")
             if isinstance(t, DeviceTensor):
                 sliced[(ci, cj)] = DeviceTensor(t.buf[lo:hi], t.dev)
             else:

@@ -15,7 +15,7 @@ only permuted, by xr_permute_copy, when an ``X`` sits between contracted letters
 """
 import numpy
 
-from .tensor import Contractor, DeviceStore, as_host, default_device
+from .tensor import Contractor, DeviceStore, FactoredTensor, as_host, default_device
 
 
 def parse_label(label):
@@ -124,7 +124,12 @@ class precontract(object):
                 idxR = ["i", "j"] + ["x%d" % k if c == "X" else c for k, c in enumerate(rho_idx)]
                 idxW = ["f%d" % k for k in range(n_free_int)] + contracted
                 free = [l for l in idxR if l not in contracted] + idxW[:n_free_int]
-                result = self.contractor.contract(R, idxR, Wt, idxW, free)
+                if isinstance(R, FactoredTensor):
+                    # a lazy density stays lazy (as under tensornet): the integral joins the factors of every term and is
+                    # contracted inside the diagram that uses this operand
+                    result = R.appended(idxR, (Wt, idxW), free)
+                else:
+                    result = self.contractor.contract(R, idxR, Wt, idxW, free)
                 if self._timings is not None:
                     self._timings.record(label)
                 return result

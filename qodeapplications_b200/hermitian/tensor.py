@@ -10,6 +10,7 @@ xr_gemm_scatter with int64 offset tables that place every (row, column) of the G
 address, so any output index order -- and accumulation straight into a block of a bigger matrix --
 costs nothing extra.  No arithmetic happens in torch or numpy.
 """
+import itertools
 import numpy
 import torch
 
@@ -30,8 +31,10 @@ def as_host(x):
     qode tensornet primitive, torch tensor)."""
     if isinstance(x, numpy.ndarray):
         return x
-    if isinstance(x, DeviceTensor):
+    if isinstance(x, (DeviceTensor, FactoredTensor)):
         return x.host()
+    if hasattr(x, "factors") or hasattr(x, "terms"):          # a lazy XR_tensor expression
+        return DeviceStore(default_device()).get(x).host()
     for attr in ("array", "data", "_raw_tensor"):
         inner = getattr(x, attr, None)
         if isinstance(inner, numpy.ndarray):
@@ -61,14 +64,74 @@ class DeviceTensor(object):
         return self.buf.shape[0]
 
 
+class FactoredTensor(object):
+    """A tensor given as a SUM of PRODUCTS of device tensors and never formed: terms = [(scalar, [(DeviceTensor, labels)])],
+    where an int label k says "axis k of the tensor this stands for" and a string label is summed inside the term.  This
+    is what a lazy XR_tensor expression (e.g. the decomposed rank-6..8 densities of frag-states/decomps.py, sums of outer
+    products of a core and a valence density) becomes on the device; Contractor splices the factors of every term into
+    the product it is asked for, so a diagram with such operands is contracted factor by factor."""
+    def __init__(self, terms, dev):
+        self.terms, self.dev = terms, dev
+        extent = {}
+        for T, labels in terms[0][1]:
+            extent.update((l, e) for l, e in zip(labels, T.shape) if isinstance(l, (int, numpy.integer)))
+        if sorted(extent) != list(range(len(extent))):
+            raise ValueError("a factored tensor needs integer labels 0..rank-1 on its free axes, got %r" % sorted(extent))
+        self._shape = tuple(extent[k] for k in range(len(extent)))
+    @property
+    def shape(self):
+        return self._shape
+    @property
+    def ndim(self):
+        return len(self._shape)
+    def __len__(self):
+        return self._shape[0]
+    def spliced(self, labels, tag):
+        """[(scalar, factors)] with axis k labelled labels[k] and the internal labels made private to operand `tag`"""
+        out = []
+        for t, (scalar, factors) in enumerate(self.terms):
+            out.append((scalar, [(T, [labels[l] if isinstance(l, (int, numpy.integer)) else "%s.%d:%s" % (tag, t, l) for l in ls])
+                                 for T, ls in factors]))
+        return out
+    def appended(self, labels, extra, axes_out):
+        """the factored tensor of  sum_{contracted} self[labels] * extra[0][extra[1]]  with result axes axes_out (labels):
+        nothing is contracted, the extra factor just joins every term (a lazy precontraction)"""
+        def back(l, t):
+            return axes_out.index(l) if l in axes_out else "pc%d:%s" % (t, l)
+        terms = []
+        for t, (scalar, factors) in enumerate(self.spliced(labels, "r")):
+            terms.append((scalar, [(T, [back(l, t) for l in ls]) for T, ls in factors + [extra]]))
+        return FactoredTensor(terms, self.dev)
+    def dense(self, contractor=None):
+        contractor = contractor or Contractor(self.dev)
+        axes = list(range(self.ndim))
+        return contractor.multi_contract([(self, axes)], axes)
+    def host(self):
+        return self.dense().host()
+    def __array__(self, dtype=None, copy=None):
+        out = self.host()
+        return out if dtype is None else out.astype(dtype)
+
+
 class DeviceStore(object):
     """host ndarray -> device copy, uploaded once (keyed by the host buffer's identity)."""
     def __init__(self, dev=None):
         self.dev = dev or default_device()
         self._by_id = {}
     def get(self, obj):
-        if isinstance(obj, DeviceTensor):
+        if isinstance(obj, (DeviceTensor, FactoredTensor)):
             return obj
+        if hasattr(obj, "terms") or hasattr(obj, "factors"):       # lazy XR_tensor sum / product: keep it factored
+            hit = self._by_id.get(id(obj))
+            if hit is None or hit[0] is not obj:
+                products = obj.terms if hasattr(obj, "terms") else [obj]
+                terms = [(float(t.scalar), [(self.get(T), tuple(ls)) for T, ls in t.factors]) for t in products]
+                for _, factors in terms:
+                    if any(isinstance(T, FactoredTensor) for T, _ in factors):
+                        raise NotImplementedError("nested factored tensors")
+                hit = (obj, FactoredTensor(terms, self.dev))
+                self._by_id[id(obj)] = hit
+            return hit[1]
         host = as_host(obj)
         key = id(host) if isinstance(obj, numpy.ndarray) else id(obj)
         hit = self._by_id.get(key)
@@ -135,6 +198,8 @@ class Contractor(object):
         output label inside it and out_offset the element offset of the block (this is how a diagram block is
         accumulated in place into the packed XR matrix)."""
         idxA, idxB, idx_out = list(idxA), list(idxB), list(idx_out)
+        if isinstance(A, FactoredTensor) or isinstance(B, FactoredTensor):
+            return self.multi_contract([(A, idxA), (B, idxB)], idx_out, alpha, out, out_offset, out_strides, accumulate)
         shared = [l for l in idxA if l in idxB and l not in idx_out]
         rows = [l for l in idxA if l not in shared]
         cols = [l for l in idxB if l not in shared]
@@ -211,7 +276,11 @@ def _multi_contract(self, factors, idx_out, alpha=1.0, out=None, out_offset=0, o
                 if best is None or size < best[0]:
                     best = (size, a, b, keep)
         if best is None:
-            raise NotImplementedError("outer products of unconnected factors")
+            # no two factors share a label (outer products of a core and a valence density, frag-states/decomps.py): take
+            # the outer product of the two smallest factors -- a K = 1 GEMM -- and go on
+            order = sorted(range(len(factors)), key=lambda k: int(numpy.prod(factors[k][0].shape)))
+            a, b = sorted(order[:2])
+            best = (0, a, b, factors[a][1] + factors[b][1])
         _, a, b, keep = best
         merged = self.contract(factors[a][0], factors[a][1], factors[b][0], factors[b][1], keep)
         factors = [f for k, f in enumerate(factors) if k not in (a, b)] + [(merged, keep)]
@@ -219,4 +288,30 @@ def _multi_contract(self, factors, idx_out, alpha=1.0, out=None, out_offset=0, o
     return self.contract(A, idxA, B, idxB, idx_out, alpha, out, out_offset, out_strides, accumulate)
 
 
-Contractor.multi_contract = _multi_contract
+def _multi_contract_factored(self, factors, idx_out, alpha=1.0, out=None, out_offset=0, out_strides=None, accumulate=False):
+    """multi_contract with FactoredTensor operands: the product is expanded over the terms of every factored operand and
+    each combination is contracted factor by factor, all of them accumulated into the one output."""
+    if not any(isinstance(T, FactoredTensor) for T, _ in factors):
+        return _multi_contract(self, factors, idx_out, alpha, out, out_offset, out_strides, accumulate)
+    idx_out = list(idx_out)
+    choices = []
+    for k, (T, idx) in enumerate(factors):
+        choices.append(T.spliced(list(idx), "f%d" % k) if isinstance(T, FactoredTensor) else [(1.0, [(T, list(idx))])])
+    if out is None:
+        extent = {}
+        for T, idx in factors:
+            extent.update(zip(idx, T.shape))
+        out = DeviceTensor(self.dev.zeros(tuple(extent[l] for l in idx_out)), self.dev)
+        accumulate = True
+    first = True
+    for combo in itertools.product(*choices):
+        scalar, spliced = alpha, []
+        for s, fs in combo:
+            scalar *= s
+            spliced += fs
+        _multi_contract(self, spliced, idx_out, scalar, out, out_offset, out_strides, accumulate or not first)
+        first = False
+    return out
+
+
+Contractor.multi_contract = _multi_contract_factored

@@ -184,17 +184,22 @@ class FakeDevice(object):
         self.torch_device = torch.device("cpu")
         self.ctx = FakeContext()
         self.h2d_bytes = self.d2h_bytes = 0
+        self.largest_allocation = 0          # elements of the biggest tensor ever created on this "device"
+
+    def _made(self, tensor):
+        self.largest_allocation = max(self.largest_allocation, tensor.numel())
+        return tensor
 
     def empty(self, shape, dtype=torch.float64):
-        return torch.zeros(shape, dtype=dtype)
+        return self._made(torch.zeros(shape, dtype=dtype))
 
     def zeros(self, shape, dtype=torch.float64):
-        return torch.zeros(shape, dtype=dtype)
+        return self._made(torch.zeros(shape, dtype=dtype))
 
     def upload(self, array, dtype=numpy.float64):
         array = numpy.array(array, dtype=dtype, order="C", copy=True)
         self.h2d_bytes += array.nbytes
-        return torch.from_numpy(array)
+        return self._made(torch.from_numpy(array))
 
     def download(self, tensor):
         self.d2h_bytes += tensor.numel() * tensor.element_size()

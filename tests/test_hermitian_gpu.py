@@ -228,3 +228,36 @@ def test_row_sharded_get_xr_H_own_rows(dev, rank, monkeypatch):
     lo, hi, per = slab_bounds(dim, rank, 3)
     _close(H1[0][lo:hi], g["H1_0"][lo:hi])
     _close(H2[lo * dim:hi * dim], g["H2"][lo * dim:hi * dim])
+
+
+def test_factored_densities(dev):
+    """densities of 5..8 operators given as lazy sums of outer products (frag-states/decomps.py form): a sample of the
+    S-order 1-4 diagram blocks that read them and get_xr_H at order 2, against the oracle on the written-out tensors"""
+    import itertools
+    from test_host_logic_cpu import factored_system, _hermitian_blocks
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    lazy, dense = factored_system()
+    charges, symm = lazy["charges"], lazy["symm"]
+    for fam, ints, labels in (("ST", ho.integrals(symm.S, T=symm.T), ["s01t00", "s01s01s10t10", "s01s01s01s10t00"]),
+                              ("SV", ho.integrals(symm.S, V=symm.V), ["s01v0000", "s01s10v0101", "s01s01s01s10v1111", "s01s01s10s10v0011"])):
+        blk = _hermitian_blocks(lazy, dev, fam)
+        for label in labels:
+            checked = 0
+            for ci0, ci1, cj0, cj1 in itertools.product(charges, repeat=4):
+                if ci0 + ci1 != cj0 + cj1:
+                    continue
+                chgs = ((ci0, cj0), (ci1, cj1))
+                ref = ho.dimer_block(label, dense["densities"], ints, (0, 1), chgs)
+                got = blk[(0, 1)][chgs][label]
+                if ref is None:
+                    assert got is None
+                    continue
+                _close(got, ref)
+                checked += 1
+            assert checked
+    lazy2, dense2 = factored_system("toy", synth.OPS_ORDER2, min_rank=5, seed=6)
+    args = (2, [lazy2["charges"], lazy2["charges"]])
+    H1, H2 = get_xr_H((lazy2["symm"], lazy2["bior"], lazy2["nuc"]), lazy2["densities"][:2], *args, device=dev)
+    R1, R2 = ho.get_xr_H(dense2["symm"], dense2["bior"], dense2["densities"][:2], *args)
+    _close(H1[0], R1[0])
+    _close(H2, R2, 1e-9)

@@ -3,6 +3,7 @@ planning) run on the TEST-ONLY NumPy device stand-in (tests/fake_xr.py) and comp
 the reference produced.  The CUDA kernels are not involved here; they are checked by the -m gpu tests."""
 import itertools
 import os
+import re
 import numpy
 import pytest
 
@@ -253,3 +254,75 @@ def test_hermitian_ragged_and_empty_sectors_host_logic(order, ops, n_states):
     _close(H1[0], R1[0])
     _close(H1[1], R1[1])
     _close(H2, R2, 1e-9 if order else 1e-10)
+
+
+def factored_system(name="toy4", ops=synth.OPS_ORDER4, min_rank=5, seed=5):
+    """(system with every density of >= min_rank operators given as a LAZY XR_tensor expression -- an antisymmetrised sum of
+    outer products of a 'core' matrix and a 'valence' density, the form of frag-states/decomps.py:111-166 --, the same
+    system with those expressions written out densely by numpy.einsum for the oracle)"""
+    from qodeapplications_b200.hermitian import XR_tensor
+    lazy = synth.make_system(name, ops=ops, with_bior=True)
+    dense = dict(lazy, densities=[dict(rho) for rho in lazy["densities"]])
+    rng = numpy.random.default_rng(seed)
+    letters = "abcdefgh"
+    for m, rho in enumerate(lazy["densities"]):
+        for op in ops:
+            k = len(op)
+            if k < min_rank:
+                continue
+            lazy_op, dense_op = {}, {}
+            for (ci, cj), t in rho[op].items():
+                Ni, Nj, n = t.shape[0], t.shape[1], t.shape[2]
+                core = rng.standard_normal((n, n)) / n
+                val = rng.standard_normal((Ni, Nj) + (n,) * (k - 2)) * n ** (-(k - 2) / 2)
+                C, V = XR_tensor.init(core), XR_tensor.init(val)
+                # core on the first and last orbital axis, minus the same with the first two orbital axes exchanged
+                base = C(2, k + 1) @ V(0, 1, *range(3, k + 1))
+                lazy_op[(ci, cj)] = base - base(0, 1, 3, 2, *range(4, k + 2))
+                orb = letters[:k]
+                full = numpy.einsum("%s%s,ij%s->ij%s" % (orb[0], orb[-1], orb[1:-1], orb), core, val)
+                dense_op[(ci, cj)] = full - full.swapaxes(2, 3)
+            lazy["densities"][m][op], dense["densities"][m][op] = lazy_op, dense_op
+    return lazy, dense
+
+
+def test_hermitian_factored_densities_host_logic():
+    """densities of 5..8 operators handed over as lazy sums of outer products (never formed): every diagram block of
+    S-orders 1-4 that reads one, and get_xr_H at order 2, against the oracle on the densely written-out tensors"""
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    from qodeapplications_b200.hermitian.tensor import FactoredTensor
+    from qodeapplications_b200.hermitian.diagrams import specs
+    from oracle import hermitian_oracle as ho
+    lazy, dense = factored_system()
+    dev = FakeDevice()
+    charges = lazy["charges"]
+    symm = lazy["symm"]
+    checked = 0
+    for fam, ints in (("ST", ho.integrals(symm.S, T=symm.T)), ("SU", ho.integrals(symm.S, U=symm.U)), ("SV", ho.integrals(symm.S, V=symm.V))):
+        blk = _hermitian_blocks(lazy, dev, fam)
+        labels = [l for l, (_, _, operands) in specs.TWO_FRAGMENT.items()
+                  if l in blk._diagrams.catalog[2] and any(len(re.match(r"[ca]+", name).group(0)) >= 5 for name, _ in operands if name[0] in "ca")]
+        assert labels
+        for label in labels[::3]:                       # every third one keeps the CPU suite short
+            for ci0, ci1, cj0, cj1 in itertools.product(charges, repeat=4):
+                if ci0 + ci1 != cj0 + cj1:
+                    continue
+                chgs = ((ci0, cj0), (ci1, cj1))
+                ref = ho.dimer_block(label, dense["densities"], ints, (0, 1), chgs)
+                got = blk[(0, 1)][chgs][label]
+                if ref is None:
+                    assert got is None
+                    continue
+                _close(got, ref)
+                checked += 1
+    assert checked > 50
+    # nothing of the size of a high-rank density was ever allocated on the device
+    biggest = max(numpy.prod(t.shape) for rho in dense["densities"][:2] for op in rho if isinstance(rho[op], dict) and len(op) >= 7
+                  for t in rho[op].values() if hasattr(t, "shape"))
+    assert dev.largest_allocation < biggest
+    lazy2, dense2 = factored_system("toy", synth.OPS_ORDER2, min_rank=5, seed=6)
+    args = (2, [lazy2["charges"], lazy2["charges"]])
+    H1, H2 = get_xr_H((lazy2["symm"], lazy2["bior"], lazy2["nuc"]), lazy2["densities"][:2], *args, device=FakeDevice())
+    R1, R2 = ho.get_xr_H(dense2["symm"], dense2["bior"], dense2["densities"][:2], *args)
+    _close(H1[0], R1[0])
+    _close(H2, R2, 1e-9)
