@@ -14,7 +14,7 @@
  *
  *  (B) Block-level entry points (xr_*): what replaces the reference's per-element Python
  *      loops (general-XRCC/test_H.py:90-142) and per-diagram tensornet einsums
- *      (hermitian-XRCC/diagrams/*.py via XRbase/XR_tensor.py:57).  They work on DEVICE
+ *      (hermitian-XRCC/diagrams/S[TUV]_?mer_?.py via XRbase/XR_tensor.py:57).  They work on DEVICE
  *      pointers, are asynchronous on the context's stream, and return 0 on success or a
  *      negative xr_status (message from xr_last_error()).  One context per host thread;
  *      a context must be created in the process that uses it (CUDA does not survive the

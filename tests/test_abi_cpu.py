@@ -41,3 +41,23 @@ def test_no_cpu_fallback():
     contract = import_C("H_contractions")
     with pytest.raises(xr.XRError):
         contract.monomer_1e(2, numpy.ones((2, 2)), numpy.ones((2, 2)))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_c99_host_links_and_loads(tmp_path):
+    """include/xr_b200.h is plain C (gcc -std=c99 -pedantic -Werror) and a C host with no Python/torch in the process can
+    link libxr_b200.so: tests/c_host/abi_check.c reports XR_ERR_NO_DEVICE + message here (its GPU branch runs a GEMM)"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    here = os.path.dirname(os.path.abspath(__file__))
+    libdir = os.path.dirname(xr.LIB_PATH)
+    exe = str(tmp_path / "abi_check")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(here, "..", "include"),
+                           os.path.join(here, "c_host", "abi_check.c"), "-o", exe, "-L", libdir, "-lxr_b200", "-lm",
+                           "-Wl,-rpath," + libdir])
+    run = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert run.returncode == 0, run.stdout
+    assert "no CPU fallback" in run.stdout
