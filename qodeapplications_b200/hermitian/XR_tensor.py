@@ -130,6 +130,10 @@ class _device_tensor(object):
         if len(labels) != len(self.shape):
             raise ValueError("tensor of rank %d indexed with %d labels" % (len(self.shape), len(labels)))
         return _product([(self.device_tensor, tuple(labels))])
+    def __getitem__(self, key):
+        """basic slicing (ints, slices, Ellipsis) of an evaluated tensor: a contiguous copy in HBM, indexable again"""
+        sliced = self.device_tensor.buf[key].contiguous()
+        return _device_tensor(DeviceTensor(sliced, self.device_tensor.dev))
 
 
 class xr_tensor(object):
@@ -151,6 +155,10 @@ class xr_tensor(object):
         return _product([(self, tuple(labels))])
     def __matmul__(self, other):
         return self() @ other
+    def __getitem__(self, key):
+        """basic slicing of primitive data, as the reference's callers write it:  v_bior[:, :, sl1, :](p, q, 1, s) @ ...
+        (StateSpaceOptimizer/orb_grads.py:67)"""
+        return xr_tensor(self.array[key])
 
 
 def init(raw_tensor):

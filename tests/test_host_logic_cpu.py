@@ -326,3 +326,31 @@ def test_hermitian_factored_densities_host_logic():
     R1, R2 = ho.get_xr_H(dense2["symm"], dense2["bior"], dense2["densities"][:2], *args)
     _close(H1[0], R1[0])
     _close(H2, R2, 1e-9)
+
+
+def test_xr_tensor_slicing_and_lazy_reindexing():
+    """the rest of the tensornet surface the reference's callers use on this seam: slices of primitive tensors
+    (StateSpaceOptimizer/orb_grads.py:67), re-indexing of products and sums without evaluation (frag-states/decomps.py:71-108)"""
+    from qodeapplications_b200.hermitian import XR_tensor
+    from qodeapplications_b200.hermitian.tensor import Contractor, DeviceStore
+    dev = FakeDevice()
+    engine = (DeviceStore(dev), Contractor(dev))
+    rng = numpy.random.default_rng(8)
+    v, m, d = rng.standard_normal((4, 4, 6, 4)), rng.standard_normal((4, 4, 4, 3)), rng.standard_normal((4, 4))
+    V, M, Dm = XR_tensor.init(v), XR_tensor.init(m), XR_tensor.init(d)
+    sl = slice(1, 5)
+    got = XR_tensor.raw(V[:, :, sl, :]("p", "q", 1, "s") @ M("p", "q", "s", 0), engine)
+    _close(got, numpy.einsum("pqbs,pqsa->ab", v[:, :, sl, :], m), 1e-13)
+    # a product re-indexed twice, then antisymmetrised, then contracted: nothing is evaluated before raw()
+    outer = Dm(0, 3) @ M(1, 2, 4, 5)                                   # [a, b, c, d, e, f] = d[a, d] m[b, c, e, f]
+    dense = numpy.einsum("ad,bcef->abcdef", d, m)
+    swapped = outer(1, 0, 2, 3, 4, 5)
+    _close(XR_tensor.raw(swapped, engine), dense.transpose(1, 0, 2, 3, 4, 5), 1e-15)
+    anti = outer - swapped
+    w = rng.standard_normal((4, 4))
+    fresh = FakeDevice()
+    got = XR_tensor.raw(anti(0, "x", "y", 1, 2, 3) @ XR_tensor.init(w)("x", "y"), (DeviceStore(fresh), Contractor(fresh)))
+    _close(got, numpy.einsum("axydef,xy->adef", dense - dense.transpose(1, 0, 2, 3, 4, 5), w), 1e-13)
+    assert fresh.largest_allocation < dense.size          # the rank-6 tensor itself was never formed
+    with pytest.raises(ValueError):
+        outer(0, 1, 2)
