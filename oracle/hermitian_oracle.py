@@ -1,4 +1,4 @@
-"""CPU oracle for the hermitian-XRCC Hamiltonian build (S-orders 0, 1 and 2).  TEST INFRASTRUCTURE: only
+"""CPU oracle for the hermitian-XRCC Hamiltonian build (diagram blocks of S-orders 0-4, get_xr_H at xr_order 0-2).  TEST INFRASTRUCTURE: only
 tests/, smoke() and bench.py's CPU legs may import this.
 
 Third-party dependency of the reference on this path: ``qode`` (github adutoi/Qode, version
