@@ -20,27 +20,42 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir):
+def _device(rank, world, port, gpu):
+    """process group + device of one rank: gloo on the test-only NumPy stand-in, or NCCL on GPU `rank` (test_distributed_gpu.py)"""
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    if gpu:
+        from qodeapplications_b200.device import Device
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        return lambda: Device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from fake_xr import FakeDevice
+    return FakeDevice
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _worker(rank, world, port, out_dir, gpu=False):
+    make_device = _device(rank, world, port, gpu)
     from qodeapplications_b200 import synth
     from qodeapplications_b200.general.build_H import build_matrix_elements
     from qodeapplications_b200.general.distributed import sharded_build
     system = synth.make_system("toy3")
-    eng = build_matrix_elements(system["fragments"], system["symm"], system["nuc"], device=FakeDevice())
+    eng = build_matrix_elements(system["fragments"], system["symm"], system["nuc"], device=make_device())
     dimers = list(itertools.combinations(range(3), 2))
     build = sharded_build(eng, dimers, [(0, 1, 2)], rank, world)
     build.step(gather=True)
     moments = build.reduced_moments()
-    payload = {"H2_%d%d" % k: build.full(*k).numpy() for k in dimers}
+    payload = {"H2_%d%d" % k: _np(build.full(*k)) for k in dimers}
     payload["moments"] = numpy.array(moments[(0, 1, 2)])
     # streamed dimer with the factor exchange (all-gather of the fragment-2 factor slabs)
     t = eng.H2_moments_device(0, 2, shard=(rank, world))
     dist.all_reduce(t)
-    payload["dimer_moments"] = t.numpy().sum(axis=0)
+    payload["dimer_moments"] = _np(t).sum(axis=0)
     # the same with each rank holding only ITS bra slab of the densities (the cfg5 input layout)
     from qodeapplications_b200.general.distributed import slab_bounds
     n_states = synth.CONFIGS["toy3"]["n_states"]
@@ -49,20 +64,20 @@ def _worker(rank, world, port, out_dir):
         lo, hi = slab_bounds(len(frags[m].state_indices), rank, world)[:2]
         held[m] = (lo, hi)
         frags[m] = synth.slab_fragment(frags[m], (lo, hi), n_states)
-    eng_slab = build_matrix_elements(frags, system["symm"], system["nuc"], device=FakeDevice(), held=held)
+    eng_slab = build_matrix_elements(frags, system["symm"], system["nuc"], device=make_device(), held=held)
     t = eng_slab.H2_moments_device(0, 2, shard=(rank, world))
     dist.all_reduce(t)
-    payload["dimer_moments_held"] = t.numpy().sum(axis=0)
+    payload["dimer_moments_held"] = _np(t).sum(axis=0)
     # ... and with the balanced per-charge-sector shard as the held range
     from qodeapplications_b200.general.distributed import balanced_shard
     mine = balanced_shard(n_states, rank, world)
     frags = list(system["fragments"])
     for m in (0, 2):
         frags[m] = synth.slab_fragment(frags[m], mine, n_states)
-    eng_sect = build_matrix_elements(frags, system["symm"], system["nuc"], device=FakeDevice(), held={0: mine, 2: mine})
+    eng_sect = build_matrix_elements(frags, system["symm"], system["nuc"], device=make_device(), held={0: mine, 2: mine})
     t = eng_sect.H2_moments_device(0, 2, shard=(rank, world))
     dist.all_reduce(t)
-    payload["dimer_moments_sector"] = t.numpy().sum(axis=0)
+    payload["dimer_moments_sector"] = _np(t).sum(axis=0)
     numpy.savez(os.path.join(out_dir, "rank%d.npz" % rank), **payload)
     dist.destroy_process_group()
 
@@ -88,12 +103,8 @@ def test_two_rank_sharded_build_matches_reference(tmp_path):
         assert numpy.allclose(out["dimer_moments_sector"], out["dimer_moments"], rtol=1e-12, atol=0)
 
 
-def _hermitian_worker(rank, world, port, out_dir):
-    sys.path.insert(0, HERE)
-    sys.path.insert(0, os.path.dirname(HERE))
-    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    from fake_xr import FakeDevice
+def _hermitian_worker(rank, world, port, out_dir, gpu=False):
+    make_device = _device(rank, world, port, gpu)
     from qodeapplications_b200 import synth
     from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
     payload = {}
@@ -101,7 +112,7 @@ def _hermitian_worker(rank, world, port, out_dir):
         system = synth.make_system("toy", ops=ops, with_bior=True)
         charges = system["charges"]
         H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), system["densities"][:2], order, [charges, charges],
-                          device=FakeDevice(), shard=(rank, world))
+                          device=make_device(), shard=(rank, world))
         payload["H1_0_order%d" % order], payload["H1_1_order%d" % order], payload["H2_order%d" % order] = H1[0], H1[1], H2
     numpy.savez(os.path.join(out_dir, "rank%d.npz" % rank), **payload)
     dist.destroy_process_group()
