@@ -354,3 +354,32 @@ def test_xr_tensor_slicing_and_lazy_reindexing():
     assert fresh.largest_allocation < dense.size          # the rank-6 tensor itself was never formed
     with pytest.raises(ValueError):
         outer(0, 1, 2)
+
+
+@pytest.mark.parametrize("seed", [101, 202, 303])
+def test_general_randomised_systems_host_logic(seed):
+    """seeded random systems -- 2 or 3 fragments, equal or different orbital counts, any subset of the charges -2..2 with 0..3
+    states each -- against the element-level port of build_H.py (the same loop run over 190 draws, and 54 hermitian ones at orders 0-2, found no mismatch)"""
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    from oracle import general_oracle as go
+    rng = numpy.random.default_rng(seed)
+    for _ in range(4):
+        F = int(rng.integers(2, 4))
+        n_orb = [int(rng.integers(2, 6)) for _ in range(F)] if rng.random() < 0.5 else int(rng.integers(2, 6))
+        n_states = {c: int(rng.integers(0, 4)) for c in [0] + [c for c in (1, -1, 2, -2) if rng.random() < 0.6]}
+        n_states[0] = max(n_states[0], 1)
+        system = synth.make_system(n_frag=F, n_orb=n_orb, n_states=n_states, seed=int(rng.integers(1 << 30)))
+        fr, ints, nuc = system["fragments"], system["symm"], system["nuc"]
+        eng = build_matrix_elements(fr, ints, nuc, device=FakeDevice())
+        for m in range(F):
+            _close(eng.H1(m), go.block_monomer(fr, ints, nuc, m))
+        for m1, m2 in itertools.combinations(range(F), 2):
+            ref = go.block_dimer(fr, ints, nuc, m1, m2)
+            _close(eng.H2(m1, m2), ref)
+            assert abs(eng.H2_moments(m1, m2)[1] - (ref ** 2).sum()) <= 1e-9 * max((ref ** 2).sum(), 1e-30)
+        if F == 3:
+            ref = go.block_trimer(fr, ints, (0, 1, 2))
+            _close(eng.H3(0, 1, 2), ref)
+            s, q = eng.H3_moments(0, 1, 2)
+            assert abs(q - (ref ** 2).sum()) <= 1e-9 * max((ref ** 2).sum(), 1e-30)
+            assert abs(s - ref.sum()) <= 1e-9 * max(numpy.abs(ref).sum(), 1e-30)
