@@ -7,3 +7,7 @@ timeout 150 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest_gpu.l
 timeout 100 ncu --set full --clock-control none --import-source on -k regex:trimer_stream -c 1 -f -o gpurun_out/${tag}_trimer_full python tools/ncu_kernels.py > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 timeout 330 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${tag}_launches_cfg4.csv python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline > gpurun_out/${tag}_launches_bench.log 2>&1; echo "ncu launches rc=$?"
 timeout 330 python bench.py --steps 1 --warmup 3 > gpurun_out/${tag}_bench_cfg4_n1.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"; cut -c1-600 gpurun_out/${tag}_bench_cfg4_n1.json
+# optional (XR_SANITIZE=1): memcheck of the trimer launcher's kernels, incl. the multi-block first-moment kernels added in r01s
+if [ "${XR_SANITIZE:-0}" = "1" ]; then
+  timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/trimer_sweep.py 18 130 330 300 > gpurun_out/${tag}_sanitizer.txt 2>&1; echo "sanitizer rc=$?"; tail -2 gpurun_out/${tag}_sanitizer.txt
+fi
