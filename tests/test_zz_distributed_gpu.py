@@ -1,6 +1,7 @@
 """The multi-rank builds of tests/test_distributed_cpu.py over NCCL on real GPUs (one process per GPU): needs a box with
 at least two of them (`gpurun --gpus 2`), skipped otherwise.  Same workers, same checks against the reference's golden vectors.
-(Named zz so that it runs after the single-GPU files: written when no multi-GPU box was available, first run pending.)"""
+Written when no multi-GPU box was available: until its first run on one has been recorded under profiles/, it only runs
+on request (XR_TEST_NCCL=1), so that an unproven test cannot fail the GPU tier; the file sorts last for the same reason."""
 import itertools
 import os
 import numpy
@@ -11,6 +12,7 @@ import torch.multiprocessing as mp
 import test_distributed_cpu as cpu
 
 pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("XR_TEST_NCCL") != "1", reason="first multi-GPU run pending: set XR_TEST_NCCL=1"),
               pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one box (NCCL, one process per GPU)")]
 
 
