@@ -1,6 +1,8 @@
 #!/bin/bash
 # One GPU call that refreshes the judged evidence: parity tests, ncu full capture of the trimer kernel, ncu launch list of one
 # bench step (about 250 s under ncu: 170 s cut the r01r list short), then the bench line itself (never under ncu).  Usage: gpurun --timeout 760 -- 'bash tools/gpu_round_evidence.sh r01r'
+# Multi-GPU follow-ups (separate calls): gpurun --gpus 2 -- 'XR_TEST_NCCL=1 python -m pytest tests/test_zz_distributed_gpu.py -m gpu -q';
+#   gpurun --gpus 8 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tools/bench_hermitian_sharded.py 0 herm100'
 tag=${1:-r01x}
 mkdir -p gpurun_out
 timeout 150 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/${tag}_pytest_gpu.log
