@@ -383,3 +383,74 @@ def test_general_randomised_systems_host_logic(seed):
             s, q = eng.H3_moments(0, 1, 2)
             assert abs(q - (ref ** 2).sum()) <= 1e-9 * max((ref ** 2).sum(), 1e-30)
             assert abs(s - ref.sum()) <= 1e-9 * max(numpy.abs(ref).sum(), 1e-30)
+
+
+REFERENCE_HERMITIAN = "/root/reference/hermitian-XRCC"
+
+
+def _reference_get_xr_result(monkeypatch):
+    """the reference's own get_xr_result.py, loaded unmodified from where it lies, on top of THIS package's modules under
+    their top-level names (hermitian.install_aliases) and the qode stand-in of oracle/qode_shim; returns (module, restore)"""
+    import importlib.util
+    import sys
+    from qodeapplications_b200 import hermitian
+    from qodeapplications_b200.hermitian import tensor
+    shim = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "qode_shim")
+    before = dict(sys.modules)
+    monkeypatch.syspath_prepend(os.path.abspath(shim))
+    monkeypatch.setattr(tensor, "_default_device", FakeDevice())
+    def restore():
+        for name in list(sys.modules):
+            if name not in before:
+                del sys.modules[name]
+        sys.modules.update(before)
+    try:
+        for name in [n for n in sys.modules if n == "qode" or n.startswith("qode.") or n == "excitonic"]:
+            del sys.modules[name]
+        hermitian.install_aliases()
+        spec = importlib.util.spec_from_file_location("reference_get_xr_result", os.path.join(REFERENCE_HERMITIAN, "get_xr_result.py"))
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        assert ref.XR_term is hermitian.XR_term and ref.diagrammatic_expansion is hermitian.diagrammatic_expansion
+        assert ref.precontract is hermitian.precontract.precontract and ref.D is hermitian.diagram_lists
+    except Exception:
+        restore()
+        raise
+    return ref, restore
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_HERMITIAN), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1), (2, synth.OPS_ORDER2)])
+def test_reference_driver_runs_unmodified_on_these_modules(order, ops, monkeypatch):
+    """The drop-in claim itself: the reference's OWN get_xr_H drives this package's XR_term / diagrammatic_expansion /
+    precontract / diagrams / diagram_lists -- its call signatures, its charge-blocked matrices, its Python reorder loop --
+    and must reproduce the golden H1/H2 that the all-reference run produced."""
+    ref, restore = _reference_get_xr_result(monkeypatch)
+    try:
+        system = synth.make_system("toy", ops=ops, with_bior=True)
+        charges = system["charges"]
+        H1, H2 = ref.get_xr_H((system["symm"], system["bior"], system["nuc"]), system["densities"][:2], order, [charges, charges])
+    finally:
+        restore()
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_order%d.npz" % order))
+    _close(H1[0], g["H1_0"])
+    _close(H1[1], g["H1_1"])
+    _close(H2, g["H2"], 1e-9 if order else 1e-10)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_HERMITIAN), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("which", ["bra", "ket"])
+def test_reference_driver_det_variants_on_these_modules(which, monkeypatch):
+    """the same for get_xr_H(bra_det=True) / (ket_det=True) as StateSpaceOptimizer/state_gradients.py:173,183 calls it"""
+    ref, restore = _reference_get_xr_result(monkeypatch)
+    try:
+        system = synth.make_det_system(which)
+        charges = system["charges"]
+        H1, H2 = ref.get_xr_H((system["symm"], system["bior"], system["nuc"]), system["densities"], 0, [charges, charges],
+                              bra_det=(which == "bra"), ket_det=(which == "ket"))
+    finally:
+        restore()
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_det_%s.npz" % which))
+    _close(H1[0], g["H1_0"])
+    _close(H1[1], g["H1_1"])
+    _close(H2, g["H2"])
