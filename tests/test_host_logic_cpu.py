@@ -454,3 +454,54 @@ def test_reference_driver_det_variants_on_these_modules(which, monkeypatch):
     _close(H1[0], g["H1_0"])
     _close(H1[1], g["H1_1"])
     _close(H2, g["H2"])
+
+
+def _xr_ccsd_recipe(order, D, dimer, monomer_in_dimer, inverse):
+    """H2 the way hermitian-XRCC/mains/xr_ccsd.py:100-185 assembles it at integer S-order `order` (any order, not only the
+    0-2 get_xr_H hard-codes): dimer(kind, active) -> matrix of the diagram lists `active` with integrals `kind`."""
+    S2 = dimer("S", {0: D.S0[0], 2: sum((D.S2[n] for n in range(1, order + 1)), [])})
+    S2H2 = dimer("ST_bior", {1: [], 2: D.ST2[order]}) + dimer("SU_bior", {1: [], 2: D.SU2[order]}) + dimer("SV_bior", {1: [], 2: D.SV2[order]})
+    S2H2 = S2H2 + dimer("ST_symm", {1: D.ST1[0], 2: sum((D.ST2[o] for o in range(order)), [])})
+    S2H2 = S2H2 + dimer("SU_symm", {1: D.SU1[0], 2: sum((D.SU2[o] for o in range(order)), [])})
+    S2H2 = S2H2 + dimer("SV_diff", {1: [], 2: D.SV2[order - 1]})
+    S2H2 = S2H2 + dimer("SV_symm", {1: D.SV1[0], 2: sum((D.SV2[o] for o in range(order - 1)), [])})
+    S2H2 = S2H2 + dimer("ST_symm", {})              # an empty selection is legal (xr_ccsd.py leaves unused families blank)
+    return inverse(S2) @ S2H2 - monomer_in_dimer()
+
+
+@pytest.mark.parametrize("order", [3, 4])
+def test_hermitian_high_order_assembly_in_the_style_of_xr_ccsd(order):
+    """mains/xr_ccsd.py drives blocks + XR_term.dimer_matrix itself with the diagram lists of S-orders 3 and 4 (8-operator
+    densities): the same recipe through this package and through the oracle"""
+    from qodeapplications_b200.hermitian import XR_term, diagrammatic_expansion, diagram_lists as D
+    from qodeapplications_b200.hermitian.diagrams import S_diagrams, ST_diagrams, SU_diagrams, SV_diagrams
+    from qodeapplications_b200.hermitian.precontract import precontract
+    from qodeapplications_b200.hermitian.tensor import Contractor, DeviceStore
+    from qodeapplications_b200.hermitian.util import struct, timer
+    from oracle import hermitian_oracle as ho
+    system = synth.make_system("toy4", ops=synth.OPS_ORDER4, with_bior=True)
+    symm, bior, dens = system["symm"], system["bior"], system["densities"][:2]
+    charges = [(a, b) for a in system["charges"] for b in system["charges"]]
+    dev = FakeDevice()
+    cache = precontract(dens, symm.S, timer(), store=DeviceStore(dev), contractor=Contractor(dev))
+    families = {"S": (symm.S, S_diagrams, ho.integrals(symm.S)),
+                "ST_symm": (struct(S=symm.S, T=symm.T), ST_diagrams, ho.integrals(symm.S, T=symm.T)),
+                "SU_symm": (struct(S=symm.S, U=symm.U), SU_diagrams, ho.integrals(symm.S, U=symm.U)),
+                "SV_symm": (struct(S=symm.S, V=symm.V), SV_diagrams, ho.integrals(symm.S, V=symm.V)),
+                "ST_bior": (struct(S=symm.S, T=bior.T), ST_diagrams, ho.integrals(symm.S, T=bior.T)),
+                "SU_bior": (struct(S=symm.S, U=bior.U), SU_diagrams, ho.integrals(symm.S, U=bior.U)),
+                "SV_bior": (struct(S=symm.S, V=bior.V), SV_diagrams, ho.integrals(symm.S, V=bior.V)),
+                "SV_diff": (struct(S=symm.S, V=bior.V_diff), SV_diagrams, ho.integrals(symm.S, V=bior.V_diff))}
+    blocks = {k: diagrammatic_expansion.blocks(densities=dens, integrals=ints, diagrams=diagrams, contract_cache=cache, timings=timer(),
+                                               precon_timings=timer()) for k, (ints, diagrams, _) in families.items()}
+    ours = _xr_ccsd_recipe(order, D,
+                           lambda kind, active: XR_term.dimer_matrix(blocks[kind], active, (0, 1), charges, timer()),
+                           lambda: sum(XR_term.dimer_matrix(blocks[k], {1: lst[0]}, (0, 1), charges, timer())
+                                       for k, lst in (("ST_symm", D.ST1), ("SU_symm", D.SU1), ("SV_symm", D.SV1))),
+                           numpy.linalg.inv)
+    ref = _xr_ccsd_recipe(order, D,
+                          lambda kind, active: ho.dimer_matrix(dens, families[kind][2], active, charges),
+                          lambda: sum(ho.dimer_matrix(dens, families[k][2], {1: lst[0]}, charges)
+                                      for k, lst in (("ST_symm", D.ST1), ("SU_symm", D.SU1), ("SV_symm", D.SV1))),
+                          numpy.linalg.inv)
+    _close(ours, ref, 1e-9)
