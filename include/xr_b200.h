@@ -99,6 +99,11 @@ int xr_sync(xr_ctx* ctx);
 int xr_launch_count(xr_ctx* ctx, int64_t* count);
 int xr_device_info(xr_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes);
 
+/* Sustained FP64 tensor-pipe rate of this device, measured now: independent DMMA.8x8x4 chains from 16 warps per SM for
+ * about `seconds` (0 < seconds <= 10), timed with CUDA events on the context's stream; synchronous.  This is the roofline
+ * denominator bench.py quotes for the tensor-bound kernels (tcgen05 has no f64 kind; MEASURED_PEAKS.json has no FP64 entry). */
+int xr_probe_fp64(xr_ctx* ctx, double seconds, double* dmma_tflops);
+
 /* Raw device memory for hosts that do not bring their own allocator. */
 int xr_malloc(xr_ctx* ctx, size_t bytes, void** dptr);
 int xr_free(xr_ctx* ctx, void* dptr);

@@ -146,7 +146,7 @@ class build_matrix_elements(object):
         self._rho_dev = {}
         self._int_dev = {}
         self._idx_dev = {}
-        self.profile = None        # set to a list to collect (label, algorithmic flops, start event, end event)
+        self.profile = None        # set to a list to collect (label, algorithmic flops, algorithmic HBM bytes, start event, end event)
         self._H1 = {}
         self._H2 = {}
         self._H3 = {}
@@ -241,8 +241,8 @@ class build_matrix_elements(object):
 
     class _timed(object):
         """records a pair of CUDA events on the launch stream around a kernel when profiling is on"""
-        def __init__(self, owner, label, flops):
-            self.owner, self.label, self.flops = owner, label, flops
+        def __init__(self, owner, label, flops, nbytes=0.0):
+            self.owner, self.label, self.flops, self.nbytes = owner, label, flops, nbytes
         def __enter__(self):
             if self.owner.profile is not None:
                 self.e0 = torch.cuda.Event(enable_timing=True)
@@ -252,7 +252,7 @@ class build_matrix_elements(object):
         def __exit__(self, *exc):
             if self.owner.profile is not None:
                 self.e1.record()
-                self.owner.profile.append((self.label, self.flops, self.e0, self.e1))
+                self.owner.profile.append((self.label, self.flops, self.nbytes, self.e0, self.e1))
             return False
 
     def drop_caches(self, densities=False):
@@ -299,26 +299,36 @@ class build_matrix_elements(object):
         return self.dev.download(self.H1_device(m))
 
     def H1_device(self, m):
+        """H1[m] on the device.  When only a bra slab of fragment m's densities is held (held=), the rows of the held
+        bra states are built and the others stay zero: the slabs of all ranks add up to the full block
+        (distributed.sharded_build sums them)."""
         rho, T, U, V, nuc, n_elec = self.data
         info = self._frag(m)
         ctx, n = self.dev.ctx, info.n_orb
         H = self.dev.zeros((info.dim, info.dim))
-        cls = _PairClass(info, 0)
+        cls = _PairClass(info, 0, self._held.get(m))
+        if cls.P == 0:
+            return H
         h = self._ints(("h1", m), lambda: (T[m, m] + U[m, m, m]).reshape(1, n * n))
         off = self._index(cls.offsets(info, info.dim, 1))
         one = self._ints(("one",), lambda: numpy.ones((1, 2)))
+        held_pos = []
         for ci, cj, i_lo, i_hi, row0 in cls.sectors:
-            N = info.n_states[ci]
-            ca = self._rho(m, "ca", (ci, cj))
-            ctx.gemm_scatter(N * N, 1, n * n, 1.0, ca, n * n, h, n * n, H, off.data_ptr() + 8 * row0, 0, None, False)
+            N = info.n_states[cj]
+            rows = (i_hi - i_lo) * N
+            ca, first = self._rho_rows(m, "ca", ci, cj, i_lo, i_hi)
+            ctx.gemm_scatter(rows, 1, n * n, 1.0, ca.data_ptr() + 8 * first, n * n, h, n * n, H, off.data_ptr() + 8 * row0, 0, None, False)
+            h_lo, h_hi = self._held_range(m, ci)
             scal = rho[m]["ccaa"][(ci, cj)]
             if isinstance(scal, torch.Tensor):      # device-resident (general.build_density_tensors(device_result=True))
-                scal = scal.reshape(N * N, 1)
+                scal = scal.reshape((h_hi - h_lo) * N, 1)
             else:
-                scal = self.dev.upload(numpy.asarray(scal, dtype=numpy.float64).reshape(N * N, 1))
-            ctx.gemm_scatter(N * N, 1, 1, 1.0, scal, 1, one, 2, H, off.data_ptr() + 8 * row0, 0, None, True)
-        diag = self._index(numpy.arange(info.dim, dtype=numpy.int64) * (info.dim + 1))
-        ctx.scatter_const(H, diag, info.dim, float(nuc[m, m]), True)
+                scal = self.dev.upload(numpy.asarray(scal, dtype=numpy.float64).reshape((h_hi - h_lo) * N, 1))
+            ctx.gemm_scatter(rows, 1, 1, 1.0, scal.data_ptr() + 8 * (i_lo - h_lo) * N, 1, one, 2, H, off.data_ptr() + 8 * row0, 0, None, True)
+            held_pos.append(info.pos[ci][i_lo:i_hi])
+        held_pos = numpy.concatenate(held_pos)
+        diag = self._index(held_pos.astype(numpy.int64) * (info.dim + 1))
+        ctx.scatter_const(H, diag, len(held_pos), float(nuc[m, m]), True)
         return H
 
     def H2(self, m1, m2):
@@ -341,7 +351,7 @@ class build_matrix_elements(object):
         for d1, c1, c2, A, B, K, ld in self._dimer_class_factors(m1, m2, (lo, hi) if bra_range is not None else None):
             off1 = self._index(lambda: c1.offsets(f1, f2.dim * D, f2.dim, bra_base=lo), ("off1", m1, m2, d1, lo, hi))
             off2 = self._index(lambda: c2.offsets(f2, D, 1), ("off2", m1, m2, d1))
-            with self._timed(self, "dimer_class_d%+d" % d1, 2.0 * c1.P * c2.P * K):
+            with self._timed(self, "dimer_class_d%+d" % d1, 2.0 * c1.P * c2.P * K, 8.0 * (c1.P * c2.P + (c1.P + c2.P) * K)):
                 ctx.gemm_scatter(c1.P, c2.P, K, 1.0, A, ld, B, ld, out, off1, 0, off2, False)
         return out
 
@@ -384,7 +394,7 @@ class build_matrix_elements(object):
                 continue
             if inspect is not None:
                 inspect(d1, A, B, c1.P, n_cols, K)
-            with self._timed(self, "dimer_stream_d%+d" % d1, 2.0 * c1.P * n_cols * K):
+            with self._timed(self, "dimer_stream_d%+d" % d1, 2.0 * c1.P * n_cols * K, 8.0 * (c1.P + n_cols) * K):
                 ctx.gemm_reduce(c1.P, n_cols, K, 1.0, A, ld, B, ld, moments.data_ptr() + 16 * (d1 + 2))
         return moments
 
@@ -594,7 +604,7 @@ class build_matrix_elements(object):
             Pa, Pb, Pc, n = fac["ck"].P, fac["cb"].P, fac["cc"].P, fac["n"]
             a_lo, a_hi = Pa * rank // world, Pa * (rank + 1) // world
             flops = 2.0 * (a_hi - a_lo) * Pb * n * n + 2.0 * (a_hi - a_lo) * Pb * Pc * n
-            with self._timed(self, "trimer_stream_%s" % cl["kind"], flops):
+            with self._timed(self, "trimer_stream_%s" % cl["kind"], flops, 8.0 * ((a_hi - a_lo) * n * n + (Pb + Pc) * n)):
                 ctx.trimer_stream(n, Pa, Pb, Pc, fac["alpha"], fac["W"], fac["ldw"], fac["beta"], fac["beta"].shape[1],
                                   fac["gamma"], fac["gamma"].shape[1], a_lo, a_hi, _lib.TRIMER_REDUCE,
                                   moments.data_ptr() + 16 * idx, None, None, None, None)
@@ -623,7 +633,7 @@ class build_matrix_elements(object):
             f = [self._frag(m) for m in ms]
             for cl in self._trimer_classes(ms):
                 Pk, Pb, Pc = (_PairClass(f[cl[r]], cl[d]).P for r, d in (("k", "dk"), ("b", "db"), ("c", "dc")))
-                n = f[cl["b"]].n_orb
+                n = max(f[cl["b"]].n_orb, f[cl["c"]].n_orb)       # the tile kernel pads both to one orbital count
                 if Pk and Pb and Pc:
                     tot_t += 2.0 * Pk * n ** 4 + 2.0 * Pk * Pb * n * n + 2.0 * Pk * Pb * Pc * n
         return tot_d + tot_t, {"dimer": tot_d, "trimer": tot_t}

@@ -53,24 +53,46 @@ class sharded_build(object):
         """the assembled H2[m1][m2] (valid on every rank after step(gather=True))"""
         return self.H2[(m1, m2)][:self.dims[m1] * self.dims[m2]]
 
-    def step(self, gather=True, after_dimers=None):
-        """One build.  after_dimers(), if given, is called once every H1/H2 launch (and all-gather) of the step has been
-        queued and before the trimer streams are: the point where a caller can start reading the assembled dimer blocks
-        back on a second stream while the (much longer) trimer phase runs."""
+    def step(self, gather=True, after_dimers=None, trimers=None, overlap=True):
+        """One build pass: every H1, every dimer block, and the trimers named by `trimers` (default: all of them; bench.py
+        passes one per step, round-robin, so that len(self.trimers) consecutive steps make one full build).
+
+        With world > 1 each dimer's all-gather is issued asynchronously (overlap=True): NCCL runs it on its own stream
+        once the slab's kernels have finished, while this rank already builds the next dimer and then streams its
+        trimer slabs; the launch stream only joins the gathers at the end of the step.  after_dimers(), if given, is called
+        once every H1/H2 launch of the step has been queued and before the trimer streams are: the point where a caller
+        can start reading ITS rows of the dimer blocks back on a second stream while the (much longer) trimer phase runs
+        (the rows of the other ranks are only guaranteed after step() returns)."""
         eng, rank, world = self.eng, self.rank, self.world
+        pending = []
         for m in range(len(self.dims)):
             self.H1[m] = eng.H1_device(m)
+            if world > 1 and m in eng._held:       # each rank built the rows of the bra slab it holds
+                dist.all_reduce(self.H1[m], group=self.group)
         for m1, m2 in self.dimers:
             lo, hi, per = slab_bounds(self.dims[m1], rank, world)
             eng.H2_device(m1, m2, bra_range=(lo, hi) if world > 1 else None, out=self.my_rows(m1, m2))
             if world > 1 and gather:
                 d2 = self.dims[m2]
                 full = self.H2[(m1, m2)]
-                dist.all_gather_into_tensor(full, full[rank * per * d2:(rank + 1) * per * d2], group=self.group)
+                work = dist.all_gather_into_tensor(full, full[rank * per * d2:(rank + 1) * per * d2], group=self.group,
+                                                   async_op=overlap)
+                if overlap:
+                    pending.append(work)
         if after_dimers is not None:
             after_dimers()
-        for ms in self.trimers:
+        for ms in (self.trimers if trimers is None else trimers):
             self.H3_moments[ms] = eng.H3_moments_device(*ms, shard=(rank, world))
+        for work in pending:
+            work.wait()        # the launch stream waits for the collective (no host block with NCCL)
+
+    def gather_bytes(self):
+        """bytes this rank RECEIVES over NVLink per step for the dimer all-gathers (the other ranks' slabs)"""
+        total = 0
+        for m1, m2 in self.dimers:
+            lo, hi, per = slab_bounds(self.dims[m1], self.rank, self.world)
+            total += (self.world - 1) * per * self.dims[m2] * self.dims[m1] * self.dims[m2] * 8
+        return total if self.world > 1 else 0
 
     def reduced_moments(self):
         """{trimer: [sum, sum of squares]} summed over classes and ranks"""

@@ -37,6 +37,7 @@ _PROTOTYPES = {
     "xr_launch_count": (_int, [_ptr, ctypes.POINTER(_i64)]),
     "xr_device_info": (_int, [_ptr, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int),
                               ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
+    "xr_probe_fp64": (_int, [_ptr, _dbl, ctypes.POINTER(_dbl)]),
     "xr_malloc": (_int, [_ptr, ctypes.c_size_t, ctypes.POINTER(_ptr)]),
     "xr_free": (_int, [_ptr, _ptr]),
     "xr_memset_zero": (_int, [_ptr, _ptr, ctypes.c_size_t]),
@@ -158,6 +159,12 @@ class Context(object):
         check(self.lib.xr_device_info(self.handle, ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor),
                                       ctypes.byref(free), ctypes.byref(total)), "xr_device_info")
         return dict(sm_count=sm.value, cc=(major.value, minor.value), free_bytes=free.value, total_bytes=total.value)
+
+    def probe_fp64(self, seconds=0.5):
+        """sustained DMMA.8x8x4 rate of this device in TFLOP/s, measured now (the tensor-roofline denominator)"""
+        out = ctypes.c_double()
+        check(self.lib.xr_probe_fp64(self.handle, float(seconds), ctypes.byref(out)), "xr_probe_fp64")
+        return out.value
 
     # ---- kernels -------------------------------------------------------------------------------
     def gemm_scatter(self, M, N, K, alpha, A, lda, B, ldb, C, offM=None, ldc=0, offN=None, accumulate=False):

@@ -53,6 +53,30 @@ def test_general_bra_slabs_host_logic():
     _close(numpy.concatenate(parts, axis=0), full, 1e-13)    # (BLAS rounding differs with the slab size; the GPU test asks for equality)
 
 
+def test_general_H1_of_held_bra_slabs_host_logic():
+    """H1_device honours held=: each slab holder builds the rows of its bra states (ccaa scalar slab included) and the
+    slabs add up to the full block; asking for states outside the slab raises instead of reading out of bounds."""
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    from qodeapplications_b200.general.distributed import balanced_shard
+    system = synth.make_system("toy5")
+    n_states = synth.CONFIGS["toy5"]["n_states"]
+    frags = system["fragments"]
+    full = build_matrix_elements(frags, system["symm"], system["nuc"], device=FakeDevice()).H1(1)
+    dim = len(frags[1].state_indices)
+    for slabs in ([(0, 2), (2, dim)], [balanced_shard(n_states, r, 3) for r in range(3)]):
+        total = numpy.zeros_like(full)
+        for held in slabs:
+            mine = list(frags)
+            mine[1] = synth.slab_fragment(frags[1], held, n_states)
+            eng = build_matrix_elements(mine, system["symm"], system["nuc"], device=FakeDevice(), held={1: held})
+            part = eng.H1(1)
+            total += part
+        _close(total, full, 1e-13)
+    eng = build_matrix_elements(mine, system["symm"], system["nuc"], device=FakeDevice(), held={1: slabs[-1]})
+    with pytest.raises(ValueError):
+        eng._rho_rows(1, "ca", 0, 0, 0, n_states[0])
+
+
 @pytest.fixture(scope="module")
 def toy1():
     return synth.make_system("toy", ops=synth.OPS_ORDER2, with_bior=True)

@@ -122,7 +122,7 @@ def main():
     eng.H2_moments_device(0, 1, shard=(rank, world), inspect=mark)
     torch.cuda.synchronize()
     phases, last = {}, begin
-    for (d1, e), (label, flops, e0, e1) in zip(marks, eng.profile):
+    for (d1, e), (label, flops, nbytes, e0, e1) in zip(marks, eng.profile):
         phases["d%+d" % d1] = {"factors_and_exchange_ms": last.elapsed_time(e), "stream_ms": e0.elapsed_time(e1),
                                "stream_tflops": flops / e0.elapsed_time(e1) / 1e9}
         last = e1
