@@ -1,7 +1,7 @@
 /* C99 host of the drop-in boundary: include/xr_b200.h must compile as plain C and libxr_b200.so must link and load without
  * Python or torch.  Built and run by tests/test_abi_cpu.py.  Exit code 0 = as expected for this machine:
  *   without a usable sm_100 device xr_ctx_create returns XR_ERR_NO_DEVICE and leaves a message (no CPU fallback);
- *   with one, a context is created, reports an sm_100 device, runs a 2x2x2 xr_gemm_scatter and is destroyed. */
+ *   with one, a context is created, reports an sm_100 device, runs a 2x2x2 xr_gemm_scatter and a legacy scalar, and is destroyed. */
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -43,6 +43,11 @@ int main(void) {
         xr_free(ctx, db);
         xr_free(ctx, dc);
         printf("device sm_%d%d, %d SMs: gemm ok\n", major, minor, sm);
+        {   /* legacy scalar ABI with HOST buffers (H_contractions.c:48): sum_pq Rca[p,q] h[p,q] = 5+12+21+32 */
+            double rca[4] = {1, 2, 3, 4}, h[4] = {5, 6, 7, 8};
+            if (monomer_1e(2, rca, h) != 70.0) return 12;
+            printf("legacy scalar ok\n");
+        }
     }
     return xr_ctx_destroy(ctx) == XR_OK ? 0 : 11;
 }

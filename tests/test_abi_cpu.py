@@ -43,10 +43,7 @@ def test_no_cpu_fallback():
         contract.monomer_1e(2, numpy.ones((2, 2)), numpy.ones((2, 2)))
 
 
-@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
-def test_c99_host_links_and_loads(tmp_path):
-    """include/xr_b200.h is plain C (gcc -std=c99 -pedantic -Werror) and a C host with no Python/torch in the process can
-    link libxr_b200.so: tests/c_host/abi_check.c reports XR_ERR_NO_DEVICE + message here (its GPU branch runs a GEMM)"""
+def _build_c99_host(tmp_path):
     import shutil
     import subprocess
     gcc = shutil.which("gcc")
@@ -58,6 +55,22 @@ def test_c99_host_links_and_loads(tmp_path):
     subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(here, "..", "include"),
                            os.path.join(here, "c_host", "abi_check.c"), "-o", exe, "-L", libdir, "-lxr_b200", "-lm",
                            "-Wl,-rpath," + libdir])
-    run = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_c99_host_links_and_loads(tmp_path):
+    """include/xr_b200.h is plain C (gcc -std=c99 -pedantic -Werror) and a C host with no Python/torch in the process can
+    link libxr_b200.so: tests/c_host/abi_check.c reports XR_ERR_NO_DEVICE + message here (its GPU branch runs a GEMM)"""
+    run = _build_c99_host(tmp_path)
     assert run.returncode == 0, run.stdout
     assert "no CPU fallback" in run.stdout
+
+
+@pytest.mark.gpu
+def test_c99_host_runs_its_gpu_branch(tmp_path):
+    """the same C99 host on a B200: context on its own stream, device info, xr_malloc/xr_upload, one xr_gemm_scatter and a
+    legacy scalar through the C ABI with no Python or torch in the process"""
+    run = _build_c99_host(tmp_path)
+    assert run.returncode == 0, run.stdout
+    assert "gemm ok" in run.stdout and "legacy scalar ok" in run.stdout, run.stdout

@@ -1,7 +1,7 @@
 """GPU parity tests for the general-XRCC path: every value computed by libxr_b200.so is compared
 with the CPU oracle (and with the golden vectors the reference itself produced).
-Tolerance (BASELINE.json north_star): |diff| <= 1e-10 * max|H_ref| per block; elements that are
-structurally zero in the reference must be exactly zero."""
+Tolerance (BASELINE.json north_star, SURVEY section 7 hard part 7): PER ELEMENT |diff| <= 1e-10 * max(|H_ref|, 1e-3 * rms of the
+block); elements that are structurally zero in the reference must be exactly zero."""
 import itertools
 import os
 import numpy
@@ -17,12 +17,17 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = 1e-10
 
 
-def _close(a, b, tol=TOL):
+def _close(a, b, tol=None):
+    """H blocks (tol=None): the per-element bar of north_star.  Kernel unit tests pass their own, much tighter, tolerance
+    relative to the largest element."""
     a, b = numpy.asarray(a), numpy.asarray(b)
     assert a.shape == b.shape
-    scale = max(numpy.abs(b).max(), 1e-300)
-    err = numpy.abs(a - b).max()
-    assert err <= tol * scale, (err, scale)
+    if tol is None:
+        floor = 1e-3 * max(float(numpy.sqrt(numpy.mean(b * b))), 1e-300) if b.size else 0.0
+        excess = numpy.abs(a - b) - 1e-10 * numpy.maximum(numpy.abs(b), floor)
+        assert b.size == 0 or excess.max() <= 0, (float(numpy.abs(a - b).max()), floor)
+    else:
+        assert b.size == 0 or numpy.abs(a - b).max() <= tol * max(numpy.abs(b).max(), 1e-300), (numpy.abs(a - b).max(), tol)
     assert numpy.all(a[b == 0] == 0), "structural zeros must stay exactly zero"
 
 
@@ -215,10 +220,11 @@ def test_cfg1_sampled_against_reference_c(dev):
     H2 = eng.H2(0, 1)
     basis = [(a, b) for a in frags[0].state_indices for b in frags[1].state_indices]
     rng = numpy.random.default_rng(2)
-    scale = numpy.abs(H2).max()
+    floor = 1e-3 * float(numpy.sqrt(numpy.mean(H2 * H2)))
     for _ in range(400):
         i, j = rng.integers(len(basis), size=2)
-        assert abs(H2[i, j] - eo.dimer((0, 1), basis[i], basis[j])) <= TOL * scale
+        ref = eo.dimer((0, 1), basis[i], basis[j]) or 0.0
+        assert abs(H2[i, j] - ref) <= TOL * max(abs(ref), floor)
 
 
 def test_bra_slab_sharding_reassembles_H2(dev):
@@ -251,7 +257,7 @@ def test_cfg3_trimer_moments_and_sampled_elements(dev):
     st = [f.state_indices for f in frags]
     dims = [len(s_) for s_ in st]
     rng = numpy.random.default_rng(4)
-    scale = float(H3.abs().max())
+    floor = 1e-3 * float((H3 * H3).mean().sqrt())
     D = dims[0] * dims[1] * dims[2]
     nz = torch.nonzero(H3.reshape(-1))[:, 0]
     picks = nz[torch.randint(len(nz), (300,), device=nz.device)].cpu().numpy()
@@ -262,7 +268,80 @@ def test_cfg3_trimer_moments_and_sampled_elements(dev):
         I = numpy.unravel_index(i, dims)
         J = numpy.unravel_index(j, dims)
         ref = eo.trimer((0, 1, 2), tuple(st[k][I[k]] for k in range(3)), tuple(st[k][J[k]] for k in range(3)))
-        assert abs(val - (ref or 0.0)) <= TOL * scale
+        assert abs(val - (ref or 0.0)) <= TOL * max(abs(ref or 0.0), floor)
+
+
+CFG4_STATES = {0: 96, +1: 34, -1: 70}
+
+
+@pytest.fixture(scope="module")
+def cfg4_three(dev):
+    """three fragments of the headline configuration (200 states each, n = 18): one dimer and one trimer at FULL size"""
+    system = synth.make_system(n_frag=3, n_orb=18, n_states=CFG4_STATES, seed=4, ops=synth.OPS_GENERAL, general_ccaa="random")
+    ref_path = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "libH_contractions_ref.so")
+    eo = go.element_oracle(system["fragments"], system["symm"], system["nuc"],
+                           go.c_contractions("ref" if os.path.exists(ref_path) else "port"))
+    return system, _engine(system, dev), eo
+
+
+@pytest.mark.timeout(900)
+def test_cfg4_size_dimer_sampled_against_reference_c(dev, cfg4_three):
+    """One dense 40 000 x 40 000 H2 of the benchmark configuration, built on the GPU exactly as bench.py builds it; 600 elements
+    (400 drawn from the charge-allowed classes, 200 anywhere) against the reference's compiled C, per element."""
+    system, eng, eo = cfg4_three
+    frags = system["fragments"]
+    H2 = eng.H2_device(0, 1)
+    D = H2.shape[0]
+    assert D == 40000
+    floor = 1e-3 * float((H2 * H2).mean().sqrt())
+    st = [f.state_indices for f in frags]
+    rng = numpy.random.default_rng(44)
+    gen = torch.Generator(device=H2.device).manual_seed(44)
+    # charge-allowed elements: rows/columns drawn uniformly, kept when non-zero on the device
+    cand = torch.randint(D * D, (4000,), device=H2.device, generator=gen)
+    vals = H2.reshape(-1)[cand]
+    nz = cand[vals != 0][:400]
+    picks = numpy.concatenate([nz.cpu().numpy(), rng.integers(D * D, size=200)])
+    got = H2.reshape(-1)[torch.from_numpy(picks).to(H2.device)].cpu().numpy()
+    d2 = len(st[1])
+    worst = 0.0
+    for flat, val in zip(picks, got):
+        i, j = divmod(int(flat), D)
+        I = (st[0][i // d2], st[1][i % d2])
+        J = (st[0][j // d2], st[1][j % d2])
+        ref = eo.dimer((0, 1), I, J) or 0.0
+        assert abs(val - ref) <= TOL * max(abs(ref), floor), (I, J, val, ref)
+        if ref == 0.0:
+            assert val == 0.0
+        else:
+            worst = max(worst, abs(val - ref) / max(abs(ref), floor))
+    assert len(nz) == 400
+    del H2
+
+
+@pytest.mark.timeout(900)
+def test_cfg4_size_trimer_class_moments_against_gram_identity(dev, cfg4_three):
+    """Every charge-transfer class of a full-size trimer (1.06e13 elements) streamed through xr_trimer_stream: the sum of
+    squares of the streamed tiles equals the exact Gram-matrix value of the class factors (O((Pa+Pb+Pc) n^4) on the host),
+    the first moment equals the factor-sum value, and two ranks' shards add up to the whole."""
+    system, eng, eo = cfg4_three
+    ms = (0, 1, 2)
+    got = eng.H3_moments(*ms, per_class=True)
+    halves = sum(eng.H3_moments(*ms, shard=(r, 2), per_class=True) for r in range(2))
+    seen = 0
+    for idx, cl in enumerate(eng._trimer_classes(ms)):
+        fac = eng._trimer_factors(ms, cl)
+        if fac is None:
+            continue
+        n = fac["n"]
+        W = dev.download(fac["W"])[:, :n * n].reshape(-1, n, n)
+        beta, gamma = dev.download(fac["beta"])[:, :n], dev.download(fac["gamma"])[:, :n]
+        total, sumsq = go.trimer_class_moments(W, beta, gamma)
+        assert abs(got[idx, 1] - sumsq) <= 1e-11 * sumsq, (idx, cl["kind"])
+        assert abs(got[idx, 0] - fac["alpha"] * total) <= 1e-9 * (sumsq * W.shape[0] * beta.shape[0] * gamma.shape[0]) ** 0.5
+        assert abs(halves[idx, 1] - got[idx, 1]) <= 1e-12 * got[idx, 1]
+        seen += 1
+    assert seen == 12
 
 
 def test_gemm_dd_newton_polish_of_an_inverse(dev):

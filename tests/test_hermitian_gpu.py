@@ -1,6 +1,7 @@
 """GPU parity tests for the hermitian-XRCC path: diagram blocks, XR_term matrices and get_xr_H computed
 by libxr_b200.so against the reference's golden vectors (toy) and the NumPy oracle (larger shapes).
-Tolerance: 1e-10 relative to the largest element of the block/matrix (BASELINE.json north_star)."""
+Tolerance (BASELINE.json north_star, SURVEY section 7 hard part 7), at every xr_order: PER ELEMENT
+|diff| <= 1e-10 * max(|H_ref|, 1e-3 * rms of the block/matrix)."""
 import os
 import numpy
 import pytest
@@ -12,11 +13,17 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _close(a, b, tol=1e-10):
+def _close(a, b, tol=None):
+    """H blocks (tol=None): the per-element bar of north_star.  Kernel unit tests pass their own, much tighter, tolerance
+    relative to the largest element."""
     a, b = numpy.asarray(a), numpy.asarray(b)
     assert a.shape == b.shape, (a.shape, b.shape)
-    scale = max(numpy.abs(b).max(), 1e-300)
-    assert numpy.abs(a - b).max() <= tol * scale, (numpy.abs(a - b).max(), scale)
+    if tol is None:
+        floor = 1e-3 * max(float(numpy.sqrt(numpy.mean(b * b))), 1e-300) if b.size else 0.0
+        excess = numpy.abs(a - b) - 1e-10 * numpy.maximum(numpy.abs(b), floor)
+        assert b.size == 0 or excess.max() <= 0, (float(numpy.abs(a - b).max()), floor)
+    else:
+        assert b.size == 0 or numpy.abs(a - b).max() <= tol * max(numpy.abs(b).max(), 1e-300), (numpy.abs(a - b).max(), tol)
 
 
 @pytest.fixture(scope="module")
@@ -78,7 +85,7 @@ def test_get_xr_H_matches_reference_golden(dev, order, ops):
     H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), system["densities"][:2], order, [charges, charges], device=dev)
     _close(H1[0], g["H1_0"])
     _close(H1[1], g["H1_1"])
-    _close(H2, g["H2"], 1e-9 if order else 1e-10)
+    _close(H2, g["H2"])
 
 
 @pytest.mark.parametrize("order", [0, 1])
@@ -114,7 +121,7 @@ def test_mid_order1_against_oracle(dev):
     H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), *args, device=dev)
     R1, R2 = ho.get_xr_H(system["symm"], system["bior"], *args)
     _close(H1[0], R1[0])
-    _close(H2, R2, 1e-9)
+    _close(H2, R2)
 
 
 def test_mid_order2_against_oracle(dev):
@@ -125,7 +132,7 @@ def test_mid_order2_against_oracle(dev):
     args = (system["densities"][:2], 2, [charges, charges])
     H1, H2 = get_xr_H((system["symm"], system["bior"], system["nuc"]), *args, device=dev)
     R1, R2 = ho.get_xr_H(system["symm"], system["bior"], *args)
-    _close(H2, R2, 1e-9)
+    _close(H2, R2)
 
 
 def test_xr_tensor_expression_syntax(dev):
@@ -194,7 +201,7 @@ def test_ragged_and_empty_charge_sectors(dev, order, ops, n_states):
     R1, R2 = ho.get_xr_H(system["symm"], system["bior"], *args)
     _close(H1[0], R1[0])
     _close(H1[1], R1[1])
-    _close(H2, R2, 1e-9 if order else 1e-10)
+    _close(H2, R2)
 
 
 @pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1)])
@@ -208,7 +215,7 @@ def test_row_sharded_get_xr_H_single_rank(dev, order, ops):
                       shard=(0, 1))
     _close(H1[0], g["H1_0"])
     _close(H1[1], g["H1_1"])
-    _close(H2, g["H2"], 1e-9 if order else 1e-10)
+    _close(H2, g["H2"])
 
 
 @pytest.mark.parametrize("rank", [0, 1, 2])
@@ -260,4 +267,4 @@ def test_factored_densities(dev):
     H1, H2 = get_xr_H((lazy2["symm"], lazy2["bior"], lazy2["nuc"]), lazy2["densities"][:2], *args, device=dev)
     R1, R2 = ho.get_xr_H(dense2["symm"], dense2["bior"], dense2["densities"][:2], *args)
     _close(H1[0], R1[0])
-    _close(H2, R2, 1e-9)
+    _close(H2, R2)
