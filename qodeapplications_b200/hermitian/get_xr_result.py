@@ -4,7 +4,8 @@
              bra_det=False, ket_det=False) -> (H1, H2)
 
 With ``bra_det`` (``ket_det``) and xr_order 0, H2 is the VECTOR over bra (ket) product states in the same final
-ordering (get_xr_result.py:343-348), as StateSpaceOptimizer/state_gradients.py:173,183 consumes it.
+ordering (get_xr_result.py:343-348), as StateSpaceOptimizer/state_gradients.py:173,183 consumes it.  At xr_order 1 and 2
+the reference itself raises with these flags (pinned by oracle/check_reference_det_orders.py), and so does this.
 
 H1 = [monomer matrix of fragment 0, of fragment 1]; H2 = dimer matrix with rows/columns ordered as
 (global state of fragment 0, global state of fragment 1), states of a fragment ordered by the charges of
@@ -45,7 +46,13 @@ def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False
     if bra_det and ket_det:
         raise NotImplementedError("bra_det and ket_det together")
     if (bra_det or ket_det) and xr_order != 0:
-        raise NotImplementedError("bra_det / ket_det are built for xr_order 0 (two-fragment diagrams) only")
+        # The reference threads both flags through its order-1 and order-2 branches (get_xr_result.py:133-296), but cannot
+        # run them: the overlap blocks it inverts are built without the flags (:65), so XR_term._evaluate_block (:62-80)
+        # adds four-index blocks into two-index arrays and numpy raises (order 1), or a non-square S2 reaches the inverse
+        # (order 2).  oracle/check_reference_det_orders.py runs the unmodified reference and records exactly that in
+        # tests/golden/reference_det_orders.json; there is no reference result to be a drop-in for.
+        raise NotImplementedError("bra_det / ket_det exist at xr_order 0 only: the reference's own get_xr_H raises for them at "
+                                  "xr_order %r (tests/golden/reference_det_orders.json)" % (xr_order,))
     if (bra_det or ket_det) and shard is not None:
         raise NotImplementedError("bra_det / ket_det with row sharding")
     diag_timer, precon_timer, matrix_timer = timer(), timer(), timer()

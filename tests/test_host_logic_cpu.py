@@ -188,6 +188,34 @@ def test_hermitian_det_variants_host_logic(which):
     _close(H2, g["H2"])
 
 
+def test_det_variants_beyond_order_0_raise_like_the_reference():
+    """the reference passes bra_det / ket_det into its order-1 and order-2 branches but raises inside them
+    (tests/golden/reference_det_orders.json = what the unmodified reference did, recorded by
+    oracle/check_reference_det_orders.py); the drop-in refuses the same combinations and serves order 0."""
+    import json
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    record = json.load(open(os.path.join(GOLDEN, "reference_det_orders.json")))
+    for which in ("bra", "ket"):
+        assert record["%s_det order 0" % which]["ok"]
+        system = synth.make_det_system(which)
+        ch = system["charges"]
+        for order in (1, 2):
+            assert not record["%s_det order %d" % (which, order)]["ok"]
+            with pytest.raises(NotImplementedError):
+                get_xr_H((system["symm"], system["bior"], system["nuc"]), system["densities"], order, [ch, ch],
+                         bra_det=(which == "bra"), ket_det=(which == "ket"), device=FakeDevice())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/hermitian-XRCC"), reason="needs the reference tree (build container only)")
+def test_reference_det_orders_fixture_is_current():
+    import json
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "check_reference_det_orders.py")
+    out = subprocess.run([sys.executable, script], stdout=subprocess.PIPE, text=True, check=True).stdout
+    assert json.loads(out) == json.load(open(os.path.join(GOLDEN, "reference_det_orders.json")))
+
+
 @pytest.mark.parametrize("name", ["toy", "toy5"])
 def test_general_streamed_dimer_moments_host_logic(name):
     """H2_moments (the consumer for dimer blocks that cannot be stored) equals the moments of the dense block"""
