@@ -209,12 +209,38 @@ int xr_density_contracted(xr_ctx* ctx, const char* ops, double* out, const doubl
  *                         is accumulated element by element from the streamed tiles; the first is linear in T and is taken
  *                         from the factor sums (sum_a sum_rs W[a,rs] (sum_b beta[b,r]) (sum_c gamma[c,s])), same value to rounding
  *   XR_TRIMER_MATERIALIZE C[offA[a] + offB[b] + offC[c]] = T[a,b,c]    (device int64 tables)
- * n <= 48. */
+ * n <= 48.
+ *
+ * Tile-consumer contract.  A consumer sees every 128 x 128 tile of T once, in DMMA accumulator registers: a lane holds
+ * T[row 32*wm + 8i + g][column 64*wn + 8j + 2t + e] (i < 4, j < 8, e < 2) of the work item (8 values of a x 16 of b) and
+ * gamma tile (128 values of c) being streamed; it may fold its elements into per-thread state (REDUCE), store them
+ * (MATERIALIZE), or emit a subset (xr_trimer_threshold, xr_trimer_sample below).  It must not block other warps: a tile's
+ * shared-memory slot is released before the consumer runs.  The reference's consumer of H3 is
+ * general-XRCC/hamiltonian.py:44-56 (excitonic.fci reads trimer couplings where >= 2 fragments change state). */
 enum xr_trimer_mode { XR_TRIMER_REDUCE = 0, XR_TRIMER_MATERIALIZE = 1 };
 int xr_trimer_stream(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int64_t Pc, double alpha,
                      const double* W, int64_t ldw, const double* beta, int64_t ldbeta,
                      const double* gamma, int64_t ldgamma, int64_t a_begin, int64_t a_end, int mode,
                      double* moments, double* C, const int64_t* offA, const int64_t* offB, const int64_t* offC);
+
+/* Compaction consumer of the same stream (screened, sparse H3): every element with |T[a,b,c]| > tau (alpha included) is
+ * appended to a COO list as (idx_out[s], val_out[s]) = (offA[a] + offB[b] + offC[c], T[a,b,c]).  *count (a DEVICE int64,
+ * zeroed by the call) receives the number of such elements; when it exceeds `capacity` only `capacity` of them were stored
+ * and the caller re-runs with a longer list.  The CONTENT of the list is reproducible, its order is not (one atomic
+ * reservation per warp and tile): sort by idx for a canonical form. */
+int xr_trimer_threshold(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int64_t Pc, double alpha,
+                        const double* W, int64_t ldw, const double* beta, int64_t ldbeta,
+                        const double* gamma, int64_t ldgamma, int64_t a_begin, int64_t a_end, double tau,
+                        const int64_t* offA, const int64_t* offB, const int64_t* offC,
+                        int64_t capacity, int64_t* idx_out, double* val_out, int64_t* count);
+
+/* Sampled-element consumer: out[s] (device) = T[abc[3s], abc[3s+1], abc[3s+2]] for a caller-given HOST list of `count`
+ * (a, b, c) triples.  Only the work items that hold a requested element are streamed, through the same tile code as every
+ * other consumer -- an element-level view into blocks that cannot be stored (the parity tests compare it with the
+ * reference's trimer_* C functions at the benchmark size). */
+int xr_trimer_sample(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int64_t Pc, double alpha,
+                     const double* W, int64_t ldw, const double* beta, int64_t ldbeta,
+                     const double* gamma, int64_t ldgamma, int64_t count, const int64_t* abc_host, double* out);
 
 #ifdef __cplusplus
 }

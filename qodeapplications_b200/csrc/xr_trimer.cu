@@ -22,6 +22,11 @@
 // k handled by DFMA on the accumulators), so n = 18 costs 18 FMA per element instead of the 20 a
 // zero-padded fifth DMMA step would; the moment reducer adds 2 FP64 ops per element on the same pipe.
 #include "xr_common.cuh"
+#include <algorithm>
+#include <utility>
+#include <vector>
+
+enum { XR_TRIMER_THRESHOLD = 2, XR_TRIMER_SAMPLE = 3 };      // internal mode numbers of the EXTRA consumers
 
 namespace {
 
@@ -64,6 +69,16 @@ struct TrimerParams {
     int64_t tiles_b, n_items;
     int c_tiles;
     int staged;             // W rows are 16-byte aligned: the producer stages each item's W/beta rows by bulk TMA
+    // ---- EXTRA consumers (template instantiations of their own: the moment / materialise stream is compiled without them)
+    const int64_t* item_list;     // SAMPLE: the work items that hold a sample (n_items = its length); null = every item
+    const int32_t* sample_ptr;    // SAMPLE: [n_items + 1] CSR over `samples`, by position in item_list
+    const int4* samples;          // SAMPLE: {row inside the item (a_local*TB + b_local), c, index into sample_out, unused}
+    double* sample_out;           // SAMPLE: [count]
+    double tau;                   // THRESHOLD: keep |alpha*T| > tau
+    unsigned long long* counter;  // THRESHOLD: number of kept elements (may exceed capacity: the caller re-runs)
+    int64_t capacity;
+    int64_t* idx_out;             // THRESHOLD: [capacity] offA[a] + offB[b] + offC[c]
+    double* val_out;              // THRESHOLD: [capacity]
 };
 
 // WN = consumer warps along c: 2 -> 8 warps, each 32 rows x 64 columns (128-column gamma tiles, 240 registers);
@@ -139,7 +154,7 @@ __device__ __forceinline__ void build_item_X(double* __restrict__ Xs, const doub
     }
 }
 
-template <int KS, int TAIL, int WN>
+template <int KS, int TAIL, int WN, bool EXTRA>
 __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_stream_kernel(const TrimerParams p) {
     using Cfg = TrimerCfg<KS, TAIL, WN>;
     const int mode = p.mode;
@@ -184,8 +199,15 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
         if (warp == CONSUMER_WARPS && lane == 0 && my_items > 0) {
             // coordinates of the next item to stage; items advance by gridDim.x
             int64_t ia = (int64_t)blockIdx.x / p.tiles_b, ib = (int64_t)blockIdx.x % p.tiles_b;
+            int64_t next_k = blockIdx.x;      // EXTRA: position in the item list of the next item to stage
             const uint32_t row_bytes = (uint32_t)(((p.n * p.n + 1) / 2 * 2) * sizeof(double));
             auto stage_item = [&]() {
+                if (EXTRA) {
+                    const int64_t id = p.item_list ? p.item_list[next_k] : next_k;
+                    ia = id / p.tiles_b;
+                    ib = id % p.tiles_b;
+                    next_k += gridDim.x;
+                }
                 const int64_t a0 = p.a_begin + ia * TA, b0 = ib * TB;
                 const int na = (int)(p.a_end - a0 < TA ? p.a_end - a0 : TA);
                 const int nb = (int)(p.Pb - b0 < TB ? p.Pb - b0 : TB);
@@ -193,10 +215,12 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
                 mbar_expect_tx(wfull, (uint32_t)na * row_bytes + beta_bytes);
                 for (int i = 0; i < na; ++i) bulk_copy_g2s(Wst + i * WS, p.W + (a0 + i) * p.ldw, row_bytes, wfull);
                 bulk_copy_g2s(Bst, p.betaP + b0 * KP, beta_bytes, wfull);
-                ib += gridDim.x;
-                while (ib >= p.tiles_b) {
-                    ib -= p.tiles_b;
-                    ++ia;
+                if (!EXTRA) {
+                    ib += gridDim.x;
+                    while (ib >= p.tiles_b) {
+                        ib -= p.tiles_b;
+                        ++ia;
+                    }
                 }
             };
             int64_t staged_items = 0, next_stage_q = SLOTS;
@@ -241,7 +265,8 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
     int64_t q = 0;
     uint32_t item_parity = 0;
 
-    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    for (int64_t item_k = blockIdx.x; item_k < p.n_items; item_k += gridDim.x) {
+        const int64_t item = EXTRA && p.item_list ? p.item_list[item_k] : item_k;
         const int64_t a0 = p.a_begin + (item / p.tiles_b) * TA;
         const int64_t b0 = (item % p.tiles_b) * TB;
         const int na = (int)(p.a_end - a0 < TA ? p.a_end - a0 : TA);
@@ -317,7 +342,77 @@ __global__ void __launch_bounds__(TrimerCfg<KS, TAIL, WN>::THREADS, 1) trimer_st
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);      // this warp no longer reads the slot
-            if (mode == XR_TRIMER_REDUCE) {
+            if (EXTRA && mode == XR_TRIMER_THRESHOLD) {
+                // compaction consumer: every lane counts its kept elements, one warp scan + ONE atomic per warp-tile reserves
+                // a contiguous run of the output list, a second pass over the accumulators fills it
+                const int64_t c_base = (int64_t)ct * CT + WCOLS * wn + 2 * t;
+                int cnt = 0;
+#pragma unroll
+                for (int i = 0; i < MI; ++i) {
+                    const int row = 32 * wm + 8 * i + g;
+                    const bool row_ok = a0 + row / TB < p.a_end && b0 + row % TB < p.Pb;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            cnt += (row_ok && c_base + 8 * j + e < p.Pc && fabs(p.alpha * acc[i][j][e]) > p.tau) ? 1 : 0;
+                }
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total > 0) {
+                    unsigned long long base = 0;
+                    if (lane == 31) base = atomicAdd(p.counter, (unsigned long long)total);
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    int64_t slot = (int64_t)base + incl - cnt;
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) {
+                        const int row = 32 * wm + 8 * i + g;
+                        const int64_t a = a0 + row / TB, b = b0 + row % TB;
+                        const bool row_ok = a < p.a_end && b < p.Pb;
+                        const int64_t oab = row_ok ? p.offA[a] + p.offB[b] : 0;
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int64_t c = c_base + 8 * j + e;
+                                const double v = p.alpha * acc[i][j][e];
+                                if (row_ok && c < p.Pc && fabs(v) > p.tau) {
+                                    if (slot < p.capacity) {
+                                        p.idx_out[slot] = oab + p.offC[c];
+                                        p.val_out[slot] = v;
+                                    }
+                                    ++slot;
+                                }
+                            }
+                    }
+                }
+            } else if (EXTRA && mode == XR_TRIMER_SAMPLE) {
+                // sampled-element consumer: the few requested elements of THIS item that fall into this gamma tile are picked
+                // out of the accumulators by the lane that owns them (acc[i][j][e] <-> row 32*wm+8i+g, column WCOLS*wn+8j+2t+e)
+                const int s_begin = p.sample_ptr[item_k], s_end = p.sample_ptr[item_k + 1];
+                for (int sidx = s_begin; sidx < s_end; ++sidx) {
+                    const int4 rec = p.samples[sidx];
+                    const int col = rec.y - ct * CT;
+                    if (col < 0 || col >= CT) continue;
+                    const int r = rec.x;
+                    if ((r >> 5) != wm || col / WCOLS != wn || (r & 7) != g || ((col & 7) >> 1) != t) continue;
+                    const int si = (r & 31) >> 3, sj = (col % WCOLS) >> 3, se = col & 1;
+                    double v = 0.0;
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e)
+                                if (i == si && j == sj && e == se) v = acc[i][j][e];
+                    p.sample_out[rec.z] = p.alpha * v;
+                }
+            } else if (mode == XR_TRIMER_REDUCE) {
 #pragma unroll
                 for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -460,9 +555,15 @@ __global__ void trimer_finalize_kernel(const double* partials, int count, const 
     }
 }
 
-template <int KS, int TAIL, int WN = 2>
+// host-side description of a sampled-element request: (a, b, c) triples, bucketed by work item in launch_trimer
+struct SampleRequest {
+    int64_t count = 0;
+    const int64_t* abc = nullptr;      // HOST [count][3]
+};
+
+template <int KS, int TAIL, bool EXTRA = false, int WN = 2>
 int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbeta, const double* gamma, int64_t ldgamma,
-                  double* moments) {
+                  double* moments, const SampleRequest* request = nullptr) {
     using Cfg = TrimerCfg<KS, TAIL, WN>;
     constexpr int CT = Cfg::CT;
     const int64_t n_a = p.a_end - p.a_begin;
@@ -470,6 +571,29 @@ int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbet
     p.tiles_b = (p.Pb + TB - 1) / TB;
     p.n_items = tiles_a * p.tiles_b;
     p.c_tiles = (int)((p.Pc + CT - 1) / CT);
+    // SAMPLE: only the work items that hold a requested element are streamed.  Samples are sorted by (item, c) on the host.
+    std::vector<int64_t> item_list;
+    std::vector<int32_t> sample_ptr;
+    std::vector<int4> records;
+    if (EXTRA && request) {
+        std::vector<std::pair<int64_t, int64_t>> order(request->count);      // (item id, sample index)
+        for (int64_t s = 0; s < request->count; ++s) {
+            const int64_t a = request->abc[3 * s] - p.a_begin, b = request->abc[3 * s + 1];
+            order[s] = {(a / TA) * p.tiles_b + b / TB, s};
+        }
+        std::sort(order.begin(), order.end());
+        for (int64_t k = 0; k < request->count; ++k) {
+            const int64_t s = order[k].second;
+            if (k == 0 || order[k].first != order[k - 1].first) {
+                item_list.push_back(order[k].first);
+                sample_ptr.push_back((int32_t)k);
+            }
+            const int64_t a = request->abc[3 * s] - p.a_begin, b = request->abc[3 * s + 1], c = request->abc[3 * s + 2];
+            records.push_back(make_int4((int)((a % TA) * TB + b % TB), (int)c, (int)s, 0));
+        }
+        sample_ptr.push_back((int32_t)request->count);
+        p.n_items = (int64_t)item_list.size();
+    }
     int grid = (int)(p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count);
 
     // scratch: packed beta | packed gamma | partials
@@ -485,7 +609,10 @@ int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbet
     const int wblocks = (int)((n_a + rows_per_block - 1) / rows_per_block);
     const size_t colsum_off = part_off + ((size_t)grid * 2 * sizeof(double) + 255) / 256 * 256;
     const size_t wpart_off = colsum_off + (2 * MAX_N * sizeof(double) + 255) / 256 * 256;
-    int rc = xr_ensure_scratch(ctx, wpart_off + (size_t)wblocks * sizeof(double) + 256);
+    const size_t items_off = wpart_off + ((size_t)wblocks * sizeof(double) + 255) / 256 * 256;
+    const size_t ptr_off = items_off + (item_list.size() * sizeof(int64_t) + 255) / 256 * 256;
+    const size_t rec_off = ptr_off + (sample_ptr.size() * sizeof(int32_t) + 255) / 256 * 256;
+    int rc = xr_ensure_scratch(ctx, rec_off + records.size() * sizeof(int4) + 256);
     if (rc != XR_OK) return rc;
     char* base = static_cast<char*>(ctx->scratch);
     double* betaP = reinterpret_cast<double*>(base + beta_off);
@@ -510,7 +637,17 @@ int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbet
     // bulk TMA needs 16-byte aligned sources: every W row is, when the base is and ldw is even (build_H pads ldw to even)
     p.staged = Cfg::STAGE && (reinterpret_cast<uintptr_t>(p.W) % 16 == 0) && (p.ldw % 2 == 0);
 
-    auto kernel = trimer_stream_kernel<KS, TAIL, WN>;
+    if (EXTRA && request) {
+        // pageable sources: the runtime stages them before cudaMemcpyAsync returns, so the vectors may go out of scope
+        XR_CUDA(cudaMemcpyAsync(base + items_off, item_list.data(), item_list.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        XR_CUDA(cudaMemcpyAsync(base + ptr_off, sample_ptr.data(), sample_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        XR_CUDA(cudaMemcpyAsync(base + rec_off, records.data(), records.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+        p.item_list = reinterpret_cast<const int64_t*>(base + items_off);
+        p.sample_ptr = reinterpret_cast<const int32_t*>(base + ptr_off);
+        p.samples = reinterpret_cast<const int4*>(base + rec_off);
+    }
+
+    auto kernel = trimer_stream_kernel<KS, TAIL, WN, EXTRA>;
     XR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     kernel<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(p);
     XR_CUDA(cudaGetLastError());
@@ -529,6 +666,38 @@ int launch_trimer(xr_ctx* ctx, TrimerParams p, const double* beta, int64_t ldbet
         ctx->launches++;
     }
     return XR_OK;
+}
+
+// k = n is covered by 4*KS DMMA k-steps + TAIL DFMA k: exactly for n <= 20 (n mod 4 = 3 rounds up to the next DMMA
+// step), in steps of 4 beyond (A fragments then come from shared memory, no tail).
+// (WN = 3, i.e. 12 consumer warps with 32x32 warp tiles, was measured too: 29.1 vs 29.9 TFLOP/s for WN = 2 at
+//  n = 18 on B200 -- the kernel is bound by its DMMA:DFMA instruction mix, not by warp-level latency hiding)
+template <bool EXTRA>
+int dispatch_trimer(xr_ctx* ctx, const TrimerParams& p, int n, const double* beta, int64_t ldbeta, const double* gamma,
+                    int64_t ldgamma, double* moments, const SampleRequest* request) {
+#define XR_TRIMER_CASE(COND, KS, TAIL) \
+    if (COND) return launch_trimer<KS, TAIL, EXTRA>(ctx, p, beta, ldbeta, gamma, ldgamma, moments, request)
+    XR_TRIMER_CASE(n <= 4, 1, 0);
+    XR_TRIMER_CASE(n == 5, 1, 1);
+    XR_TRIMER_CASE(n == 6, 1, 2);
+    XR_TRIMER_CASE(n <= 8, 2, 0);
+    XR_TRIMER_CASE(n == 9, 2, 1);
+    XR_TRIMER_CASE(n == 10, 2, 2);
+    XR_TRIMER_CASE(n <= 12, 3, 0);
+    XR_TRIMER_CASE(n == 13, 3, 1);
+    XR_TRIMER_CASE(n == 14, 3, 2);
+    XR_TRIMER_CASE(n <= 16, 4, 0);
+    XR_TRIMER_CASE(n == 17, 4, 1);
+    XR_TRIMER_CASE(n == 18, 4, 2);
+    XR_TRIMER_CASE(n <= 20, 5, 0);
+    XR_TRIMER_CASE(n <= 24, 6, 0);
+    XR_TRIMER_CASE(n <= 28, 7, 0);
+    XR_TRIMER_CASE(n <= 32, 8, 0);
+    XR_TRIMER_CASE(n <= 36, 9, 0);
+    XR_TRIMER_CASE(n <= 40, 10, 0);
+    XR_TRIMER_CASE(n <= 44, 11, 0);
+#undef XR_TRIMER_CASE
+    return launch_trimer<12, 0, EXTRA>(ctx, p, beta, ldbeta, gamma, ldgamma, moments, request);
 }
 
 }  // namespace
@@ -565,31 +734,77 @@ extern "C" int xr_trimer_stream(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int6
     p.offA = offA;
     p.offB = offB;
     p.offC = offC;
-    // k = n is covered by 4*KS DMMA k-steps + TAIL DFMA k: exactly for n <= 20 (n mod 4 = 3 rounds up to the next DMMA
-    // step), in steps of 4 beyond (A fragments then come from shared memory, no tail).
-    // (WN = 3, i.e. 12 consumer warps with 32x32 warp tiles, was measured too: 29.1 vs 29.9 TFLOP/s for WN = 2 at
-    //  n = 18 on B200 -- the kernel is bound by its DMMA:DFMA instruction mix, not by warp-level latency hiding)
-#define XR_TRIMER_CASE(COND, KS, TAIL) \
-    if (COND) return launch_trimer<KS, TAIL>(ctx, p, beta, ldbeta, gamma, ldgamma, moments)
-    XR_TRIMER_CASE(n <= 4, 1, 0);
-    XR_TRIMER_CASE(n == 5, 1, 1);
-    XR_TRIMER_CASE(n == 6, 1, 2);
-    XR_TRIMER_CASE(n <= 8, 2, 0);
-    XR_TRIMER_CASE(n == 9, 2, 1);
-    XR_TRIMER_CASE(n == 10, 2, 2);
-    XR_TRIMER_CASE(n <= 12, 3, 0);
-    XR_TRIMER_CASE(n == 13, 3, 1);
-    XR_TRIMER_CASE(n == 14, 3, 2);
-    XR_TRIMER_CASE(n <= 16, 4, 0);
-    XR_TRIMER_CASE(n == 17, 4, 1);
-    XR_TRIMER_CASE(n == 18, 4, 2);
-    XR_TRIMER_CASE(n <= 20, 5, 0);
-    XR_TRIMER_CASE(n <= 24, 6, 0);
-    XR_TRIMER_CASE(n <= 28, 7, 0);
-    XR_TRIMER_CASE(n <= 32, 8, 0);
-    XR_TRIMER_CASE(n <= 36, 9, 0);
-    XR_TRIMER_CASE(n <= 40, 10, 0);
-    XR_TRIMER_CASE(n <= 44, 11, 0);
-#undef XR_TRIMER_CASE
-    return launch_trimer<12, 0>(ctx, p, beta, ldbeta, gamma, ldgamma, moments);
+    return dispatch_trimer<false>(ctx, p, n, beta, ldbeta, gamma, ldgamma, moments, nullptr);
+}
+
+/* The compaction consumer: every element with |alpha * T[a,b,c]| > tau is appended to (idx_out, val_out) as
+ * (offA[a] + offB[b] + offC[c], value); *count (device) receives the number of such elements, which may exceed
+ * `capacity` -- then only the first `capacity` reservations were stored and the caller re-runs with a larger list. */
+extern "C" int xr_trimer_threshold(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int64_t Pc, double alpha, const double* W,
+                                   int64_t ldw, const double* beta, int64_t ldbeta, const double* gamma, int64_t ldgamma,
+                                   int64_t a_begin, int64_t a_end, double tau, const int64_t* offA, const int64_t* offB,
+                                   const int64_t* offC, int64_t capacity, int64_t* idx_out, double* val_out, int64_t* count) {
+    XR_REQUIRE(ctx, "xr_trimer_threshold: null ctx");
+    XR_REQUIRE(count, "xr_trimer_threshold: null count");
+    XR_CUDA(cudaMemsetAsync(count, 0, sizeof(int64_t), ctx->stream));
+    XR_REQUIRE(n >= 1 && n <= 48, "xr_trimer_threshold: n=%d unsupported (1..48)", n);
+    XR_REQUIRE(a_begin >= 0 && a_end <= Pa && a_begin <= a_end, "xr_trimer_threshold: bad a range [%lld,%lld) of %lld",
+               (long long)a_begin, (long long)a_end, (long long)Pa);
+    if (a_begin == a_end || Pb <= 0 || Pc <= 0) return XR_OK;
+    XR_REQUIRE(W && beta && gamma && offA && offB && offC, "xr_trimer_threshold: null operand or offset table");
+    XR_REQUIRE(capacity >= 0 && (capacity == 0 || (idx_out && val_out)), "xr_trimer_threshold: output list missing");
+    XR_REQUIRE(tau >= 0.0, "xr_trimer_threshold: tau must be >= 0");
+    XR_REQUIRE(ldw >= (int64_t)n * n && ldbeta >= n && ldgamma >= n, "xr_trimer_threshold: leading dimension too small");
+    TrimerParams p{};
+    p.n = n;
+    p.Pb = Pb;
+    p.Pc = Pc;
+    p.alpha = alpha;
+    p.W = W;
+    p.ldw = ldw;
+    p.a_begin = a_begin;
+    p.a_end = a_end;
+    p.mode = XR_TRIMER_THRESHOLD;
+    p.offA = offA;
+    p.offB = offB;
+    p.offC = offC;
+    p.tau = tau;
+    p.counter = reinterpret_cast<unsigned long long*>(count);
+    p.capacity = capacity;
+    p.idx_out = idx_out;
+    p.val_out = val_out;
+    return dispatch_trimer<true>(ctx, p, n, beta, ldbeta, gamma, ldgamma, nullptr, nullptr);
+}
+
+/* The sampled-element consumer: out[t] = alpha * T[abc[3t], abc[3t+1], abc[3t+2]] for a caller-given HOST list of triples;
+ * only the work items that hold a sample are streamed (through the same tile code as every other consumer). */
+extern "C" int xr_trimer_sample(xr_ctx* ctx, int n, int64_t Pa, int64_t Pb, int64_t Pc, double alpha, const double* W, int64_t ldw,
+                                const double* beta, int64_t ldbeta, const double* gamma, int64_t ldgamma, int64_t count,
+                                const int64_t* abc_host, double* out) {
+    XR_REQUIRE(ctx, "xr_trimer_sample: null ctx");
+    if (count <= 0) return XR_OK;
+    XR_REQUIRE(n >= 1 && n <= 48, "xr_trimer_sample: n=%d unsupported (1..48)", n);
+    XR_REQUIRE(W && beta && gamma && abc_host && out, "xr_trimer_sample: null argument");
+    XR_REQUIRE(count < (1ll << 31), "xr_trimer_sample: too many samples");
+    XR_REQUIRE(ldw >= (int64_t)n * n && ldbeta >= n && ldgamma >= n, "xr_trimer_sample: leading dimension too small");
+    for (int64_t s = 0; s < count; ++s) {
+        const int64_t a = abc_host[3 * s], b = abc_host[3 * s + 1], c = abc_host[3 * s + 2];
+        XR_REQUIRE(a >= 0 && a < Pa && b >= 0 && b < Pb && c >= 0 && c < Pc, "xr_trimer_sample: sample %lld = (%lld,%lld,%lld) out of range",
+                   (long long)s, (long long)a, (long long)b, (long long)c);
+    }
+    TrimerParams p{};
+    p.n = n;
+    p.Pb = Pb;
+    p.Pc = Pc;
+    p.alpha = alpha;
+    p.W = W;
+    p.ldw = ldw;
+    p.a_begin = 0;
+    p.a_end = Pa;
+    p.mode = XR_TRIMER_SAMPLE;
+    p.sample_out = out;
+    SampleRequest request;
+    request.count = count;
+    request.abc = abc_host;
+    return dispatch_trimer<true>(ctx, p, n, beta, ldbeta, gamma, ldgamma, nullptr, &request);
 }

@@ -610,6 +610,76 @@ class build_matrix_elements(object):
                                   moments.data_ptr() + 16 * idx, None, None, None, None)
         return moments
 
+    # ---- consumers of the streamed trimer tiles other than the moments: sampled elements, screened sparse block ----
+    def H3_elements(self, m1, m2, m3, I, J):
+        """H3[m1][m2][m3] elements <I| H |J> for lists of bra / ket state triples (each state a (charge, index) pair, as in
+        build_H.trimer, build_H.py:103) -- for blocks far too large to store: the requested elements are picked out of the
+        streamed tiles by xr_trimer_sample.  Returns a host ndarray [len(I)]; charge-forbidden elements are 0."""
+        ms = (m1, m2, m3)
+        f = [self._frag(m) for m in ms]
+        out = numpy.zeros(len(I))
+        delta = numpy.array([[i[x][0] - j[x][0] for x in range(3)] for i, j in zip(I, J)], dtype=numpy.int64).reshape(len(I), 3)
+        for cl in self._trimer_classes(ms):
+            want = numpy.zeros(3, dtype=numpy.int64)
+            want[cl["k"]], want[cl["b"]], want[cl["c"]] = cl["dk"], cl["db"], cl["dc"]
+            mine = numpy.nonzero((delta == want).all(axis=1))[0]
+            if len(mine) == 0:
+                continue
+            fac = self._trimer_factors(ms, cl)
+            if fac is None:
+                continue
+            abc = numpy.empty((len(mine), 3), dtype=numpy.int64)
+            for col, (role, cls) in enumerate(((cl["k"], fac["ck"]), (cl["b"], fac["cb"]), (cl["c"], fac["cc"]))):
+                where = {(ci, cj): (i_lo, off) for ci, cj, i_lo, i_hi, off in cls.sectors}
+                for row, t in enumerate(mine):
+                    (ci, i), (cj, j) = I[t][role], J[t][role]
+                    i_lo, off = where[(ci, cj)]
+                    abc[row, col] = off + (i - i_lo) * f[role].n_states[cj] + j
+            vals = self.dev.empty((len(mine),))
+            self.dev.ctx.trimer_sample(fac["n"], fac["ck"].P, fac["cb"].P, fac["cc"].P, fac["alpha"], fac["W"], fac["ldw"],
+                                       fac["beta"], fac["beta"].shape[1], fac["gamma"], fac["gamma"].shape[1], abc, vals)
+            out[mine] = self.dev.download(vals)
+        return out
+
+    def H3_sparse(self, m1, m2, m3, tau, capacity=1 << 22, shard=(0, 1)):
+        """Screened H3[m1][m2][m3]: (flat indices into the dense [D, D] block in test_H.py:113-126 ordering, values) of every
+        element with |H3| > tau, sorted by index (host ndarrays) -- the compaction consumer of the tile stream
+        (xr_trimer_threshold).  shard=(rank, world) restricts to this rank's slab of each class's leading pair index."""
+        ms = (m1, m2, m3)
+        f = [self._frag(m) for m in ms]
+        D = f[0].dim * f[1].dim * f[2].dim
+        stride = (f[1].dim * f[2].dim, f[2].dim, 1)
+        rank, world = shard
+        ctx = self.dev.ctx
+        count = self.dev.zeros((1,), dtype=torch.int64)
+        idx_parts, val_parts = [], []
+        for cl in self._trimer_classes(ms):
+            fac = self._trimer_factors(ms, cl)
+            if fac is None:
+                continue
+            offs = [self._index(cls.offsets(f[role], stride[role] * D, stride[role]))
+                    for role, cls in ((cl["k"], fac["ck"]), (cl["b"], fac["cb"]), (cl["c"], fac["cc"]))]
+            Pa = fac["ck"].P
+            a_lo, a_hi = Pa * rank // world, Pa * (rank + 1) // world
+            cap = int(capacity)
+            while True:
+                idx = self.dev.empty((cap,), dtype=torch.int64)
+                val = self.dev.empty((cap,))
+                ctx.trimer_threshold(fac["n"], Pa, fac["cb"].P, fac["cc"].P, fac["alpha"], fac["W"], fac["ldw"], fac["beta"],
+                                     fac["beta"].shape[1], fac["gamma"], fac["gamma"].shape[1], a_lo, a_hi, tau, offs[0], offs[1],
+                                     offs[2], cap, idx, val, count)
+                kept = int(self.dev.download(count)[0])
+                if kept <= cap:
+                    break
+                cap = kept          # the list overflowed: the count is exact, run the class again with room for all of it
+            idx_parts.append(self.dev.download(idx[:kept]))
+            val_parts.append(self.dev.download(val[:kept]))
+        if not idx_parts:
+            return numpy.zeros(0, dtype=numpy.int64), numpy.zeros(0)
+        idx, val = numpy.concatenate(idx_parts), numpy.concatenate(val_parts)
+        order = numpy.argsort(idx, kind="stable")
+        return idx[order], val[order]
+
     # ------------------------------------------------------------------- flop accounting
     def algorithmic_flops(self, dimers=(), trimers=()):
         """FP64 flops of the factored algorithm: precontractions

@@ -54,6 +54,9 @@ _PROTOTYPES = {
     "xr_permute_copy": (_int, [_ptr, _ptr, _ptr, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _dbl]),
     "xr_trimer_stream": (_int, [_ptr, _int, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _int,
                                 _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "xr_trimer_threshold": (_int, [_ptr, _int, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _dbl,
+                                   _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
+    "xr_trimer_sample": (_int, [_ptr, _int, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _ptr, _ptr]),
 }
 
 _lib = None
@@ -214,6 +217,17 @@ class Context(object):
         check(self.lib.xr_trimer_stream(self.handle, n, Pa, Pb, Pc, float(alpha), _p(W), ldw, _p(beta), ldbeta,
                                         _p(gamma), ldgamma, a_begin, a_end, mode, _p(moments), _p(C), _p(offA),
                                         _p(offB), _p(offC)), "xr_trimer_stream")
+
+    def trimer_threshold(self, n, Pa, Pb, Pc, alpha, W, ldw, beta, ldbeta, gamma, ldgamma, a_begin, a_end, tau, offA, offB, offC,
+                         capacity, idx_out, val_out, count):
+        check(self.lib.xr_trimer_threshold(self.handle, n, Pa, Pb, Pc, float(alpha), _p(W), ldw, _p(beta), ldbeta, _p(gamma), ldgamma,
+                                           a_begin, a_end, float(tau), _p(offA), _p(offB), _p(offC), capacity, _p(idx_out),
+                                           _p(val_out), _p(count)), "xr_trimer_threshold")
+
+    def trimer_sample(self, n, Pa, Pb, Pc, alpha, W, ldw, beta, ldbeta, gamma, ldgamma, abc_host, out):
+        """abc_host: C-contiguous int64 ndarray [count, 3] on the HOST; out: device doubles [count]"""
+        check(self.lib.xr_trimer_sample(self.handle, n, Pa, Pb, Pc, float(alpha), _p(W), ldw, _p(beta), ldbeta, _p(gamma), ldgamma,
+                                        len(abc_host), _p(abc_host), _p(out)), "xr_trimer_sample")
 
 
 TRIMER_REDUCE = 0

@@ -176,6 +176,37 @@ class FakeContext(object):
             at = (oa[:, None, None] + ob[None, :, None] + oc[None, None, :]).reshape(-1)
             _view(C, int(at.max()) + 1)[at] = T.reshape(-1)
 
+    def _trimer_T(self, n, Pa, Pb, Pc, alpha, W, ldw, beta, ldbeta, gamma, ldgamma, a_begin, a_end):
+        w = numpy.lib.stride_tricks.as_strided(_view(W, (Pa - 1) * ldw + n * n), (Pa, n * n), (8 * ldw, 8))[a_begin:a_end]
+        b = numpy.lib.stride_tricks.as_strided(_view(beta, (Pb - 1) * ldbeta + n), (Pb, n), (8 * ldbeta, 8))
+        g = numpy.lib.stride_tricks.as_strided(_view(gamma, (Pc - 1) * ldgamma + n), (Pc, n), (8 * ldgamma, 8))
+        return alpha * numpy.einsum("ars,br,cs->abc", w.reshape(-1, n, n), b, g, optimize=True)
+
+    def trimer_threshold(self, n, Pa, Pb, Pc, alpha, W, ldw, beta, ldbeta, gamma, ldgamma, a_begin, a_end, tau, offA, offB, offC,
+                         capacity, idx_out, val_out, count):
+        self.launches += 1
+        cnt = _view(count, 1, numpy.int64)
+        cnt[0] = 0
+        if a_begin == a_end or Pb <= 0 or Pc <= 0:
+            return
+        T = self._trimer_T(n, Pa, Pb, Pc, alpha, W, ldw, beta, ldbeta, gamma, ldgamma, a_begin, a_end)
+        oa = _view(offA, Pa, numpy.int64)[a_begin:a_end]
+        at = oa[:, None, None] + _view(offB, Pb, numpy.int64)[None, :, None] + _view(offC, Pc, numpy.int64)[None, None, :]
+        keep = numpy.abs(T) > tau
+        cnt[0] = int(keep.sum())
+        stored = min(int(cnt[0]), capacity)
+        if stored:
+            _view(idx_out, stored, numpy.int64)[...] = at[keep][:stored]
+            _view(val_out, stored)[...] = T[keep][:stored]
+
+    def trimer_sample(self, n, Pa, Pb, Pc, alpha, W, ldw, beta, ldbeta, gamma, ldgamma, abc_host, out):
+        self.launches += 1
+        if len(abc_host) == 0:
+            return
+        T = self._trimer_T(n, Pa, Pb, Pc, alpha, W, ldw, beta, ldbeta, gamma, ldgamma, 0, Pa)
+        abc = numpy.asarray(abc_host)
+        _view(out, len(abc))[...] = T[abc[:, 0], abc[:, 1], abc[:, 2]]
+
 
 class FakeDevice(object):
     """same surface as qodeapplications_b200.device.Device, on CPU torch tensors"""

@@ -127,6 +127,49 @@ def test_trimer_stream(dev, n, Pa, Pb, Pc, pad):
     assert numpy.array_equal(dev.download(mom2), got)
 
 
+@pytest.mark.parametrize("n,Pa,Pb,Pc", [(5, 3, 4, 7), (6, 400, 200, 40), (18, 130, 330, 300), (18, 70, 530, 700), (17, 9, 17, 130),
+                                        (20, 9, 40, 129), (24, 9, 20, 140), (48, 30, 100, 140)])
+def test_trimer_sample_and_threshold_consumers(dev, n, Pa, Pb, Pc):
+    """xr_trimer_sample / xr_trimer_threshold: elements picked out of, and screened from, the streamed tiles"""
+    rng = numpy.random.default_rng(n * 7 + Pa + Pb + Pc)
+    W, beta, gamma = rng.standard_normal((Pa, n * n)), rng.standard_normal((Pb, n)), rng.standard_normal((Pc, n))
+    ref = 0.5 * numpy.einsum("ars,br,cs->abc", W.reshape(Pa, n, n), beta, gamma, optimize=True)
+    ldw = n * n + (n * n) % 2
+    Wp = numpy.zeros((Pa, ldw))
+    Wp[:, :n * n] = W
+    dW, dB, dG = dev.upload(Wp), dev.upload(beta), dev.upload(gamma)
+    count = min(500, Pa * Pb * Pc)
+    abc = numpy.stack([rng.integers(Pa, size=count), rng.integers(Pb, size=count), rng.integers(Pc, size=count)], axis=1).astype(numpy.int64)
+    abc[0], abc[-1] = (0, 0, 0), (Pa - 1, Pb - 1, Pc - 1)
+    abc[1] = abc[2]                                             # a repeated request
+    out = dev.empty((count,))
+    dev.ctx.trimer_sample(n, Pa, Pb, Pc, 0.5, dW, ldw, dB, n, dG, n, numpy.ascontiguousarray(abc), out)
+    _close(dev.download(out), ref[abc[:, 0], abc[:, 1], abc[:, 2]], 1e-13 * n)
+    # screening: keep ~3 % of the elements, in a permuted layout [c, a, b], first with a list that is too short
+    tau = float(numpy.quantile(numpy.abs(ref), 0.97))
+    offA = numpy.arange(Pa, dtype=numpy.int64) * Pb
+    offB = numpy.arange(Pb, dtype=numpy.int64)
+    offC = numpy.arange(Pc, dtype=numpy.int64) * (Pa * Pb)
+    tables = [dev.upload(o, numpy.int64) for o in (offA, offB, offC)]
+    keep = numpy.flatnonzero(numpy.abs(ref.transpose(2, 0, 1).reshape(-1)) > tau)
+    cnt = dev.zeros((1,), dtype=torch.int64)
+    for cap in (max(1, len(keep) // 3), len(keep) + 5):
+        idx, val = dev.empty((cap,), dtype=torch.int64), dev.empty((cap,))
+        dev.ctx.trimer_threshold(n, Pa, Pb, Pc, 0.5, dW, ldw, dB, n, dG, n, 0, Pa, tau, tables[0], tables[1], tables[2], cap, idx, val, cnt)
+        assert int(cnt.cpu()[0]) == len(keep)
+    got_idx, got_val = idx.cpu().numpy()[:len(keep)], val.cpu().numpy()[:len(keep)]
+    order = numpy.argsort(got_idx)
+    assert numpy.array_equal(got_idx[order], keep)
+    _close(got_val[order], ref.transpose(2, 0, 1).reshape(-1)[keep], 1e-13 * n)
+    # a sub-range of a: the two halves partition the list
+    half = Pa // 2
+    total = 0
+    for lo, hi in ((0, half), (half, Pa)):
+        dev.ctx.trimer_threshold(n, Pa, Pb, Pc, 0.5, dW, ldw, dB, n, dG, n, lo, hi, tau, tables[0], tables[1], tables[2], 0, None, None, cnt)
+        total += int(cnt.cpu()[0])
+    assert total == len(keep)
+
+
 def test_legacy_scalar_abi(dev):
     """The 11 H_contractions.c symbols, same ABI, against the CPU oracle's C library."""
     from qodeapplications_b200.general.H_contractions import import_C
@@ -342,6 +385,59 @@ def test_cfg4_size_trimer_class_moments_against_gram_identity(dev, cfg4_three):
         assert abs(halves[idx, 1] - got[idx, 1]) <= 1e-12 * got[idx, 1]
         seen += 1
     assert seen == 12
+
+
+@pytest.mark.parametrize("name", ["toy3", "toyh3", "cfg3"])
+def test_trimer_consumers_against_dense_block(dev, name):
+    """H3_elements / H3_sparse (block level, all 12 classes, signs and offsets) against the materialised H3"""
+    system = synth.make_system(name)
+    eng = _engine(system, dev)
+    dense = eng.H3_device(0, 1, 2).reshape(-1)
+    st = [f.state_indices for f in system["fragments"]]
+    dims = [len(x) for x in st]
+    D = int(numpy.prod(dims))
+    rng = numpy.random.default_rng(6)
+    nz = torch.nonzero(dense)[:, 0]
+    flat = numpy.concatenate([rng.integers(D * D, size=200), nz[torch.randint(len(nz), (300,), device=nz.device)].cpu().numpy()])
+    I = [tuple(st[k][x] for k, x in enumerate(numpy.unravel_index(int(e) // D, dims))) for e in flat]
+    J = [tuple(st[k][x] for k, x in enumerate(numpy.unravel_index(int(e) % D, dims))) for e in flat]
+    want = dense[torch.from_numpy(flat).to(dense.device)].cpu().numpy()
+    assert numpy.array_equal(eng.H3_elements(0, 1, 2, I, J), want)          # the same tile arithmetic: bit-identical
+    tau = float(dense.abs().max()) * 0.5
+    idx, val = eng.H3_sparse(0, 1, 2, tau, capacity=64)
+    keep = torch.nonzero(dense.abs() > tau)[:, 0]
+    assert numpy.array_equal(idx, keep.cpu().numpy())
+    assert numpy.array_equal(val, dense[keep].cpu().numpy())
+
+
+@pytest.mark.timeout(900)
+def test_cfg4_size_trimer_elements_against_reference_c(dev, cfg4_three):
+    """Elements of a full-size trimer block (8e6 x 8e6: it cannot exist) picked out of the streamed tiles by the
+    sampled-element consumer, against the reference's compiled trimer_* C functions, per element."""
+    system, eng, eo = cfg4_three
+    frags = system["fragments"]
+    st = [f.state_indices for f in frags]
+    rng = numpy.random.default_rng(45)
+    chg = {c: [s for s in st[0] if s[0] == c] for c in CFG4_STATES}
+    I, J = [], []
+    patterns = [p for kind in ((-2, 1, 1), (2, -1, -1), (0, -1, 1)) for p in sorted(set(itertools.permutations(kind)))]
+    while len(I) < 360:
+        pat = patterns[len(I) % len(patterns)]
+        bra = [int(rng.choice(list(CFG4_STATES))) for _ in range(3)]
+        ket = [b - d for b, d in zip(bra, pat)]
+        if not all(k in CFG4_STATES for k in ket):
+            continue
+        I.append(tuple((c, int(rng.integers(CFG4_STATES[c]))) for c in bra))
+        J.append(tuple((c, int(rng.integers(CFG4_STATES[c]))) for c in ket))
+    for _ in range(40):                                           # charge-forbidden elements: exactly zero
+        I.append(tuple((0, int(rng.integers(96))) for _ in range(3)))
+        J.append(tuple((0, int(rng.integers(96))) for _ in range(3)))
+    got = eng.H3_elements(0, 1, 2, I, J)
+    ref = numpy.array([eo.trimer((0, 1, 2), i, j) or 0.0 for i, j in zip(I, J)])
+    assert numpy.count_nonzero(ref) >= 360
+    floor = 1e-3 * float(numpy.sqrt(numpy.mean(ref[ref != 0] ** 2)))
+    assert (numpy.abs(got - ref) <= TOL * numpy.maximum(numpy.abs(ref), floor)).all(), float(numpy.abs(got - ref).max())
+    assert numpy.all(got[ref == 0] == 0)
 
 
 def test_gemm_dd_newton_polish_of_an_inverse(dev):

@@ -42,6 +42,31 @@ def test_general_blocks_host_logic(name):
         assert abs(parts[0][1] + parts[1][1] - q) <= 1e-10 * q
 
 
+@pytest.mark.parametrize("name", ["toy3", "toy5", "toyh3"])
+def test_general_trimer_consumers_host_logic(name):
+    """H3_elements (sampled-element consumer) and H3_sparse (screened compaction) against the dense block"""
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    system = synth.make_system(name)
+    eng = build_matrix_elements(system["fragments"], system["symm"], system["nuc"], device=FakeDevice())
+    dense = eng.H3(0, 1, 2)
+    st = [f.state_indices for f in system["fragments"]]
+    dims = [len(x) for x in st]
+    D = int(numpy.prod(dims))
+    rng = numpy.random.default_rng(5)
+    flat = numpy.concatenate([rng.integers(D * D, size=150), rng.choice(numpy.flatnonzero(dense), size=150)])
+    I = [tuple(st[k][x] for k, x in enumerate(numpy.unravel_index(int(e) // D, dims))) for e in flat]
+    J = [tuple(st[k][x] for k, x in enumerate(numpy.unravel_index(int(e) % D, dims))) for e in flat]
+    got = eng.H3_elements(0, 1, 2, I, J)
+    _close(got, dense.reshape(-1)[flat], 1e-13)
+    tau = float(numpy.median(numpy.abs(dense[dense != 0])))
+    idx, val = eng.H3_sparse(0, 1, 2, tau, capacity=7)          # a tiny list: every class overflows once and is re-run
+    keep = numpy.flatnonzero(numpy.abs(dense.reshape(-1)) > tau)
+    assert numpy.array_equal(idx, keep)
+    _close(val, dense.reshape(-1)[keep], 1e-13)
+    parts = [eng.H3_sparse(0, 1, 2, tau, shard=(r, 2)) for r in range(2)]
+    assert numpy.array_equal(numpy.sort(numpy.concatenate([q[0] for q in parts])), keep)
+
+
 def test_general_bra_slabs_host_logic():
     from qodeapplications_b200.general.build_H import build_matrix_elements
     system = synth.make_system("toy")
