@@ -52,8 +52,9 @@ typedef double  Double;
 /* (A') The eight entry points of the reference's general-XRCC/density_tensors.c (the step before the H build, bound by
  * build_density_tensors.py:23 and called at :85-153), identical C signature: HOST pointers, z_list / configs /
  * combinatorics are arrays of per-charge-sector pointers, `storage` [n_states[bra]*n_states[ket]*(2 n_orbs)^k] is added
- * into.  `combinatorics` and `n_threads` are accepted and unused.  Errors (2*n_orbs > 64, CUDA failures) leave storage
- * untouched and set xr_last_error(). */
+ * into.  `combinatorics` and `n_threads` are accepted and unused.  The reference's signature has no error channel: on any
+ * failure (no sm_100 device, 2*n_orbs > 64, CUDA errors) the message is printed to stderr, xr_last_error() is set and the
+ * requested block of `storage` is filled with NaN -- never left as the zeros the caller allocated. */
 typedef int64_t BigInt;
 #define XR_DENSITY_ARGS Double storage[], PyInt bra_chg_idx, PyInt ket_chg_idx, BigInt n_elec[], BigInt n_states[], \
                         Double* z_list[], BigInt n_configs[], BigInt* configs[], PyInt n_orbs, PyInt n_core,         \
@@ -120,10 +121,12 @@ int xr_download(xr_ctx* ctx, void* dst_host, const void* src_device, size_t byte
  * with offM(m) = offM[m] if offM else m*ldc, offN(n) = offN[n] if offN else n.  The offset
  * tables (device int64) let the epilogue write straight into the final Hamiltonian layout
  * ([i0,i1,j0,j1] blocks, transposed permutations, charge-blocked or state_indices ordering)
- * so no transpose/packing pass exists.  FP64 DMMA (mma.sync m8n8k4) with a multi-stage
- * cp.async shared-memory pipeline; K tails are zero-filled, M/N tails predicated.
- * Requirements: A, B, C device pointers to doubles.  Rows 16-byte aligned (even lda/ldb and
- * 16-byte-aligned bases) take the vectorised path; anything else takes an 8-byte path. */
+ * so no transpose/packing pass exists.  FP64 DMMA (mma.sync m8n8k4); operand tiles reach shared
+ * memory by tensor-map TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, mbarrier ring) in persistent
+ * CTAs, K/M/N tails zero-filled by the TMA unit; products with few output tiles and a long K are split
+ * over K with a fixed-order second pass.  Requirements: A, B, C device pointers to doubles.  Rows must
+ * be 16-byte aligned (even lda/ldb, 16-byte-aligned bases) for the TMA path; anything else takes a
+ * cp.async-staged kernel with 8-byte copies (same results). */
 int xr_gemm_scatter(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
                     const double* A, int64_t lda, const double* B, int64_t ldb,
                     double* C, const int64_t* offM, int64_t ldc, const int64_t* offN, int accumulate);

@@ -10,6 +10,7 @@
 // of ket states) and sum its list in order -- no atomics, and the floating-point summation order and rounding (and so every
 // bit of the result) are the reference's.  HBM-write bound on the output (N_bra N_ket dim^k doubles).
 #include "xr_common.cuh"
+#include <cmath>
 #include <cub/device/device_scan.cuh>
 #include <mutex>
 #include <vector>
@@ -422,28 +423,32 @@ namespace {
 std::mutex g_density_mutex;
 xr_ctx* g_density_ctx = nullptr;
 
-void legacy_density(const char* ops, double* storage, int64_t bra, int64_t ket, const int64_t* n_elec, const int64_t* n_states,
-                    double* const* z_list, const int64_t* n_configs, int64_t* const* configs, int64_t n_orbs, int64_t n_core) {
+// returns false (with xr_last_error set) on any failure
+bool legacy_density_run(const char* ops, double* storage, int64_t bra, int64_t ket, const int64_t* n_elec, const int64_t* n_states,
+                        double* const* z_list, const int64_t* n_configs, int64_t* const* configs, int64_t n_orbs, int64_t n_core,
+                        int64_t* storage_elements) {
     std::lock_guard<std::mutex> lock(g_density_mutex);
-    if (!g_density_ctx && xr_ctx_create(0, nullptr, 1, &g_density_ctx) != XR_OK) return;
-    xr_ctx* ctx = g_density_ctx;
+    *storage_elements = 0;
     if (!storage || !n_elec || !n_states || !z_list || !n_configs || !configs) {
         xr_set_error("%s_tensor: null argument", ops);
-        return;
+        return false;
     }
     int k = 0;
     while (ops[k]) ++k;
     int64_t T = 1;
     for (int o = 0; o < k; ++o) T *= 2 * n_orbs;
     const int64_t nb = n_states[bra], nk = n_states[ket], cb = n_configs[bra], ck = n_configs[ket], ne = n_elec[ket];
-    if (nb <= 0 || nk <= 0 || ck <= 0) return;
+    if (nb <= 0 || nk <= 0 || ck <= 0) return true;           // an empty sector: nothing to add
+    *storage_elements = nb * nk * T;
+    if (!g_density_ctx && xr_ctx_create(0, nullptr, 1, &g_density_ctx) != XR_OK) return false;
+    xr_ctx* ctx = g_density_ctx;
     std::vector<unsigned long long> masks((size_t)ck, 0ull);
     for (int64_t Q = 0; Q < ck; ++Q)
         for (int64_t e = 0; e < ne; ++e) {
             const int64_t orb = configs[ket][Q * ne + e];
             if (orb < 0 || orb >= 64) {
                 xr_set_error("%s_tensor: orbital index %lld outside 0..63", ops, (long long)orb);
-                return;
+                return false;
             }
             masks[(size_t)Q] |= 1ull << orb;
         }
@@ -458,14 +463,32 @@ void legacy_density(const char* ops, double* storage, int64_t bra, int64_t ket, 
          cudaMemcpyAsync(d_zk, z_list[ket], bytes_zk, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
          cudaMemcpyAsync(d_m, masks.data(), bytes_m, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
     if (!ok) xr_set_error("%s_tensor: device allocation or upload failed: %s", ops, cudaGetErrorString(cudaGetLastError()));
-    if (ok && xr_density_tensor(ctx, ops, d_rho, nb, nk, d_zb, cb, d_zk, ck, reinterpret_cast<const uint64_t*>(d_m), n_elec[bra], ne,
-                                n_orbs, n_core, /*accumulate=*/1) == XR_OK) {
-        if (cudaMemcpyAsync(storage, d_rho, bytes_rho, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-            cudaStreamSynchronize(ctx->stream) != cudaSuccess)
-            xr_set_error("%s_tensor: download failed: %s", ops, cudaGetErrorString(cudaGetLastError()));
+    ok = ok && xr_density_tensor(ctx, ops, d_rho, nb, nk, d_zb, cb, d_zk, ck, reinterpret_cast<const uint64_t*>(d_m), n_elec[bra], ne,
+                                 n_orbs, n_core, /*accumulate=*/1) == XR_OK;
+    if (ok && (cudaMemcpyAsync(storage, d_rho, bytes_rho, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+               cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
+        xr_set_error("%s_tensor: download failed: %s", ops, cudaGetErrorString(cudaGetLastError()));
+        ok = false;
     }
     cudaStreamSynchronize(ctx->stream);
     cudaFree(d_rho); cudaFree(d_zb); cudaFree(d_zk); cudaFree(d_m);
+    return ok;
+}
+
+// The reference's entry points return void, so there is no error channel: a failed build must not pass as the zeros the
+// caller allocated.  On any failure the message goes to stderr and the requested block is filled with NaN.
+void legacy_density(const char* ops, double* storage, int64_t bra, int64_t ket, const int64_t* n_elec, const int64_t* n_states,
+                    double* const* z_list, const int64_t* n_configs, int64_t* const* configs, int64_t n_orbs, int64_t n_core) {
+    int64_t elements = 0;
+    if (legacy_density_run(ops, storage, bra, ket, n_elec, n_states, z_list, n_configs, configs, n_orbs, n_core, &elements)) return;
+    fprintf(stderr, "libxr_b200: %s (there is no CPU fallback; the block is filled with NaN)\n", xr_last_error());
+    if (storage && elements == 0 && n_states && n_orbs > 0) {      // the failure came before the size was known
+        int k = 0;
+        while (ops[k]) ++k;
+        elements = n_states[bra] * n_states[ket];
+        for (int o = 0; o < k; ++o) elements *= 2 * n_orbs;
+    }
+    for (int64_t e = 0; storage && e < elements; ++e) storage[e] = NAN;
 }
 
 }  // namespace

@@ -13,20 +13,10 @@
 // (BM/WARPS_M) x (BN/WARPS_N) sub-tile as 8x8 DMMA accumulators in registers.  The epilogue adds
 // two int64 offset tables, which is how results land directly in the Hamiltonian's final layout.
 #include "xr_common.cuh"
-#include <cstdlib>
 
 int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                         const double* B, int64_t ldb, double* C, const int64_t* offM, int64_t ldc, const int64_t* offN,
                         int accumulate);
-
-static bool xr_gemm_use_tma() {
-    static int mode = -1;                  // tensor-map TMA staging is the default; XR_GEMM_TMA=0 forces cp.async staging
-    if (mode < 0) {
-        const char* env = getenv("XR_GEMM_TMA");
-        mode = (env && env[0] == '0') ? 0 : 1;
-    }
-    return mode == 1;
-}
 
 namespace {
 
@@ -205,7 +195,7 @@ extern "C" int xr_gemm_scatter(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, dou
     // (16 warps) share an SM and one CTA's barriers / epilogue hide behind the others' DMMA streams.  Measured on
     // B200 against 128x128 (1 CTA/SM) and 128x64 (2 CTAs/SM) tiles: 30.7 vs 26.1 / 28.2 TFLOP/s at K=326,
     // 32.6 vs 29.9 / 32.6 at K=2304, 1.97 vs 1.48 / 1.57 TB/s of C written at K=36.
-    if (vec16 && xr_gemm_use_tma()) {
+    if (vec16) {
         // tensor-map TMA staging (xr_gemm_tma.cu); falls through to cp.async staging if no tensor map can describe the operands
         int rc = xr_gemm_scatter_tma(ctx, M, N, K, alpha, A, lda, B, ldb, C, offM, ldc, offN, accumulate);
         if (rc != XR_ERR_UNSUPPORTED) return rc;

@@ -37,6 +37,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
         : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 constexpr int TBM = 64, TBN = 64, TBK = 16, TSTAGES = 3, TTHREADS = 128;
 constexpr int TILE_A_BYTES = TBM * TBK * 8, TILE_B_BYTES = TBN * TBK * 8;     // 8 KB each, 1024-byte aligned
 constexpr int GROUP_M = 16;
@@ -205,6 +209,138 @@ gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
     }
 }
 
+// Persistent variant of the scatter mode.  A CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... and its TMA ring runs
+// ACROSS tile boundaries: thread 0 keeps TSTAGES-1 k-tiles in flight in the CTA's global k-tile sequence, so the first
+// operand tiles of tile i+1 are already landing while the warps scatter tile i, and a stage is recycled through an `empty`
+// mbarrier (one arrival per warp) instead of a block-wide barrier per k-tile.  For the short-K charge-transfer classes
+// (d = +-1: K = 2n = 36 = three k-tiles, the whole K resident in the ring) a one-tile CTA spent more time being launched,
+// fetching its tensor maps and filling its pipeline than on its 1.2 us of DMMAs.
+__global__ void __launch_bounds__(TTHREADS, 4)
+gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmTmaParams p) {
+    constexpr int MI = 4, NJ = 4;      // 2 x 2 warps, each 32 x 32
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[TSTAGES], empty[TSTAGES];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int warp_m = warp & 1, warp_n = warp >> 1;
+    const int KT = (int)((p.K + TBK - 1) / TBK);
+    const int last_ksteps = (int)((p.K - (int64_t)(KT - 1) * TBK + 3) / 4);       // real k-steps of the last k-tile (1..4)
+    const int64_t n_tiles = p.tiles_m * p.tiles_n;
+    const int64_t per_group = GROUP_M * p.tiles_n;
+    auto tile_origin = [&](int64_t tile, int64_t& m0, int64_t& n0) {      // grouped rasterisation, as in the one-tile kernel
+        const int64_t first_m = (tile / per_group) * GROUP_M;
+        const int64_t group_m = p.tiles_m - first_m < GROUP_M ? p.tiles_m - first_m : GROUP_M;
+        m0 = (first_m + (tile % per_group) % group_m) * TBM;
+        n0 = ((tile % per_group) / group_m) * TBN;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], TTHREADS / 32);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // producer state (thread 0): the next k-tile to issue in this CTA's sequence
+    const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total_q = my_tiles * KT;
+    int64_t pq = 0, ptile = blockIdx.x, pm0 = 0, pn0 = 0;
+    int pkt = 0;
+    auto issue_next = [&]() {
+        if (pq >= total_q) return;
+        const int s = (int)(pq % TSTAGES);
+        mbar_wait(&empty[s], (uint32_t)((pq / TSTAGES) & 1) ^ 1);       // passes at once on the first lap
+        if (pkt == 0) tile_origin(ptile, pm0, pn0);
+        unsigned char* a = smem + (size_t)s * (TILE_A_BYTES + TILE_B_BYTES);
+        mbar_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
+        tma_load_2d(a, &mapA, pkt * TBK, (int)pm0, &full[s]);
+        tma_load_2d(a + TILE_A_BYTES, &mapB, pkt * TBK, (int)pn0, &full[s]);
+        ++pq;
+        if (++pkt == KT) {
+            pkt = 0;
+            ptile += gridDim.x;
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES - 1; ++s) issue_next();
+    }
+
+    int64_t q = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t m0, n0;
+        tile_origin(tile, m0, n0);
+        double acc[MI][NJ][2];
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int kt = 0; kt < KT; ++kt, ++q) {
+            const int s = (int)(q % TSTAGES);
+            if (tid == 0) issue_next();                          // k-tile q + TSTAGES - 1 into the stage k-tile q - 1 used
+            mbar_wait(&full[s], (uint32_t)(q / TSTAGES) & 1);
+            const unsigned char* as = smem + (size_t)s * (TILE_A_BYTES + TILE_B_BYTES);
+            const unsigned char* bs = as + TILE_A_BYTES;
+            const int ksteps = kt == KT - 1 ? last_ksteps : TBK / 4;
+#pragma unroll
+            for (int ks = 0; ks < TBK / 4; ++ks) {
+                if (ks >= ksteps) break;
+                double a[MI], b[NJ];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const double*>(as + swz(warp_m * 32 + i * 8 + g, ks * 4 + t));
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double*>(bs + swz(warp_n * 32 + j * 8 + g, ks * 4 + t));
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&empty[s]);           // this warp no longer reads the stage
+        }
+
+        // epilogue: lane holds C[8i+g][8j+2t], C[8i+g][8j+2t+1]
+        int64_t on[NJ][2];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            int64_t col = n0 + warp_n * 32 + j * 8 + 2 * t;
+            on[j][0] = col < p.N ? (p.offN ? p.offN[col] : col) : -1;
+            on[j][1] = col + 1 < p.N ? (p.offN ? p.offN[col + 1] : col + 1) : -1;
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            int64_t row = m0 + warp_m * 32 + i * 8 + g;
+            if (row >= p.M) continue;
+            int64_t om = p.offM ? p.offM[row] : row * p.ldc;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                double* dst0 = p.C + om + on[j][0];
+                if (on[j][0] >= 0 && on[j][1] == on[j][0] + 1 && (reinterpret_cast<uintptr_t>(dst0) & 15) == 0) {
+                    double2 v = make_double2(p.alpha * acc[i][j][0], p.alpha * acc[i][j][1]);
+                    if (p.accumulate) {
+                        const double2 old = *reinterpret_cast<double2*>(dst0);
+                        v.x += old.x;
+                        v.y += old.y;
+                    }
+                    *reinterpret_cast<double2*>(dst0) = v;
+                    continue;
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (on[j][e] < 0) continue;
+                    double* dst = p.C + om + on[j][e];
+                    double v = p.alpha * acc[i][j][e];
+                    *dst = p.accumulate ? *dst + v : v;
+                }
+            }
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -291,8 +427,10 @@ int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alp
         ctx->launches += 2;
         return XR_OK;
     }
-    XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel<MODE_SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
-    gemm_tma_scatter_kernel<MODE_SCATTER><<<(unsigned)tiles, TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
+    // persistent CTAs, 4 per SM (48 KB of ring + <= 128 registers each): one launch-and-fill per CTA instead of per tile
+    const int64_t resident = (int64_t)ctx->sm_count * 4;
+    XR_CUDA(cudaFuncSetAttribute(gemm_tma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+    gemm_tma_persistent_kernel<<<(unsigned)(tiles < resident ? tiles : resident), TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
     XR_CUDA(cudaGetLastError());
     ctx->launches++;
     return XR_OK;

@@ -9,10 +9,13 @@ namespace {
 
 constexpr int DT = 16;
 
+// Error-free transformations.  Written with the _rn intrinsics, which the compiler may not contract: with plain operators
+// nvcc's default -fmad=true can fuse `p = a*b; s = hi + p` into fma(a, b, hi), after which s is no longer fl(hi + p) and
+// the compensation term is wrong.
 __device__ __forceinline__ void two_sum(double a, double b, double& s, double& e) {
-    s = a + b;
-    const double bb = s - a;
-    e = (a - (s - bb)) + (b - bb);
+    s = __dadd_rn(a, b);
+    const double bb = __dadd_rn(s, -a);
+    e = __dadd_rn(__dadd_rn(a, -__dadd_rn(s, -bb)), __dadd_rn(b, -bb));
 }
 
 // out[i,j] = C0[i,j] (or delta_ij when C0 == nullptr) + sign * sum_k A[i,k] B[k,j]
@@ -30,20 +33,20 @@ gemm_dd_kernel(int64_t M, int64_t N, int64_t K, const double* __restrict__ A, in
 #pragma unroll
         for (int k = 0; k < DT; ++k) {
             const double a = As[ty][k], b = Bs[k][tx];
-            const double p = a * b;
-            const double pe = fma(a, b, -p);          // a*b == p + pe exactly
+            const double p = __dmul_rn(a, b);
+            const double pe = __fma_rn(a, b, -p);     // a*b == p + pe exactly
             double s, se;
             two_sum(hi, p, s, se);
             hi = s;
-            lo += se + pe;
+            lo = __dadd_rn(lo, __dadd_rn(se, pe));
         }
         __syncthreads();
     }
     if (i < M && j < N) {
         const double c = C0 ? C0[i * ldc0 + j] : (i == j ? 1.0 : 0.0);
         double s, se;
-        two_sum(c, sign * hi, s, se);
-        out[i * ldo + j] = s + (se + sign * lo);
+        two_sum(c, sign * hi, s, se);          // sign = +-1: exact
+        out[i * ldo + j] = __dadd_rn(s, __dadd_rn(se, sign * lo));
     }
 }
 

@@ -256,11 +256,12 @@ def u100(X, special_processing=None):
     if pieces is None:
         return []
     res, K, which = pieces
-    res = res.host()
-    if which == "ket":
-        out = res if K is None else res @ K.host()
+    if K is not None:       # the product with the ket coefficients runs on the device like every other contraction
+        C = _contractor(X)
+        res = C.contract(res, ["a", "z"] if which == "ket" else ["z", "a"], K, ["z", "b"], ["a", "b"])
+        out = res.host()
     else:
-        out = res.T if K is None else res.T @ K.host()
+        out = res.host() if which == "ket" else res.host().T
     return out.T if special_processing in (1, 3) else out
 
 

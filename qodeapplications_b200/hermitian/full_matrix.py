@@ -19,15 +19,17 @@ def full_matrix(H1, H2, state_dict, monomer_charges, device=None, device_result=
     dev = big.dev
     big.add((0, 1), H2)
     for m in (0, 1):
-        # keep the charge-diagonal blocks only (workflow.py:221-225 adds H1[m][slice(chg), slice(chg)] per charge)
-        mask = numpy.zeros((dims[m], dims[m]))
+        # keep the charge-diagonal blocks only (workflow.py:221-225 adds H1[m][slice(chg), slice(chg)] per charge): each of them
+        # is copied into a zeroed block on the device (xr_copy2d_scaled), so no element of H1 is touched by the host
+        d = dims[m]
+        block = H1[m]
+        src = block if isinstance(block, torch.Tensor) else dev.upload(numpy.asarray(block, dtype=numpy.float64))
+        masked = dev.zeros((d, d))
         at = 0
         for chg in monomer_charges[m]:
             n = state_dict[m][chg]
-            mask[at:at + n, at:at + n] = 1.0
+            if n:
+                dev.ctx.copy2d_scaled(masked.data_ptr() + 8 * (at * d + at), d, src.data_ptr() + 8 * (at * d + at), d, n, n, 1.0)
             at += n
-        block = H1[m]
-        if isinstance(block, torch.Tensor):
-            block = dev.download(block)
-        big.add((m,), numpy.asarray(block, dtype=numpy.float64) * mask)
+        big.add((m,), masked)
     return big.matrix if device_result else dev.download(big.matrix)
