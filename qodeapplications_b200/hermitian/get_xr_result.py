@@ -29,20 +29,75 @@ from .tensor import Contractor, DeviceStore, DeviceTensor, default_device
 from .util import struct, timer
 
 
-def precise_inverse(M, dev):
-    """device tensor of M^-1: LAPACK inverse, then one Newton step with double-double products and sums on the GPU"""
-    M = numpy.ascontiguousarray(M, dtype=numpy.float64)
-    n = M.shape[0]
-    dM, dX = dev.upload(M), dev.upload(numpy.linalg.inv(M))
-    R, out = dev.empty((n, n)), dev.empty((n, n))
-    dev.ctx.gemm_dd(n, n, n, dM, n, dX, n, None, 0, -1.0, R, n)       # R = I - M X
-    dev.ctx.gemm_dd(n, n, n, dX, n, R, n, dX, n, +1.0, out, n)        # X + X R
-    return DeviceTensor(out, dev)
+NEWTON_SCHULZ_STEPS = 10
 
 
-def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False, device=None, shard=None):
+def precise_inverse(S2, dev, contractor=None):
+    """(device tensor of S2^-1, device scalar |I - S2 X|_F^2 of the result).  Entirely on the GPU, no data-dependent host
+    step (so a whole get_xr_H call is one replayable launch sequence, hermitian/plan.py): Newton-Schulz X <- X (2 I - S2 X)
+    from X = I on the FP64 tensor cores -- the dimer overlap matrix is the identity plus the overlap diagrams, so the
+    iteration contracts quadratically (NEWTON_SCHULZ_STEPS = 10 covers |I - S2| up to 0.96) -- then one more step
+    X + X (I - S2 X) carried in double-double (xr_gemm_dd), the counterpart of the extended-precision polish inside the
+    reference's qode.math.precise_numpy_inverse (get_xr_result.py:165).  The caller checks the returned residual and falls
+    back to a LAPACK starting guess when the iteration did not converge (an overlap matrix far from the identity)."""
+    contractor = contractor or Contractor(dev)
+    S = S2 if isinstance(S2, DeviceTensor) else DeviceTensor(dev.upload(numpy.ascontiguousarray(S2, dtype=numpy.float64)), dev)
+    n = S.shape[0]
+    diag = contractor._table([n], [n + 1])
+    X = dev.zeros((n, n))
+    dev.ctx.scatter_const(X, diag, n, 1.0, False)
+    for _ in range(NEWTON_SCHULZ_STEPS):
+        R = dev.empty((n, n))
+        dev.ctx.gemm_scatter(n, n, n, -1.0, S.buf, n, _transposed(X, dev, n), n, R, None, n, None, False)    # R = -S X
+        dev.ctx.scatter_const(R, diag, n, 2.0, True)                                                    # R = 2 I - S X
+        Xn = dev.empty((n, n))
+        dev.ctx.gemm_scatter(n, n, n, 1.0, X, n, _transposed(R, dev, n), n, Xn, None, n, None, False)         # X <- X R
+        X = Xn
+    return _polish(S.buf, X, dev, contractor)
+
+
+def _transposed(M, dev, n):
+    """xr_gemm_scatter contracts the TRAILING index of both operands (C = A . B^T): hand it B^T"""
+    out = dev.empty((n, n))
+    dev.ctx.permute_copy(out, M, [n, n], [1, n], 1.0)
+    return out
+
+
+def _polish(S, X, dev, contractor):
+    n = X.shape[0]
+    R, out, res = dev.empty((n, n)), dev.empty((n, n)), dev.empty((n, n))
+    dev.ctx.gemm_dd(n, n, n, S, n, X, n, None, 0, -1.0, R, n)       # R = I - S X
+    dev.ctx.gemm_dd(n, n, n, X, n, R, n, X, n, +1.0, out, n)        # X + X R
+    dev.ctx.gemm_dd(n, n, n, S, n, out, n, None, 0, -1.0, res, n)   # what is left: I - S X'
+    flat = DeviceTensor(res.reshape(n * n), dev)
+    norm2 = contractor.contract(flat, ["k"], flat, ["k"], [])
+    return DeviceTensor(out, dev), norm2
+
+
+def lapack_inverse(S2_host, dev, contractor=None):
+    """fallback when Newton-Schulz from the identity did not converge: LAPACK starting guess (host), same polish"""
+    contractor = contractor or Contractor(dev)
+    S = numpy.ascontiguousarray(S2_host, dtype=numpy.float64)
+    return _polish(dev.upload(S), dev.upload(numpy.linalg.inv(S)), dev, contractor)
+
+
+INVERSE_RESIDUAL_TOL = 1e-20        # on |I - S2 X|_F^2: the polished inverse leaves ~1e-30
+
+
+def checked_inverse(S2, dev, contractor=None):
+    """device tensor of S2^-1 for an eager (not recorded) caller: device inverse, residual checked, LAPACK start if needed"""
+    S2inv, res2 = precise_inverse(S2, dev, contractor)
+    if not float(res2.host()) <= INVERSE_RESIDUAL_TOL:
+        host = S2.host() if isinstance(S2, DeviceTensor) else S2
+        S2inv, res2 = lapack_inverse(host, dev, contractor)
+    return S2inv
+
+
+def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False, device=None, shard=None, device_result=False):
     """shard=(rank, world[, process group]): one process per GPU, each building the rows of its slab of fragment 0's bra
-    states; every rank returns the assembled (H1, H2) after one all-gather per matrix (hermitian/distributed.py)."""
+    states; every rank returns the assembled (H1, H2) after one all-gather per matrix (hermitian/distributed.py).
+    device_result=True returns DeviceTensors (H1 list, H2) plus the device scalar |I - S2 S2inv|_F^2 (None at order 0)
+    without any host synchronisation -- the form hermitian/plan.py records and replays."""
     if bra_det and ket_det:
         raise NotImplementedError("bra_det and ket_det together")
     if (bra_det or ket_det) and xr_order != 0:
@@ -91,7 +146,9 @@ def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False
                 full, M = rows.buffer(dev, 1, dims[0])
             for b, lst in ((ST, D.ST1), (SU, D.SU1), (SV, D.SV1)):
                 M = XR_term.monomer_matrix(b, {1: lst[0]}, m, monomer_charges[m], matrix_timer, device_result=True, into=M)
-            H1.append(M.host() if full is None else dev.download(rows.gather(full, 1)))
+            if full is not None:
+                M = DeviceTensor(rows.gather(full, 1), dev)
+            H1.append(M)
         return H1
 
     def dimer_sum(terms, into=None, scale=1.0):
@@ -121,35 +178,44 @@ def get_xr_H(ints, dens, xr_order, monomer_charges, bra_det=False, ket_det=False
         contractor.contract(mine_rows, ["a", "k"], assembled(S2H2), ["k", "b"], ["a", "b"], out=mine, accumulate=True)
         return assembled(out)
 
+    def inverse(active):
+        """S2^-1 on the device (Newton-Schulz + double-double polish) and its squared residual; outside a recorded trace
+        the residual is checked at once and a LAPACK starting guess takes over if the iteration did not converge"""
+        S2 = XR_term.dimer_matrix(S_blocks, active, (0, 1), all_dimer_charges, matrix_timer, ordering="final", device_result=True)
+        S2inv, res2 = precise_inverse(S2, dev, contractor)
+        if not dev.tracing and not float(res2.host()) <= INVERSE_RESIDUAL_TOL:
+            S2inv, res2 = lapack_inverse(S2.host(), dev, contractor)
+        return S2inv, res2
+
+    residual = None
     if xr_order == 0:                                   # get_xr_result.py:86-132
         H1 = monomers(ST_bior, SU_bior, SV_bior)
-        H2 = assembled(dimer_sum([(ST_bior, {2: D.ST2[0]}), (SU_bior, {2: D.SU2[0]}), (SV_bior, {2: D.SV2[0]})])).host()
+        H2 = assembled(dimer_sum([(ST_bior, {2: D.ST2[0]}), (SU_bior, {2: D.SU2[0]}), (SV_bior, {2: D.SV2[0]})]))
     elif xr_order == 1:                                 # get_xr_result.py:133-213
         SV_diff = make(struct(S=S, V=bior_ints.V_diff), SV_diagrams)
         H1 = monomers(ST_symm, SU_symm, SV_symm)
-        S2 = XR_term.dimer_matrix(S_blocks, {0: D.S0[0], 2: D.S2[1]}, (0, 1), all_dimer_charges, matrix_timer, ordering="final")
-        S2inv = precise_inverse(S2, dev)
+        S2inv, residual = inverse({0: D.S0[0], 2: D.S2[1]})
         S2H2 = dimer_sum([(ST_symm, {1: D.ST1[0], 2: D.ST2[0]}), (SU_symm, {1: D.SU1[0], 2: D.SU2[0]}),
                           (ST_bior, {2: D.ST2[1]}), (SU_bior, {2: D.SU2[1]}),
                           (SV_diff, {1: D.SV1[0], 2: D.SV2[0]}), (SV_bior, {2: D.SV2[1]})])
         # H2 = S2inv @ S2H2 - (monomer terms in the dimer basis): the subtraction is accumulated first, with
         # scale -1, and the matrix product is then added on top by the GEMM epilogue
         out = dimer_sum([(ST_symm, {1: D.ST1[0]}), (SU_symm, {1: D.SU1[0]}), (SV_symm, {1: D.SV1[0]})], scale=-1.0)
-        H2 = apply_S2inv(S2inv, S2H2, out).host()
+        H2 = apply_S2inv(S2inv, S2H2, out)
     elif xr_order == 2:                                 # get_xr_result.py:214-296
         SV_diff = make(struct(S=S, V=bior_ints.V_diff), SV_diagrams)
         H1 = monomers(ST_symm, SU_symm, SV_symm)
-        S2 = XR_term.dimer_matrix(S_blocks, {0: D.S0[0], 2: D.S2[1] + D.S2[2]}, (0, 1), all_dimer_charges, matrix_timer,
-                                  ordering="final")
-        S2inv = precise_inverse(S2, dev)
+        S2inv, residual = inverse({0: D.S0[0], 2: D.S2[1] + D.S2[2]})
         S2H2 = dimer_sum([(ST_symm, {1: D.ST1[0], 2: D.ST2[0] + D.ST2[1]}), (SU_symm, {1: D.SU1[0], 2: D.SU2[0] + D.SU2[1]}),
                           (ST_bior, {2: D.ST2[2]}), (SU_bior, {2: D.SU2[2]}),
                           (SV_symm, {1: D.SV1[0], 2: D.SV2[0]}), (SV_diff, {2: D.SV2[1]}), (SV_bior, {2: D.SV2[2]})])
         out = dimer_sum([(ST_symm, {1: D.ST1[0]}), (SU_symm, {1: D.SU1[0]}), (SV_symm, {1: D.SV1[0]})], scale=-1.0)
-        H2 = apply_S2inv(S2inv, S2H2, out).host()
+        H2 = apply_S2inv(S2inv, S2H2, out)
     else:
         raise NotImplementedError("xr order %r is not implemented" % (xr_order,))
-    return H1, H2
+    if device_result:
+        return H1, H2, residual
+    return [M.host() for M in H1], H2.host()
 
 def get_xr_S(ints, dens, xr_order, monomer_charges, device=None):
     """Dimer overlap matrix of the orbital solver -- hermitian-XRCC/get_xr_result.py:357-422 (called at

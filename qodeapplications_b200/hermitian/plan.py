@@ -1,0 +1,133 @@
+"""Record-once / replay-many ``get_xr_H`` for the loop that calls it every iteration.
+
+The reference builds the dimer Hamiltonian inside its optimiser loops (StateSpaceOptimizer/state_solver.py:64,271;
+state_gradients.py:144-183): same integrals, same state counts, new fragment densities each time.  At Be2/6-31G sizes the
+GPU work of one call is ~25 ms spread over ~1000 small launches, and the Python diagram machinery that issues them costs
+four times that.  None of that machinery depends on the VALUES of the densities: the launch sequence of a call is a pure
+function of (xr_order, charges, shapes, integrals).  So the first call of a ``plan`` runs ``get_xr_H`` once with launch
+recording on (lib.Context.begin_trace / Device.begin_trace: every xr kernel call and every zero fill, with the device
+buffers they touch kept alive), notes which device buffer each density block was uploaded into, and captures the
+recorded sequence into ONE CUDA graph.  Every later call copies the new densities into those buffers and launches the
+graph (or, where graph capture is unavailable, re-issues the recorded calls -- still without any planning).
+
+The inverse of the overlap matrix is part of the sequence (Newton-Schulz + double-double polish on the device,
+get_xr_result.precise_inverse); its residual is read back with the result and a call whose iteration did not converge is
+redone eagerly with the LAPACK starting guess.
+
+    build = plan(ints, dens, xr_order, monomer_charges, device=dev)     # records; returns after the first evaluation
+    H1, H2 = build(dens)                                                # dens: same structure, new values
+    H1, H2 = build()                                                    # densities updated in place in build.slots
+
+Not planned (they go through get_xr_H directly): bra_det / ket_det, row sharding, factored (lazy) densities.
+"""
+import numpy
+import torch
+
+from .get_xr_result import get_xr_H, INVERSE_RESIDUAL_TOL
+from .tensor import DeviceTensor, FactoredTensor, as_host, default_device
+
+_NOT_BLOCKS = ("n_elec", "n_states", "n_states_bra", "bra_offset")
+
+
+def _density_blocks(dens):
+    """[((fragment, key, sector), block)] of every tensor-valued entry of the density dictionaries"""
+    out = []
+    for m, rho in enumerate(dens):
+        for key, value in rho.items():
+            if key in _NOT_BLOCKS or not isinstance(value, dict):
+                continue
+            for sector, block in value.items():
+                out.append(((m, key, sector), block))
+    return out
+
+
+class plan(object):
+    def __init__(self, ints, dens, xr_order, monomer_charges, device=None, graph=True, verify=True):
+        self.dev = dev = device or default_device()
+        self.ints, self.xr_order, self.monomer_charges = ints, xr_order, monomer_charges
+        self.verify = verify
+        self.replays = 0
+        # 1. every density block into a buffer of its own (the input slots of the recorded sequence)
+        self.slots, resident = {}, []
+        for rho in dens:
+            resident.append({key: (dict(value) if isinstance(value, dict) else value) for key, value in rho.items()})
+        for (m, key, sector), block in _density_blocks(dens):
+            if isinstance(block, FactoredTensor) or hasattr(block, "terms") or hasattr(block, "factors"):
+                raise NotImplementedError("plan: factored (lazy) densities are evaluated eagerly by get_xr_H")
+            if isinstance(block, DeviceTensor):
+                slot = block                                  # already resident: the caller updates it in place
+            else:
+                slot = DeviceTensor(dev.upload(as_host(block)), dev)
+            self.slots[(m, key, sector)] = slot
+            resident[m][key][sector] = slot
+        self._resident = resident
+        # 2. one eager evaluation (allocates the context scratch, fills the offset-table caches), then the recorded one
+        get_xr_H(ints, resident, xr_order, monomer_charges, device=dev, device_result=True)
+        dev.begin_trace()
+        try:
+            self.H1, self.H2, self.residual = get_xr_H(ints, resident, xr_order, monomer_charges, device=dev, device_result=True)
+        finally:
+            self.trace, self._alive = dev.end_trace()
+        self.launches = len(self.trace)
+        # 3. the same sequence as one CUDA graph
+        self.graph = None
+        if graph and dev.torch_device.type == "cuda":
+            self._capture()
+
+    def _capture(self):
+        dev = self.dev
+        try:
+            stream = torch.cuda.Stream(device=dev.torch_device)
+            stream.wait_stream(torch.cuda.current_stream(dev.torch_device))
+            g = torch.cuda.CUDAGraph()
+            with dev.use_stream(stream):
+                with torch.cuda.graph(g, stream=stream):
+                    dev.ctx.replay(self.trace)
+            torch.cuda.current_stream(dev.torch_device).wait_stream(stream)
+            self.graph = g
+        except Exception as exc:          # the recorded calls can still be re-issued one by one
+            self.graph, self.graph_error = None, repr(exc)
+
+    def update(self, dens):
+        """copy new density values into the input slots (host blocks: H2D; device blocks: D2D unless they ARE the slot)"""
+        for path, block in _density_blocks(dens):
+            slot = self.slots.get(path)
+            if slot is None:
+                raise KeyError("plan: density block %r was not part of the recorded build" % (path,))
+            if block is slot:
+                continue
+            if isinstance(block, DeviceTensor):
+                if block.buf.data_ptr() != slot.buf.data_ptr():
+                    slot.buf.copy_(block.buf)
+                continue
+            host = torch.from_numpy(numpy.ascontiguousarray(as_host(block), dtype=numpy.float64))
+            if tuple(host.shape) != tuple(slot.buf.shape):
+                raise ValueError("plan: density block %r changed shape %r -> %r (record a new plan)" % (path, tuple(slot.buf.shape), tuple(host.shape)))
+            self.dev.h2d_bytes += host.numel() * 8
+            slot.buf.copy_(host, non_blocking=host.is_pinned())
+
+    def run(self):
+        """launch the recorded build; results stay on the device in self.H1 / self.H2"""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.dev.ctx.replay(self.trace)
+        self.replays += 1
+
+    def __call__(self, dens=None):
+        if dens is not None:
+            self.update(dens)
+        self.run()
+        H1, H2 = [M.host() for M in self.H1], self.H2.host()
+        redo = self.residual is not None and not float(self.residual.host()) <= INVERSE_RESIDUAL_TOL
+        if redo or (self.verify and self.replays == 1):
+            # the overlap inverse did not converge from the identity (eager path: LAPACK start), or the one-time
+            # check that the replayed sequence reproduces the eager build on the data now in the slots
+            E1, E2 = get_xr_H(self.ints, self._resident, self.xr_order, self.monomer_charges, device=self.dev)
+            if redo:
+                return E1, E2
+            scale = max(float(numpy.abs(E2).max()), 1e-300)
+            if not numpy.abs(E2 - H2).max() <= 1e-12 * scale:
+                raise RuntimeError("plan: the replayed launch sequence does not reproduce get_xr_H on new densities "
+                                   "(max diff %.3e); some input of the build was not recorded as a slot" % numpy.abs(E2 - H2).max())
+        return H1, H2

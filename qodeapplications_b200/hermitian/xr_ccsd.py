@@ -14,7 +14,7 @@ Everything is accumulated in HBM by the GEMM epilogues, as in get_xr_result.get_
 from . import diagrammatic_expansion, XR_term
 from . import diagram_lists as D
 from .diagrams import S_diagrams, ST_diagrams, SU_diagrams, SV_diagrams
-from .get_xr_result import precise_inverse
+from .get_xr_result import checked_inverse
 from .precontract import precontract
 from .tensor import Contractor, DeviceStore, default_device
 from .util import struct, timer
@@ -91,7 +91,7 @@ def build_H(ints, dens, order, monomer_charges=(0, +1, -1), device=None):
     if not explicit_S:
         return H1, S2H2.host()
     S_active = {0: D.S0[0], 2: sum((D.S2[n] for n in range(1, order + 1)), [])}
-    S2 = XR_term.dimer_matrix(blocks("S"), S_active, (0, 1), all_dimer_charges, matrix_timer, ordering="final")
+    S2 = XR_term.dimer_matrix(blocks("S"), S_active, (0, 1), all_dimer_charges, matrix_timer, ordering="final", device_result=True)
     out = dimer_sum([(blocks(family + "_symm"), mono[family]) for family in ("ST", "SU", "SV")], scale=-1.0)
-    contractor.contract(precise_inverse(S2, dev), ["a", "k"], S2H2, ["k", "b"], ["a", "b"], out=out, accumulate=True)
+    contractor.contract(checked_inverse(S2, dev, contractor), ["a", "k"], S2H2, ["k", "b"], ["a", "b"], out=out, accumulate=True)
     return H1, out.host()

@@ -122,6 +122,17 @@ def _p(x):
     raise TypeError("cannot take a pointer of %r" % type(x))
 
 
+def _recorded(method):
+    """kernel method of a Context: while a trace is being recorded (Context.begin_trace) the call is also appended to it,
+    so that the whole launch sequence of a build can be replayed without the Python planning that produced it"""
+    def call(self, *args, **kwargs):
+        if self._trace is not None:
+            self._trace.append((call, args, kwargs))
+        return method(self, *args, **kwargs)
+    call.__name__, call.__doc__ = method.__name__, method.__doc__
+    return call
+
+
 class Context(object):
     """One xr_ctx: a device plus the CUDA stream all xr kernels of this context are launched on."""
     def __init__(self, device=0, stream=None, own_stream=False):
@@ -133,6 +144,26 @@ class Context(object):
                                      1 if own_stream else 0, ctypes.byref(handle)), "xr_ctx_create")
         self.handle = handle
         self.device = int(device)
+        self._trace = None
+
+    # ---- launch-sequence recording (hermitian/plan.py): the data-independent launch list of a build, replayable as is
+    def begin_trace(self):
+        if self._trace is not None:
+            raise XRError("a trace is already being recorded on this context")
+        self._trace = []
+
+    def end_trace(self):
+        trace, self._trace = self._trace, None
+        return trace
+
+    def replay(self, trace):
+        """re-issue a recorded launch sequence (same device buffers, same arguments) on the context's current stream"""
+        for call, args, kwargs in trace:
+            call(self, *args, **kwargs)
+
+    @_recorded
+    def memset_zero(self, ptr, nbytes):
+        check(self.lib.xr_memset_zero(self.handle, _p(ptr), int(nbytes)), "xr_memset_zero")
 
     def close(self):
         if getattr(self, "handle", None):
@@ -170,17 +201,21 @@ class Context(object):
         return out.value
 
     # ---- kernels -------------------------------------------------------------------------------
+    @_recorded
     def gemm_scatter(self, M, N, K, alpha, A, lda, B, ldb, C, offM=None, ldc=0, offN=None, accumulate=False):
         check(self.lib.xr_gemm_scatter(self.handle, M, N, K, float(alpha), _p(A), lda, _p(B), ldb, _p(C), _p(offM),
                                        ldc, _p(offN), 1 if accumulate else 0), "xr_gemm_scatter")
 
+    @_recorded
     def gemm_reduce(self, M, N, K, alpha, A, lda, B, ldb, moments):
         check(self.lib.xr_gemm_reduce(self.handle, M, N, K, float(alpha), _p(A), lda, _p(B), ldb, _p(moments)), "xr_gemm_reduce")
 
+    @_recorded
     def copy2d_scaled(self, dst, dst_ld, src, src_ld, rows, cols, alpha=1.0):
         check(self.lib.xr_copy2d_scaled(self.handle, _p(dst), dst_ld, _p(src), src_ld, rows, cols, float(alpha)),
               "xr_copy2d_scaled")
 
+    @_recorded
     def permute_copy(self, dst, src, shape, src_strides, alpha=1.0):
         nd = len(shape)
         arr = _i64 * nd
@@ -200,18 +235,22 @@ class Context(object):
                                              n_configs_bra, _p(z_ket), n_configs_ket, _p(ket_masks), n_elec_bra, n_elec_ket, n_orbs,
                                              n_core, 1 if accumulate else 0), "xr_density_contracted")
 
+    @_recorded
     def gemm_dd(self, M, N, K, A, lda, B, ldb, C0, ldc0, sign, out, ldo):
         check(self.lib.xr_gemm_dd(self.handle, M, N, K, _p(A), lda, _p(B), ldb, _p(C0), ldc0, float(sign), _p(out), ldo), "xr_gemm_dd")
 
+    @_recorded
     def embed_add(self, H, src, ld, R, Cn, S, offR, offC, offS=None, dims_sub=(), min_transitions=0, alpha=1.0):
         dims = (ctypes.c_int64 * max(1, len(dims_sub)))(*[int(d) for d in dims_sub])
         check(self.lib.xr_embed_add(self.handle, _p(H), _p(src), ld, R, Cn, S, _p(offR), _p(offC), _p(offS), len(dims_sub),
                                     dims, int(min_transitions), float(alpha)), "xr_embed_add")
 
+    @_recorded
     def scatter_const(self, C, idx, count, value, accumulate=False):
         check(self.lib.xr_scatter_const(self.handle, _p(C), _p(idx), count, float(value), 1 if accumulate else 0),
               "xr_scatter_const")
 
+    @_recorded
     def trimer_stream(self, n, Pa, Pb, Pc, alpha, W, ldw, beta, ldbeta, gamma, ldgamma, a_begin, a_end, mode,
                       moments=None, C=None, offA=None, offB=None, offC=None):
         check(self.lib.xr_trimer_stream(self.handle, n, Pa, Pb, Pc, float(alpha), _p(W), ldw, _p(beta), ldbeta,

@@ -20,9 +20,33 @@ def _view(ptr, count, dtype=numpy.float64):
     return numpy.ctypeslib.as_array((ctype * int(count)).from_address(int(ptr)))
 
 
+def _recorded(method):
+    def call(self, *args, **kwargs):
+        if self._trace is not None:
+            self._trace.append((call, args, kwargs))
+        return method(self, *args, **kwargs)
+    return call
+
+
 class FakeContext(object):
     def __init__(self):
         self.launches = 0
+        self._trace = None
+
+    def begin_trace(self):
+        self._trace = []
+
+    def end_trace(self):
+        trace, self._trace = self._trace, None
+        return trace
+
+    def replay(self, trace):
+        for call, args, kwargs in trace:
+            call(self, *args, **kwargs)
+
+    @_recorded
+    def memset_zero(self, ptr, nbytes):
+        _view(ptr, nbytes // 8)[...] = 0.0
 
     def launch_count(self):
         return self.launches
@@ -30,6 +54,7 @@ class FakeContext(object):
     def sync(self):
         pass
 
+    @_recorded
     def gemm_scatter(self, M, N, K, alpha, A, lda, B, ldb, C, offM=None, ldc=0, offN=None, accumulate=False):
         self.launches += 1
         if M <= 0 or N <= 0:
@@ -48,6 +73,7 @@ class FakeContext(object):
         else:
             c[at] = val
 
+    @_recorded
     def gemm_reduce(self, M, N, K, alpha, A, lda, B, ldb, moments):
         self.launches += 1
         if M <= 0 or N <= 0:
@@ -60,6 +86,7 @@ class FakeContext(object):
         m[0] += C.sum()
         m[1] += (C * C).sum()
 
+    @_recorded
     def copy2d_scaled(self, dst, dst_ld, src, src_ld, rows, cols, alpha=1.0):
         self.launches += 1
         if rows <= 0 or cols <= 0:
@@ -104,6 +131,7 @@ class FakeContext(object):
         o = _view(out, n_bra_states * n_ket_states)
         o[...] = o + res if accumulate else res
 
+    @_recorded
     def gemm_dd(self, M, N, K, A, lda, B, ldb, C0, ldc0, sign, out, ldo):
         self.launches += 1
         if M <= 0 or N <= 0:
@@ -117,6 +145,7 @@ class FakeContext(object):
         o = numpy.lib.stride_tricks.as_strided(_view(out, (M - 1) * ldo + N), (M, N), (8 * ldo, 8))
         o[...] = (c + sign * (a @ b)).astype(numpy.float64)
 
+    @_recorded
     def embed_add(self, H, src, ld, R, Cn, S, offR, offC, offS=None, dims_sub=(), min_transitions=0, alpha=1.0):
         self.launches += 1
         if R <= 0 or Cn <= 0 or S <= 0:
@@ -134,6 +163,7 @@ class FakeContext(object):
         h = _view(H, int(at.max()) + 1)
         numpy.add.at(h, at.reshape(-1), numpy.broadcast_to(alpha * block[:, None, :], at.shape).reshape(-1))
 
+    @_recorded
     def scatter_const(self, C, idx, count, value, accumulate=False):
         self.launches += 1
         if count <= 0:
@@ -145,6 +175,7 @@ class FakeContext(object):
         else:
             c[at] = value
 
+    @_recorded
     def permute_copy(self, dst, src, shape, src_strides, alpha=1.0):
         self.launches += 1
         assert 1 <= len(shape) <= 12, "xr_permute_copy supports 1..12 dimensions"      # same limit as the CUDA kernel
@@ -156,6 +187,7 @@ class FakeContext(object):
         S = numpy.lib.stride_tricks.as_strided(s, tuple(shape), tuple(8 * x for x in src_strides))
         _view(dst, total)[...] = (alpha * S).reshape(-1)
 
+    @_recorded
     def trimer_stream(self, n, Pa, Pb, Pc, alpha, W, ldw, beta, ldbeta, gamma, ldgamma, a_begin, a_end, mode,
                       moments=None, C=None, offA=None, offB=None, offC=None):
         self.launches += 1
@@ -216,16 +248,34 @@ class FakeDevice(object):
         self.ctx = FakeContext()
         self.h2d_bytes = self.d2h_bytes = 0
         self.largest_allocation = 0          # elements of the biggest tensor ever created on this "device"
+        self._keep = None
+
+    def begin_trace(self):
+        self._keep = []
+        self.ctx.begin_trace()
+
+    def end_trace(self):
+        keep, self._keep = self._keep, None
+        return self.ctx.end_trace(), keep
+
+    @property
+    def tracing(self):
+        return self._keep is not None
 
     def _made(self, tensor):
         self.largest_allocation = max(self.largest_allocation, tensor.numel())
+        if self._keep is not None:
+            self._keep.append(tensor)
         return tensor
 
     def empty(self, shape, dtype=torch.float64):
         return self._made(torch.zeros(shape, dtype=dtype))
 
     def zeros(self, shape, dtype=torch.float64):
-        return self._made(torch.zeros(shape, dtype=dtype))
+        out = self._made(torch.zeros(shape, dtype=dtype))
+        if self._keep is not None and out.numel():
+            self.ctx.memset_zero(out, out.numel() * out.element_size())
+        return out
 
     def upload(self, array, dtype=numpy.float64):
         array = numpy.array(array, dtype=dtype, order="C", copy=True)

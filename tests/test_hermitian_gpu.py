@@ -268,3 +268,45 @@ def test_factored_densities(dev):
     R1, R2 = ho.get_xr_H(dense2["symm"], dense2["bior"], dense2["densities"][:2], *args)
     _close(H1[0], R1[0])
     _close(H2, R2)
+
+
+@pytest.mark.parametrize("name,order,ops", [("toy", 0, synth.OPS_ORDER0), ("toy", 2, synth.OPS_ORDER2), ("mid", 1, synth.OPS_ORDER1)])
+def test_plan_replays_get_xr_H_as_one_cuda_graph(dev, name, order, ops):
+    """hermitian/plan.py on the GPU: the recorded launch sequence is captured into a CUDA graph; replayed on new densities
+    it equals a fresh get_xr_H on them (bit for bit: the same kernels on the same buffers) and the oracle"""
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    from qodeapplications_b200.hermitian.plan import plan
+    system = synth.make_system(name, ops=ops, with_bior=True)
+    ch = system["charges"]
+    ints = (system["symm"], system["bior"], system["nuc"])
+    build = plan(ints, system["densities"][:2], order, [ch, ch], device=dev)
+    assert build.graph is not None, getattr(build, "graph_error", None)
+    H1, H2 = build()
+    E1, E2 = get_xr_H(ints, system["densities"][:2], order, [ch, ch], device=dev)
+    assert numpy.array_equal(H2, E2) and numpy.array_equal(H1[0], E1[0])
+    other = synth.make_system(name, ops=ops, with_bior=True, seed=78)["densities"][:2]
+    R1, R2 = build(other)
+    F1, F2 = get_xr_H(ints, other, order, [ch, ch], device=dev)
+    assert numpy.array_equal(R2, F2) and numpy.array_equal(R1[1], F1[1])
+    O1, O2 = ho.get_xr_H(system["symm"], system["bior"], other, order, [ch, ch])
+    _close(R2, O2)
+    _close(R1[0], O1[0])
+    assert numpy.array_equal(build(other)[1], R2)
+
+
+def test_device_inverse_converges_and_falls_back(dev):
+    """get_xr_result.precise_inverse: Newton-Schulz from the identity + double-double polish on the device; a matrix far
+    from the identity leaves a large residual and checked_inverse then takes the LAPACK starting guess"""
+    from qodeapplications_b200.hermitian.get_xr_result import precise_inverse, checked_inverse, INVERSE_RESIDUAL_TOL
+    rng = numpy.random.default_rng(9)
+    n = 300
+    noise = rng.standard_normal((n, n))
+    S = numpy.eye(n) + 0.3 * (noise + noise.T) / numpy.linalg.norm(noise + noise.T, 2)
+    X, res2 = precise_inverse(S, dev)
+    assert float(res2.host()) <= INVERSE_RESIDUAL_TOL
+    assert numpy.abs(X.host() @ S - numpy.eye(n)).max() <= 1e-14
+    far = 5.0 * numpy.eye(n) + noise / numpy.sqrt(n)            # |I - S| > 1: the iteration from the identity diverges
+    _, res2 = precise_inverse(far, dev)
+    assert not float(res2.host()) <= INVERSE_RESIDUAL_TOL
+    Y = checked_inverse(far, dev)
+    assert numpy.abs(Y.host() @ far - numpy.eye(n)).max() <= 1e-13

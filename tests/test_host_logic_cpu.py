@@ -617,3 +617,30 @@ def test_hermitian_xr_ccsd_build_H_host_logic(order):
     _close(H2, ho.reorder(blocked, dens, [ch, ch]), 1e-9)
     for m in (0, 1):
         _close(H1[m], sum(ho.monomer_matrix(dens, kinds[k], lst[0], m, ch) for k, lst in (("ST_symm", D.ST1), ("SU_symm", D.SU1), ("SV_symm", D.SV1))))
+
+
+@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1), (2, synth.OPS_ORDER2)])
+def test_hermitian_plan_replays_get_xr_H_on_new_densities(order, ops):
+    """hermitian/plan.py: the launch sequence recorded on one set of densities, replayed on another, equals a fresh
+    get_xr_H on the new densities (and the golden reference result on the original ones)"""
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    from qodeapplications_b200.hermitian.plan import plan
+    system = synth.make_system("toy", ops=ops, with_bior=True)
+    ch = system["charges"]
+    ints = (system["symm"], system["bior"], system["nuc"])
+    dev = FakeDevice()
+    build = plan(ints, system["densities"][:2], order, [ch, ch], device=dev)
+    assert build.launches > 10
+    H1, H2 = build()
+    g = numpy.load(os.path.join(GOLDEN, "hermitian_toy_order%d.npz" % order))
+    _close(H1[0], g["H1_0"])
+    _close(H2, g["H2"], 1e-9 if order else 1e-10)
+    # new densities of the same shapes (another seed): the replay must follow them
+    other = synth.make_system("toy", ops=ops, with_bior=True, seed=77)["densities"][:2]
+    R1, R2 = build(other)
+    E1, E2 = get_xr_H(ints, other, order, [ch, ch], device=FakeDevice())
+    _close(R2, E2, 1e-12)
+    _close(R1[1], E1[1], 1e-12)
+    assert numpy.abs(R2 - H2).max() > 1e-3 * numpy.abs(H2).max()
+    again = build(other)[1]
+    assert numpy.array_equal(again, R2)
