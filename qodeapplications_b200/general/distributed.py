@@ -6,6 +6,17 @@
 * trimers: rank r streams its slab of every class's leading pair index; the only exchange is the sum
   of 24 doubles per trimer (moments).  No data-path collective exists anywhere else.
 
+Assemble step.  The H2 all-gather moves 8 B per element against 2K flop per element of compute: at n = 18 it is
+~20x the dimer compute of a rank, and it sits in front of a trimer phase that keeps every SM busy with a persistent
+FP64 kernel (all 64 K registers of each SM).  Two ways to run it, both off the launch stream:
+
+* "nccl" (default): one all_gather_into_tensor per dimer, issued asynchronously; NCCL's kernels need SMs, so they
+  interleave with the trimer kernels at kernel boundaries;
+* "ce": the H2 buffers live in symmetric memory (torch.distributed._symmetric_memory: every rank maps every peer's buffer
+  over NVLink), and after a device-side barrier each rank PULLS the other ranks' slabs with plain device-to-device copies
+  on a side stream -- the copy engines move the data through the NVSwitch while the SMs stream trimer tiles, so the
+  gather costs the step nothing.  Falls back to "nccl" when symmetric memory cannot be set up on the box.
+
 torch.distributed is plumbing here (NCCL on GPUs, gloo in the CPU tests); the arithmetic is in
 libxr_b200.so.
 """
@@ -30,18 +41,71 @@ def balanced_shard(n_states, rank, world):
     return out
 
 
+class _peer_gather(object):
+    """Copy-engine all-gather of row slabs over NVLink peer memory (see the module docstring)."""
+    def __init__(self, dev, shapes, rank, world, group):
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world = rank, world
+        self.local, self.handle = {}, {}
+        group = group if group is not None else dist.group.WORLD
+        for key, shape in shapes.items():
+            t = symm.empty(shape, dtype=torch.float64, device=dev.torch_device)
+            self.local[key] = t
+            self.handle[key] = symm.rendezvous(t, group=group)
+        self.stream = torch.cuda.Stream(device=dev.torch_device)
+        self.done = None
+
+    def gather(self, key, rows_per_rank):
+        """called on the launch stream right after this rank's slab of `key` was queued"""
+        ready = torch.cuda.Event()
+        ready.record()
+        full, handle = self.local[key], self.handle[key]
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            handle.barrier(channel=0)                       # every rank's slab is complete
+            for step in range(1, self.world):               # staggered: at any time each rank is read by one peer
+                p = (self.rank + step) % self.world
+                theirs = handle.get_buffer(p, tuple(full.shape), torch.float64)
+                rows = slice(p * rows_per_rank, (p + 1) * rows_per_rank)
+                full[rows].copy_(theirs[rows], non_blocking=True)
+            handle.barrier(channel=1)                       # nobody rewrites its slab while a peer still reads it
+            self.done = torch.cuda.Event()
+            self.done.record()
+
+    def join(self):
+        if self.done is not None:
+            torch.cuda.current_stream().wait_event(self.done)
+            self.done = None
+
+
 class sharded_build(object):
     """Holds the output buffers of a (possibly multi-rank) build and runs one build step."""
-    def __init__(self, engine, dimers, trimers, rank=0, world=1, group=None):
+    def __init__(self, engine, dimers, trimers, rank=0, world=1, group=None, assemble="nccl"):
         self.eng, self.dimers, self.trimers = engine, list(dimers), list(trimers)
         self.rank, self.world, self.group = rank, world, group
         self.dims = [engine._frag(m).dim for m in range(len(engine._supersystem))]
         self.H1, self.H2, self.H3_moments = {}, {}, {}
         dev = engine.dev
+        shapes = {}
         for m1, m2 in self.dimers:
             lo, hi, per = slab_bounds(self.dims[m1], rank, world)
             # rows padded to world*per bra states so that all slabs have equal size; rows >= dim1*dim2 are unused
-            self.H2[(m1, m2)] = dev.empty((per * world * self.dims[m2], self.dims[m1] * self.dims[m2]))
+            shapes[(m1, m2)] = (per * world * self.dims[m2], self.dims[m1] * self.dims[m2])
+        self.peer, self.assemble, self.assemble_note = None, "nccl", None
+        if assemble == "ce" and world > 1 and dev.torch_device.type == "cuda":
+            ok = torch.ones(1, device=dev.torch_device)
+            try:
+                self.peer = _peer_gather(dev, shapes, rank, world, group)
+            except Exception as exc:         # symmetric memory is not available on every box: NCCL then
+                self.assemble_note = "symmetric memory unavailable (%s): NCCL all-gather" % (repr(exc)[:200],)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if float(ok.item()) == 0.0:
+                self.peer = None
+            else:
+                self.assemble = "ce"
+        for key, shape in shapes.items():
+            self.H2[key] = self.peer.local[key] if self.peer is not None else dev.empty(shape)
 
     def my_rows(self, m1, m2):
         """view of this rank's slab of H2[m1][m2] (only the rows that exist)"""
@@ -75,6 +139,13 @@ class sharded_build(object):
             if world > 1 and gather:
                 d2 = self.dims[m2]
                 full = self.H2[(m1, m2)]
+                if self.peer is not None:
+                    self.peer.gather((m1, m2), per * d2)      # gathers queue up in order on the peer stream
+                    if not overlap:
+                        self.peer.join()
+                    elif self.peer not in pending:
+                        pending.append(self.peer)
+                    continue
                 work = dist.all_gather_into_tensor(full, full[rank * per * d2:(rank + 1) * per * d2], group=self.group,
                                                    async_op=overlap)
                 if overlap:
@@ -84,7 +155,7 @@ class sharded_build(object):
         for ms in (self.trimers if trimers is None else trimers):
             self.H3_moments[ms] = eng.H3_moments_device(*ms, shard=(rank, world))
         for work in pending:
-            work.wait()        # the launch stream waits for the collective (no host block with NCCL)
+            (work.join if work is self.peer else work.wait)()        # the launch stream waits for the collective (no host block)
 
     def gather_bytes(self):
         """bytes this rank RECEIVES over NVLink per step for the dimer all-gathers (the other ranks' slabs)"""

@@ -25,6 +25,7 @@ def _recorded(method):
         if self._trace is not None:
             self._trace.append((call, args, kwargs))
         return method(self, *args, **kwargs)
+    call.__name__ = method.__name__
     return call
 
 
