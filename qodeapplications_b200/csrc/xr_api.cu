@@ -57,6 +57,7 @@ extern "C" int xr_ctx_destroy(xr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -17,6 +17,7 @@ struct xr_ctx {
     size_t scratch_bytes = 0;
     void* pinned = nullptr;      // small pinned host staging (legacy scalars)
     size_t pinned_bytes = 0;
+    void* counters = nullptr;    // a few device words for kernels that hand out work dynamically
 };
 
 void xr_set_error(const char* fmt, ...);

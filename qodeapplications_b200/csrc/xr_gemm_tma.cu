@@ -25,6 +25,7 @@ struct GemmTmaParams {
     double* partials;      // REDUCE mode: [tiles][2] per-CTA (sum, sum of squares); nothing is stored to C
     int kt_per_split;      // SPLITK mode: k-tiles per blockIdx.y slice; raw partial tiles go to ws[split][M][N]
     double* ws;
+    unsigned long long* tile_counter;      // persistent kernel, dynamic scheduling: next tile to hand out (zeroed per launch)
 };
 
 enum { MODE_SCATTER = 0, MODE_REDUCE = 1, MODE_SPLITK = 2 };
@@ -40,6 +41,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+// XR_GEMM_VARIANT (build-time only; tools/gemm_variants.py builds one library per value and times them in one GPU call):
+//   0  one output tile per CTA (gemm_tma_scatter_kernel<MODE_SCATTER>)
+//   1  persistent CTAs, static tile striding, thread 0 issues every TMA load
+//   2  persistent, static, the issuing duty rotates over the four warps (one sub-core is not always the late one)
+//   3  persistent, tiles handed out by an atomic counter (thread 0 issues), so faster SMs take more tiles
+#ifndef XR_GEMM_VARIANT
+#define XR_GEMM_VARIANT 1
+#endif
+// ... and the K range the persistent kernel is used for (k-tiles of 16): below/above, the one-tile kernel
+#ifndef XR_GEMM_PERSISTENT_MAX_KT
+#define XR_GEMM_PERSISTENT_MAX_KT 1000000
+#endif
 
 constexpr int TBM = 64, TBN = 64, TBK = 16, TSTAGES = 3, TTHREADS = 128;
 constexpr int TILE_A_BYTES = TBM * TBK * 8, TILE_B_BYTES = TBN * TBK * 8;     // 8 KB each, 1024-byte aligned
@@ -245,32 +259,58 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     }
     __syncthreads();
 
-    // producer state (thread 0): the next k-tile to issue in this CTA's sequence
+    constexpr bool ROTATE = XR_GEMM_VARIANT == 2, DYNAMIC = XR_GEMM_VARIANT == 3;
+    __shared__ int64_t tile_ring[4];       // DYNAMIC: tile ids in hand-out order (-1 = no more), written by the issuer
+
+    // producer state: the next k-tile to issue in this CTA's sequence.  Kept by EVERY thread (it is a function of the
+    // step count alone), so that the issuing duty can move between warps; only the elected thread touches barriers / TMA.
     const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total_q = my_tiles * KT;
-    int64_t pq = 0, ptile = blockIdx.x, pm0 = 0, pn0 = 0;
+    int64_t pq = 0, ptile = blockIdx.x, pm0 = 0, pn0 = 0, pseq = 0;
     int pkt = 0;
+    bool drained = false;                  // DYNAMIC: the counter ran past the last tile (issuer's knowledge)
     auto issue_next = [&]() {
-        if (pq >= total_q) return;
+        if (DYNAMIC ? drained : pq >= total_q) return;
+        const bool elected = ROTATE ? tid == 32 * (int)(pq % (TTHREADS / 32)) : tid == 0;
         const int s = (int)(pq % TSTAGES);
-        mbar_wait(&empty[s], (uint32_t)((pq / TSTAGES) & 1) ^ 1);       // passes at once on the first lap
+        if (elected) {
+            mbar_wait(&empty[s], (uint32_t)((pq / TSTAGES) & 1) ^ 1);       // passes at once on the first lap
+            if (DYNAMIC && pkt == 0) {
+                ptile = (int64_t)atomicAdd(p.tile_counter, 1ull);
+                if (ptile >= n_tiles) ptile = -1;
+                tile_ring[pseq & 3] = ptile;                                // published by the barrier arrival below
+            }
+        }
+        if (DYNAMIC && ptile < 0) {        // (only the issuer runs the dynamic producer: ptile is its own)
+            if (elected) mbar_arrive_cta(&full[s]);                         // wake the consumers: they read the -1 and leave
+            drained = true;
+            return;
+        }
         if (pkt == 0) tile_origin(ptile, pm0, pn0);
-        unsigned char* a = smem + (size_t)s * (TILE_A_BYTES + TILE_B_BYTES);
-        mbar_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
-        tma_load_2d(a, &mapA, pkt * TBK, (int)pm0, &full[s]);
-        tma_load_2d(a + TILE_A_BYTES, &mapB, pkt * TBK, (int)pn0, &full[s]);
+        if (elected) {
+            unsigned char* a = smem + (size_t)s * (TILE_A_BYTES + TILE_B_BYTES);
+            mbar_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
+            tma_load_2d(a, &mapA, pkt * TBK, (int)pm0, &full[s]);
+            tma_load_2d(a + TILE_A_BYTES, &mapB, pkt * TBK, (int)pn0, &full[s]);
+        }
         ++pq;
         if (++pkt == KT) {
             pkt = 0;
             ptile += gridDim.x;
+            ++pseq;
         }
     };
-    if (tid == 0) {
+    if (ROTATE || tid == 0) {
         for (int s = 0; s < TSTAGES - 1; ++s) issue_next();
     }
 
     int64_t q = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x, seq = 0; DYNAMIC || tile < n_tiles; tile += gridDim.x, ++seq) {
+        if (DYNAMIC) {      // the tile id travels with the first k-tile of the tile: wait for it, then read the ring
+            mbar_wait(&full[q % TSTAGES], (uint32_t)(q / TSTAGES) & 1);
+            tile = tile_ring[seq & 3];
+            if (tile < 0) break;
+        }
         int64_t m0, n0;
         tile_origin(tile, m0, n0);
         double acc[MI][NJ][2];
@@ -281,7 +321,7 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
 
         for (int kt = 0; kt < KT; ++kt, ++q) {
             const int s = (int)(q % TSTAGES);
-            if (tid == 0) issue_next();                          // k-tile q + TSTAGES - 1 into the stage k-tile q - 1 used
+            if (ROTATE || tid == 0) issue_next();                // k-tile q + TSTAGES - 1 into the stage k-tile q - 1 used
             mbar_wait(&full[s], (uint32_t)(q / TSTAGES) & 1);
             const unsigned char* as = smem + (size_t)s * (TILE_A_BYTES + TILE_B_BYTES);
             const unsigned char* bs = as + TILE_A_BYTES;
@@ -399,7 +439,7 @@ int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alp
     if (K < 1 || M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return XR_ERR_UNSUPPORTED;
     CUtensorMap mapA, mapB;
     if (!make_map(&mapA, A, M, K, lda) || !make_map(&mapB, B, N, K, ldb)) return XR_ERR_UNSUPPORTED;
-    GemmTmaParams p{M, N, K, alpha, C, offM, ldc, offN, accumulate, (M + TBM - 1) / TBM, (N + TBN - 1) / TBN, nullptr, 0, nullptr};
+    GemmTmaParams p{M, N, K, alpha, C, offM, ldc, offN, accumulate, (M + TBM - 1) / TBM, (N + TBN - 1) / TBN, nullptr, 0, nullptr, nullptr};
     const int64_t tiles = p.tiles_m * p.tiles_n;
     XR_REQUIRE(tiles < (1ll << 31), "xr_gemm_scatter: too many tiles (%lld)", (long long)tiles);
     // Few output tiles but a long contraction (the rho x V precontractions of hermitian-XRCC: [P, n^4] x [n^4, 1..n]): split K
@@ -426,6 +466,18 @@ int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alp
         XR_CUDA(cudaGetLastError());
         ctx->launches += 2;
         return XR_OK;
+    }
+    if (XR_GEMM_VARIANT == 0 || KT > XR_GEMM_PERSISTENT_MAX_KT) {
+        XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel<MODE_SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+        gemm_tma_scatter_kernel<MODE_SCATTER><<<(unsigned)tiles, TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
+        XR_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return XR_OK;
+    }
+    if (XR_GEMM_VARIANT == 3) {
+        if (!ctx->counters) XR_CUDA(cudaMalloc(&ctx->counters, 256));
+        XR_CUDA(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+        p.tile_counter = static_cast<unsigned long long*>(ctx->counters);
     }
     // persistent CTAs, 4 per SM (48 KB of ring + <= 128 registers each): one launch-and-fill per CTA instead of per tile
     const int64_t resident = (int64_t)ctx->sm_count * 4;
@@ -494,7 +546,7 @@ extern "C" int xr_gemm_reduce(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, doub
     XR_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "xr_gemm_reduce: dimension too large");
     CUtensorMap mapA, mapB;
     XR_REQUIRE(make_map(&mapA, A, M, K, lda) && make_map(&mapB, B, N, K, ldb), "xr_gemm_reduce: cuTensorMapEncodeTiled failed");
-    GemmTmaParams p{M, N, K, alpha, nullptr, nullptr, 0, nullptr, 0, (M + TBM - 1) / TBM, (N + TBN - 1) / TBN, nullptr, 0, nullptr};
+    GemmTmaParams p{M, N, K, alpha, nullptr, nullptr, 0, nullptr, 0, (M + TBM - 1) / TBM, (N + TBN - 1) / TBN, nullptr, 0, nullptr, nullptr};
     const int64_t tiles = p.tiles_m * p.tiles_n;
     XR_REQUIRE(tiles < (1ll << 31), "xr_gemm_reduce: too many tiles (%lld)", (long long)tiles);
     int rc = xr_ensure_scratch(ctx, (size_t)(tiles + RED_BLOCKS) * 2 * sizeof(double) + 256);

@@ -2,7 +2,7 @@
 oracle, same assertions), with the test-only NumPy device stand-in replaced by the real Device -- i.e. every product in
 them is computed by libxr_b200.so on the B200.  Covers what had CPU-only coverage: xr_ccsd.build_H at every S-order
 ("proper", 0-4; 8-operator densities at orders 3/4), the high-order assembly in the style of mains/xr_ccsd.py, the seeded
-random general systems, H1 of held bra slabs, ragged sectors and the factored high-rank densities."""
+random general systems, H1 of held bra slabs and the det variants."""
 import pytest
 
 import test_host_logic_cpu as host
@@ -43,7 +43,3 @@ def test_general_H1_of_held_bra_slabs_on_device(on_device):
 @pytest.mark.parametrize("which", ["bra", "ket"])
 def test_det_variants_on_device(on_device, which):
     host.test_hermitian_det_variants_host_logic(which)
-
-
-def test_factored_densities_on_device(on_device):
-    host.test_hermitian_factored_densities_host_logic()
