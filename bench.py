@@ -357,7 +357,7 @@ def run_general(args):
             extras["dimer_phase"].update({
                 "with_gather_ms": with_gather_ms, "gather_bytes_received_per_rank": recv,
                 "gather_gbs_per_rank": recv / max(with_gather_ms - compute_ms, 1e-6) / 1e6,
-                "nvlink_peak_gbs": 900.0, "limiting_collective": "NCCL all_gather_into_tensor of the H2 bra slabs (8 B/element in, 2K flop/element: gather-bound at n = 18)"})
+                "nvlink_peak_gbs": 770.0, "nvlink_peak_source": "B200_PROFILING.md: measured peer copy per direction per GPU (900 nominal)", "limiting_collective": "NCCL all_gather_into_tensor of the H2 bra slabs (8 B/element in, 2K flop/element: gather-bound at n = 18)"})
             one = lambda **kw: (lambda: step(**kw))
             def four(**kw):          # a whole round-robin cycle, so the three variants time the same trimers
                 return timed(one(**kw), len(trimers) or 1)

@@ -48,11 +48,11 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
 //   2  persistent, static, the issuing duty rotates over the four warps (one sub-core is not always the late one)
 //   3  persistent, tiles handed out by an atomic counter (thread 0 issues), so faster SMs take more tiles
 #ifndef XR_GEMM_VARIANT
-#define XR_GEMM_VARIANT 1
+#define XR_GEMM_VARIANT 3
 #endif
 // ... and the K range the persistent kernel is used for (k-tiles of 16): below/above, the one-tile kernel
 #ifndef XR_GEMM_PERSISTENT_MAX_KT
-#define XR_GEMM_PERSISTENT_MAX_KT 1000000
+#define XR_GEMM_PERSISTENT_MAX_KT 4
 #endif
 
 constexpr int TBM = 64, TBN = 64, TBK = 16, TSTAGES = 3, TTHREADS = 128;
