@@ -131,6 +131,21 @@ int xr_gemm_scatter(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
                     const double* A, int64_t lda, const double* B, int64_t ldb,
                     double* C, const int64_t* offM, int64_t ldc, const int64_t* offN, int accumulate);
 
+/* The same product for a tall-skinny output with a long contraction (N <= 32; the rho x integral precontractions of
+ * hermitian-XRCC, hermitian-XRCC/precontract.py:26-94), with A addressed where it lies instead of as a matrix:
+ *
+ *     row   m = r1*E2 + r2     at element offset  r1*s1 + r2*s2          (r1 < E1, r2 < E2)
+ *     index k = k1*EK2 + k2    at element offset  k1*sk1 + k2            (k1 < EK1, k2 < EK2: the contiguous index)
+ *     C[ offM(m) + offN(n) ]  (= or +=)  alpha * sum_k A[row(m) + col(k)] * B[n*ldb + k]
+ *
+ * so a density rho[ij, a, b, c, d, e] contracted over (a,b,d,e) is E1 = #ij, E2 = #c, EK1 = #(a,b), EK2 = #(d,e) -- no
+ * re-ordering copy of the density.  E2 = EK1 = 1 is a plain matrix with lda = s1.  The contraction is always split over
+ * the whole GPU and summed in a fixed order (bit-reproducible); the roofline is one read of A from HBM.  Requirements:
+ * 16-byte aligned A and B, even s1 / s2 / sk1 / ldb (else XR_ERR_UNSUPPORTED: use xr_permute_copy + xr_gemm_scatter). */
+int xr_gemm_stream(xr_ctx* ctx, int64_t E1, int64_t s1, int64_t E2, int64_t s2, int64_t EK1, int64_t sk1, int64_t EK2,
+                   int64_t N, double alpha, const double* A, const double* B, int64_t ldb,
+                   double* C, const int64_t* offM, int64_t ldc, const int64_t* offN, int accumulate);
+
 /* The same product handed to the streaming consumer instead of memory:
  *     moments[0] += alpha * sum_{m,n} C[m,n],   moments[1] += alpha^2 * sum_{m,n} C[m,n]^2,   C = A . B^T
  * (device doubles, caller zeroes; bit-reproducible).  For dimer blocks that cannot be stored (the 1e12-element H2 of

@@ -319,6 +319,18 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
 #pragma unroll
             for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+        // The epilogue's offset-table entries are pulled into L1 NOW, so that their L2 round trip runs under the tile's DMMAs:
+        // with three k-tiles per tile those loads were a quarter of all stall samples when first touched after the k loop
+        // (profiles/r02c).  Prefetches, not register loads: the kernel has no registers to spare at 4 CTAs per SM.
+        if (p.offN) {
+            const int64_t col = n0 + warp_n * 32 + 2 * t + 8 * (g & 3);       // the lane's columns are 8j + 2t: j <-> g & 3
+            if (col < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.offN + col));
+        }
+        if (p.offM) {
+            const int64_t row = m0 + warp_m * 32 + lane;
+            if (row < p.M) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.offM + row));
+        }
+
         for (int kt = 0; kt < KT; ++kt, ++q) {
             const int s = (int)(q % TSTAGES);
             if (ROTATE || tid == 0) issue_next();                // k-tile q + TSTAGES - 1 into the stage k-tile q - 1 used
@@ -432,6 +444,235 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const double* __rest
 
 }  // namespace
 
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Stream kernel: tall-skinny products with a long contraction, the rho x integral precontractions of hermitian-XRCC
+// ([P, n^3..n^4] x [n^3..n^4, 1..n]): the work is READING the density once, so the roofline is HBM, and two things kept the
+// general 64 x 64 tile kernel at a quarter of it: (1) it multiplies a full 64-column tile although N is 1..18 -- DMMA-bound
+// on zeros -- and (2) densities whose free orbital index sits between contracted ones were first re-ordered by
+// xr_permute_copy, a read + write of the whole tensor.  Here a CTA owns <= 64 rows x (8 or 32) columns, every warp 16 rows,
+// and A is addressed through a 4-D tensor map: rows m = r1*E2 + r2 at element offset r1*s1 + r2*s2, contraction index
+// k = k1*EK2 + k2 at offset k1*sk1 + k2 (k2 contiguous).  One TMA box [16 k2][r2 box][1 k1][r1 box] lands in shared
+// memory as [rows][16] in exactly the layout of the dense kernel, so a density [ij, a, b, c, d, e] contracted over (a,b,d,e)
+// is streamed where it lies.  K is always split over blockIdx.y (the whole GPU streams the operand); the partial tiles go
+// through the same fixed-order second pass as MODE_SPLITK (bit-reproducible).
+struct StreamParams {
+    int64_t M, N;
+    int64_t E2;                 // rows of the inner row group (1 for a plain matrix)
+    int r1_box, r2_box;         // rows per tile = r1_box * r2_box <= 64
+    int64_t tiles_r2;           // tiles along the inner row group
+    int64_t EK2;                // extent of the contiguous contraction group
+    int chunks;                 // ceil(EK2 / 16)
+    int64_t total_kt;           // EK1 * chunks
+    int kt_per_split;
+    double* ws;                 // [splits][M][N]
+};
+
+constexpr int SSTAGES = 5, SBM = 64;
+
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <int NJ>      // 8-column blocks per CTA: 1 (N <= 8) or 4 (N <= 32)
+__global__ void __launch_bounds__(TTHREADS, 4)
+gemm_tma_stream_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const StreamParams p) {
+    constexpr int MI = 2, BN = NJ * 8;
+    constexpr int A_BYTES = SBM * TBK * 8, B_BYTES = BN * TBK * 8, STAGE_BYTES = A_BYTES + (B_BYTES < 1024 ? 1024 : B_BYTES);
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[SSTAGES], empty[SSTAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t tile = blockIdx.x;
+    const int64_t r1_0 = (tile / p.tiles_r2) * p.r1_box, r2_0 = (tile % p.tiles_r2) * p.r2_box;
+    const int64_t kt_begin = (int64_t)blockIdx.y * p.kt_per_split;
+    const int KT = (int)(p.total_kt - kt_begin < p.kt_per_split ? p.total_kt - kt_begin : p.kt_per_split);
+    const uint32_t a_tx = (uint32_t)(p.r1_box * p.r2_box * TBK * 8);
+
+    if (tid == 0) {
+        for (int s = 0; s < SSTAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], TTHREADS / 32);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    int issued = 0;
+    auto issue_next = [&]() {       // thread 0
+        if (issued >= KT) return;
+        const int s = issued % SSTAGES;
+        mbar_wait(&empty[s], (uint32_t)((issued / SSTAGES) & 1) ^ 1);
+        const int64_t q = kt_begin + issued;
+        const int64_t k1 = q / p.chunks;
+        const int c = (int)(q % p.chunks);
+        unsigned char* a = smem + (size_t)s * STAGE_BYTES;
+        mbar_expect_tx(&full[s], a_tx + B_BYTES);
+        tma_load_4d(a, &mapA, c * TBK, (int)r2_0, (int)k1, (int)r1_0, &full[s]);
+        tma_load_2d(a + A_BYTES, &mapB, (int)(k1 * p.EK2 + c * TBK), 0, &full[s]);
+        ++issued;
+    };
+    if (tid == 0) {
+        for (int s = 0; s < SSTAGES - 1; ++s) issue_next();
+    }
+
+    double acc[MI][NJ][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % SSTAGES;
+        if (tid == 0) issue_next();
+        mbar_wait(&full[s], (uint32_t)(kt / SSTAGES) & 1);
+        const unsigned char* as = smem + (size_t)s * STAGE_BYTES;
+        const unsigned char* bs = as + A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < TBK / 4; ++ks) {
+            double a[MI], b[NJ];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const double*>(as + swz(warp * 16 + i * 8 + g, ks * 4 + t));
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double*>(bs + swz(j * 8 + g, ks * 4 + t));
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(&empty[s]);
+    }
+
+    // raw partial tile -> ws[split][m][n]; row r of the tile is (r1_0 + r / r2_box, r2_0 + r % r2_box)
+    double* ws = p.ws + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N;
+    const int rows_in_tile = p.r1_box * p.r2_box;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int r = warp * 16 + i * 8 + g;
+        if (r >= rows_in_tile) continue;
+        const int64_t r1 = r1_0 + r / p.r2_box, r2 = r2_0 + r % p.r2_box;
+        if (r2 >= p.E2) continue;
+        const int64_t m = r1 * p.E2 + r2;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int64_t col = j * 8 + 2 * t;
+            if (col < p.N) ws[m * p.N + col] = acc[i][j][0];
+            if (col + 1 < p.N) ws[m * p.N + col + 1] = acc[i][j][1];
+        }
+    }
+}
+
+// A as [EK2 | E2 | EK1 | E1] with byte strides (8 | s2*8 | sk1*8 | s1*8) and box [16 | r2_box | 1 | r1_box]
+bool make_map_4d(CUtensorMap* map, const double* base, int64_t EK2, int64_t E2, int64_t s2, int64_t EK1, int64_t sk1, int64_t E1,
+                 int64_t s1, int r2_box, int r1_box) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return false;
+    cuuint64_t gdim[4] = {(cuuint64_t)EK2, (cuuint64_t)E2, (cuuint64_t)EK1, (cuuint64_t)E1};
+    cuuint64_t gstride[3] = {(cuuint64_t)s2 * 8, (cuuint64_t)sk1 * 8, (cuuint64_t)s1 * 8};
+    cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)r2_box, 1, (cuuint32_t)r1_box};
+    cuuint32_t estride[4] = {1, 1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), gdim, gstride, box, estride,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool make_map_rows(CUtensorMap* map, const double* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
+    cuuint32_t estride[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estride,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NJ>
+int launch_stream(xr_ctx* ctx, const CUtensorMap& mapA, const CUtensorMap& mapB, StreamParams p, int64_t tiles, int64_t splits) {
+    constexpr int BN = NJ * 8;
+    constexpr size_t SMEM = (size_t)SSTAGES * (SBM * TBK * 8 + (BN * TBK * 8 < 1024 ? 1024 : BN * TBK * 8)) + 1024;
+    XR_CUDA(cudaFuncSetAttribute(gemm_tma_stream_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    gemm_tma_stream_kernel<NJ><<<dim3((unsigned)tiles, (unsigned)splits), TTHREADS, SMEM, ctx->stream>>>(mapA, mapB, p);
+    XR_CUDA(cudaGetLastError());
+    return XR_OK;
+}
+
+}  // namespace
+
+// The stream product (see gemm_tma_stream_kernel).  XR_ERR_UNSUPPORTED when a tensor map cannot describe the operands.
+int xr_gemm_stream_impl(xr_ctx* ctx, int64_t E1, int64_t s1, int64_t E2, int64_t s2, int64_t EK1, int64_t sk1, int64_t EK2, int64_t N,
+                        double alpha, const double* A, const double* B, int64_t ldb, double* C, const int64_t* offM, int64_t ldc,
+                        const int64_t* offN, int accumulate) {
+    const int64_t M = E1 * E2, K = EK1 * EK2;
+    if (N > 32 || M >= (1ll << 31) || K >= (1ll << 31) || E1 < 1 || E2 < 1 || EK1 < 1 || EK2 < 1) return XR_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (ldb & 1)) return XR_ERR_UNSUPPORTED;
+    if ((E2 > 1 && (s2 & 1)) || (EK1 > 1 && (sk1 & 1)) || (E1 > 1 && (s1 & 1))) return XR_ERR_UNSUPPORTED;      // 16-byte strides
+    StreamParams p{};
+    p.M = M;
+    p.N = N;
+    p.E2 = E2;
+    p.r2_box = (int)(E2 < SBM ? E2 : SBM);
+    p.r1_box = SBM / p.r2_box;
+    if (p.r1_box > E1) p.r1_box = (int)E1;
+    if (p.r1_box > 256 || p.r2_box > 256) return XR_ERR_UNSUPPORTED;
+    p.tiles_r2 = (E2 + p.r2_box - 1) / p.r2_box;
+    const int64_t tiles = ((E1 + p.r1_box - 1) / p.r1_box) * p.tiles_r2;
+    p.EK2 = EK2;
+    p.chunks = (int)((EK2 + TBK - 1) / TBK);
+    p.total_kt = EK1 * p.chunks;
+    if (tiles >= 65536ll * 32768 || tiles < 1) return XR_ERR_UNSUPPORTED;
+    int64_t splits = (8 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
+    if (splits > p.total_kt / 8) splits = p.total_kt / 8;
+    if (splits > 1024) splits = 1024;
+    if (splits < 1) splits = 1;
+    p.kt_per_split = (int)((p.total_kt + splits - 1) / splits);
+    splits = (p.total_kt + p.kt_per_split - 1) / p.kt_per_split;
+    CUtensorMap mapA, mapB;
+    const int bn = N <= 8 ? 8 : 32;
+    if (!make_map_4d(&mapA, A, EK2, E2, E2 > 1 ? s2 : 2, EK1, EK1 > 1 ? sk1 : 2, E1, E1 > 1 ? s1 : 2, p.r2_box, p.r1_box) ||      // (extent-1 dims: any 16-byte stride)
+        !make_map_rows(&mapB, B, N, K, ldb, bn))
+        return XR_ERR_UNSUPPORTED;
+    int rc = xr_ensure_scratch(ctx, (size_t)splits * (size_t)M * (size_t)N * sizeof(double));
+    if (rc != XR_OK) return rc;
+    p.ws = static_cast<double*>(ctx->scratch);
+    rc = N <= 8 ? launch_stream<1>(ctx, mapA, mapB, p, tiles, splits) : launch_stream<4>(ctx, mapA, mapB, p, tiles, splits);
+    if (rc != XR_OK) return rc;
+    GemmTmaParams f{M, N, K, alpha, C, offM, ldc, offN, accumulate, 0, 0, nullptr, 0, nullptr, nullptr};
+    int64_t blocks = (M * N + 255) / 256;
+    if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+    splitk_finish_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p.ws, (int)splits, f);
+    XR_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    return XR_OK;
+}
+
+extern "C" int xr_gemm_stream(xr_ctx* ctx, int64_t E1, int64_t s1, int64_t E2, int64_t s2, int64_t EK1, int64_t sk1, int64_t EK2,
+                              int64_t N, double alpha, const double* A, const double* B, int64_t ldb, double* C,
+                              const int64_t* offM, int64_t ldc, const int64_t* offN, int accumulate) {
+    XR_REQUIRE(ctx, "xr_gemm_stream: null ctx");
+    if (E1 <= 0 || E2 <= 0 || N <= 0) return XR_OK;
+    XR_REQUIRE(EK1 >= 1 && EK2 >= 1 && A && B && C, "xr_gemm_stream: null pointer or empty contraction");
+    XR_REQUIRE(offM || ldc >= 1, "xr_gemm_stream: need offM or ldc");
+    XR_REQUIRE(ldb >= EK1 * EK2, "xr_gemm_stream: ldb smaller than K");
+    int rc = xr_gemm_stream_impl(ctx, E1, s1, E2, s2, EK1, sk1, EK2, N, alpha, A, B, ldb, C, offM, ldc, offN, accumulate);
+    if (rc == XR_ERR_UNSUPPORTED)
+        xr_set_error("xr_gemm_stream: operands not expressible (N <= 32, 16-byte aligned bases and even strides are required)");
+    return rc;
+}
+
+int xr_gemm_stream_impl(xr_ctx* ctx, int64_t E1, int64_t s1, int64_t E2, int64_t s2, int64_t EK1, int64_t sk1, int64_t EK2, int64_t N,
+                        double alpha, const double* A, const double* B, int64_t ldb, double* C, const int64_t* offM, int64_t ldc,
+                        const int64_t* offN, int accumulate);
+
 // returns XR_ERR_UNSUPPORTED when the operands cannot be described by a tensor map (caller falls back to cp.async staging)
 int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                         const double* B, int64_t ldb, double* C, const int64_t* offM, int64_t ldc, const int64_t* offN,
@@ -450,6 +691,11 @@ int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alp
         splits = (4 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
         if (splits > KT / 8) splits = KT / 8;
         if (splits > 512) splits = 512;
+    }
+    if (splits >= 2 && N <= 32) {
+        // skinny output: the stream kernel (8- or 32-column tiles instead of 64: the DMMA pipe no longer multiplies zeros)
+        int rc = xr_gemm_stream_impl(ctx, M, lda, 1, 0, 1, 0, K, N, alpha, A, B, ldb, C, offM, ldc, offN, accumulate);
+        if (rc != XR_ERR_UNSUPPORTED) return rc;
     }
     if (splits >= 2) {
         p.kt_per_split = (int)((KT + splits - 1) / splits);

@@ -190,6 +190,37 @@ class Contractor(object):
         self.dev.ctx.permute_copy(out, T.buf, shape, src, 1.0)
         return out
 
+    STREAM_MIN_ELEMENTS = 1 << 20
+
+    def _stream_plan(self, A, idxA, rowsA, M, B, idxB, colsB, N, shared, K, extent):
+        """A large operand whose free indices are INTERLEAVED with contracted ones (a density rho[i,j,p,X,s,r] contracted over
+        p,s,r) used to be re-ordered by xr_permute_copy -- a read and a write of the whole tensor -- before the GEMM could
+        read it.  When the other operand is small (<= 32 output columns) xr_gemm_stream reads the large one where it
+        lies: its index list, in memory order, must be [free run R1][contracted run K1][free run R2][contracted run K2].
+        Returns (large tensor, small operand arranged as [its free labels, contracted labels in the large one's order], free
+        labels of the large one in memory order, free labels of the small one, (E1, s1, E2, s2, EK1, sk1, EK2)) or None."""
+        for T, idxT, freeT, nT, S, idxS, freeS, nS in ((A, idxA, rowsA, M, B, idxB, colsB, N), (B, idxB, colsB, N, A, idxA, rowsA, M)):
+            if nS > 32 or nT * K < self.STREAM_MIN_ELEMENTS or K < 256 or K % 2:
+                continue
+            runs = []                                   # [(is_contracted, [labels])] in memory order
+            for l in idxT:
+                kind = l in shared
+                if runs and runs[-1][0] == kind:
+                    runs[-1][1].append(l)
+                else:
+                    runs.append((kind, [l]))
+            if [k for k, _ in runs] != [False, True, False, True]:
+                continue
+            size = lambda labels: int(numpy.prod([extent[l] for l in labels]))
+            R1, K1, R2, K2 = (labels for _, labels in runs)
+            E1, EK1, E2, EK2 = size(R1), size(K1), size(R2), size(K2)
+            s2, sk1, s1 = EK2, E2 * EK2, EK1 * E2 * EK2
+            if s2 % 2 or T.buf.data_ptr() % 16:
+                continue
+            small2 = self._arranged(S, idxS, freeS, K1 + K2)
+            return T, small2, R1 + R2, list(freeS), (E1, s1, E2, s2, EK1, sk1, EK2)
+        return None
+
     def contract(self, A, idxA, B, idxB, idx_out, alpha=1.0, out=None, out_offset=0, out_strides=None, accumulate=False):
         """out[idx_out] (+)= alpha * sum_{shared} A[idxA] * B[idxB].
 
@@ -210,11 +241,13 @@ class Contractor(object):
             for l, e in zip(idx, T.shape):
                 if extent.setdefault(l, e) != e:
                     raise ValueError("contract: label %r has extents %d and %d" % (l, extent[l], e))
-        A2 = self._arranged(A, idxA, rows, shared)
-        B2 = self._arranged(B, idxB, cols, shared)
         M = int(numpy.prod([extent[l] for l in rows])) if rows else 1
         N = int(numpy.prod([extent[l] for l in cols])) if cols else 1
         K = int(numpy.prod([extent[l] for l in shared])) if shared else 1
+        streamed = self._stream_plan(A, idxA, rows, M, B, idxB, cols, N, shared, K, extent)
+        if streamed is None:
+            A2 = self._arranged(A, idxA, rows, shared)
+            B2 = self._arranged(B, idxB, cols, shared)
         if out is None:
             out_buf = self.dev.empty(tuple(extent[l] for l in idx_out))
             stride_of = dict(zip(idx_out, _strides([extent[l] for l in idx_out])))
@@ -226,6 +259,16 @@ class Contractor(object):
         col_strides = [stride_of[l] for l in cols]
         plain = (out is None or out_strides is None) and idx_out == rows + cols
         base = out_buf.data_ptr() + 8 * int(out_offset)
+        if streamed is not None:
+            big, small2, big_free, small_free, geometry = streamed
+            offM = self._table([extent[l] for l in big_free], [stride_of[l] for l in big_free])
+            offN = self._table([extent[l] for l in small_free], [stride_of[l] for l in small_free])
+            n_small = int(numpy.prod([extent[l] for l in small_free])) if small_free else 1
+            if self.dev.ctx.gemm_stream(*geometry, n_small, alpha, big.buf, small2, K, base, offM, 0, offN, accumulate):
+                self.flops += 2.0 * M * N * K
+                return DeviceTensor(out_buf, self.dev) if out is None else out
+            A2 = self._arranged(A, idxA, rows, shared)      # the kernel declined (alignment): the re-ordering path
+            B2 = self._arranged(B, idxB, cols, shared)
         if plain:
             self.dev.ctx.gemm_scatter(M, N, K, alpha, A2, K, B2, K, base, None, N, None, accumulate)
         else:

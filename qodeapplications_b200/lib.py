@@ -44,6 +44,7 @@ _PROTOTYPES = {
     "xr_upload": (_int, [_ptr, _ptr, _ptr, ctypes.c_size_t]),
     "xr_download": (_int, [_ptr, _ptr, _ptr, ctypes.c_size_t]),
     "xr_gemm_scatter": (_int, [_ptr, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _int]),
+    "xr_gemm_stream": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _dbl, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _int]),
     "xr_gemm_reduce": (_int, [_ptr, _i64, _i64, _i64, _dbl, _ptr, _i64, _ptr, _i64, _ptr]),
     "xr_copy2d_scaled": (_int, [_ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _dbl]),
     "xr_scatter_const": (_int, [_ptr, _ptr, _ptr, _i64, _dbl, _int]),
@@ -205,6 +206,16 @@ class Context(object):
     def gemm_scatter(self, M, N, K, alpha, A, lda, B, ldb, C, offM=None, ldc=0, offN=None, accumulate=False):
         check(self.lib.xr_gemm_scatter(self.handle, M, N, K, float(alpha), _p(A), lda, _p(B), ldb, _p(C), _p(offM),
                                        ldc, _p(offN), 1 if accumulate else 0), "xr_gemm_scatter")
+
+    @_recorded
+    def gemm_stream(self, E1, s1, E2, s2, EK1, sk1, EK2, N, alpha, A, B, ldb, C, offM=None, ldc=0, offN=None, accumulate=False):
+        """returns False (nothing launched) when the operands cannot be addressed by the stream kernel"""
+        rc = self.lib.xr_gemm_stream(self.handle, E1, s1, E2, s2, EK1, sk1, EK2, N, float(alpha), _p(A), _p(B), ldb, _p(C), _p(offM),
+                                     ldc, _p(offN), 1 if accumulate else 0)
+        if rc == -4:            # XR_ERR_UNSUPPORTED
+            return False
+        check(rc, "xr_gemm_stream")
+        return True
 
     @_recorded
     def gemm_reduce(self, M, N, K, alpha, A, lda, B, ldb, moments):

@@ -75,6 +75,27 @@ class FakeContext(object):
             c[at] = val
 
     @_recorded
+    def gemm_stream(self, E1, s1, E2, s2, EK1, sk1, EK2, N, alpha, A, B, ldb, C, offM=None, ldc=0, offN=None, accumulate=False):
+        self.launches += 1
+        if N > 32 or (E2 > 1 and s2 % 2) or (EK1 > 1 and sk1 % 2) or (E1 > 1 and s1 % 2) or ldb % 2:
+            return False
+        span = (E1 - 1) * s1 + (E2 - 1) * s2 + (EK1 - 1) * sk1 + EK2
+        a = numpy.lib.stride_tricks.as_strided(_view(A, span), (E1, E2, EK1, EK2), (8 * s1, 8 * s2, 8 * sk1, 8))
+        M, K = E1 * E2, EK1 * EK2
+        a = numpy.ascontiguousarray(a).reshape(M, K)
+        b = numpy.lib.stride_tricks.as_strided(_view(B, (N - 1) * ldb + K), (N, K), (8 * ldb, 8))
+        prod = alpha * (a @ b.T)
+        om = _view(offM, M, numpy.int64) if offM is not None else numpy.arange(M, dtype=numpy.int64) * ldc
+        on = _view(offN, N, numpy.int64) if offN is not None else numpy.arange(N, dtype=numpy.int64)
+        at = (om[:, None] + on[None, :]).reshape(-1)
+        c = _view(C, int(at.max()) + 1)
+        if accumulate:
+            numpy.add.at(c, at, prod.reshape(-1))
+        else:
+            c[at] = prod.reshape(-1)
+        return True
+
+    @_recorded
     def gemm_reduce(self, M, N, K, alpha, A, lda, B, ldb, moments):
         self.launches += 1
         if M <= 0 or N <= 0:

@@ -66,6 +66,49 @@ def test_gemm_scatter_plain(dev, M, N, K, aligned):
     _close(dev.download(dC)[:, :N], ref - 0.5 * A[:, :K] @ B[:, :K].T, 1e-13 * max(1, K))
 
 
+@pytest.mark.parametrize("E1,E2,EK1,EK2,N", [(5, 18, 36, 36, 1), (3, 1, 1, 5000, 1), (7, 18, 324, 324, 1), (2, 70, 16, 100, 8),
+                                             (11, 18, 18, 324, 18), (130, 1, 1, 2600, 32), (4, 6, 36, 36, 3), (1, 100, 40, 18, 5)])
+def test_gemm_stream(dev, E1, E2, EK1, EK2, N):
+    """xr_gemm_stream: A addressed through a 4-D tensor map as [E1][EK1][E2][EK2] (free index between contracted ones),
+    tall-skinny output, K split over the GPU; against numpy on the same strided view"""
+    rng = numpy.random.default_rng(E1 + E2 + EK1 + EK2 + N)
+    T = rng.standard_normal((E1, EK1, E2, EK2))
+    K = EK1 * EK2
+    ldb = K + 2
+    B = rng.standard_normal((N, ldb))
+    ref = -0.5 * numpy.einsum("aubv,nuv->abn", T, B[:, :K].reshape(N, EK1, EK2)).reshape(E1 * E2, N)
+    dT, dB = dev.upload(T), dev.upload(B)
+    M = E1 * E2
+    offM = numpy.arange(M, dtype=numpy.int64) * 3                 # output transposed-ish: C[n, m] with padding
+    offN = numpy.arange(N, dtype=numpy.int64) * (3 * M + 1)
+    C0 = rng.standard_normal((N * (3 * M + 1) + 5,))
+    dC = dev.upload(C0)
+    ok = dev.ctx.gemm_stream(E1, EK1 * E2 * EK2, E2, EK2, EK1, E2 * EK2, EK2, N, -0.5, dT, dB, ldb, dC,
+                             dev.upload(offM, numpy.int64), 0, dev.upload(offN, numpy.int64), True)
+    assert ok
+    want = C0.copy()
+    want[(offM[:, None] + offN[None, :]).reshape(-1)] += ref.reshape(-1)
+    got = dev.download(dC)
+    assert numpy.abs(got - want).max() <= 1e-13 * K ** 0.5 * max(1.0, numpy.abs(ref).max())
+    # plain output, overwrite
+    dP = dev.empty((M, N))
+    assert dev.ctx.gemm_stream(E1, EK1 * E2 * EK2, E2, EK2, EK1, E2 * EK2, EK2, N, -0.5, dT, dB, ldb, dP, None, N, None, False)
+    assert numpy.abs(dev.download(dP) - ref).max() <= 1e-13 * K ** 0.5 * max(1.0, numpy.abs(ref).max())
+    # bit-reproducible
+    dQ = dev.empty((M, N))
+    dev.ctx.gemm_stream(E1, EK1 * E2 * EK2, E2, EK2, EK1, E2 * EK2, EK2, N, -0.5, dT, dB, ldb, dQ, None, N, None, False)
+    assert numpy.array_equal(dev.download(dQ), dev.download(dP))
+
+
+def test_gemm_stream_declines_what_it_cannot_address(dev):
+    rng = numpy.random.default_rng(1)
+    T, B = dev.upload(rng.standard_normal((4, 3, 5, 7))), dev.upload(rng.standard_normal((2, 22)))
+    C = dev.zeros((20, 2))
+    assert dev.ctx.gemm_stream(4, 105, 5, 7, 3, 35, 7, 2, 1.0, T, B, 22, C, None, 2, None, False) is False       # odd strides
+    assert dev.ctx.gemm_stream(4, 106, 5, 8, 3, 40, 8, 40, 1.0, T, B, 24, C, None, 40, None, False) is False     # N > 32
+    assert numpy.all(dev.download(C) == 0)
+
+
 def test_gemm_scatter_offset_tables(dev):
     """C[i0,i1,j0,j1] <- A[(i0,j0),k] B[(i1,j1),k]: the [ikjl] shuffle every dimer diagram needs."""
     rng = numpy.random.default_rng(7)

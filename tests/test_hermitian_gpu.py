@@ -310,3 +310,27 @@ def test_device_inverse_converges_and_falls_back(dev):
     assert not float(res2.host()) <= INVERSE_RESIDUAL_TOL
     Y = checked_inverse(far, dev)
     assert numpy.abs(Y.host() @ far - numpy.eye(n)).max() <= 1e-13
+
+
+def test_contractor_streams_large_interleaved_operands_without_reordering(dev):
+    """a large operand whose free index sits between contracted ones (rho[i,j,a,b,c,d,e] contracted over a,b,d,e) goes
+    through xr_gemm_stream where it lies: no xr_permute_copy of it is launched, and the result equals the einsum"""
+    from qodeapplications_b200.hermitian.tensor import Contractor, DeviceTensor
+    rng = numpy.random.default_rng(12)
+    n = 12
+    rho, V = rng.standard_normal((3, 4, n, n, n, n, n)), rng.standard_normal((n, n, n, n))
+    W = rng.standard_normal((5, n, n, n))
+    R, dV, dW = (DeviceTensor(dev.upload(x), dev) for x in (rho, V, W))
+    C = Contractor(dev)
+    C.STREAM_MIN_ELEMENTS = 1 << 18
+    dev.begin_trace()
+    out = C.contract(R, ["i", "j", "a", "b", "c", "d", "e"], dV, ["a", "b", "d", "e"], ["c", "i", "j"])
+    rho4 = DeviceTensor(R.buf[0], dev)            # [j, a, b, c, d, e] viewed as [i=j, j=a, p, x, s, r]
+    out2 = C.contract(dW, ["f", "p", "s", "r"], rho4, ["i", "j", "p", "x", "s", "r"], ["x", "f", "i", "j"])
+    trace, _ = dev.end_trace()
+    names = [call.__name__ for call, a, k in trace]
+    assert names.count("gemm_stream") == 2
+    big = [a for call, a, k in trace if call.__name__ == "permute_copy" and numpy.prod(a[2]) >= rho[0].size]
+    assert not big, "the large operand was re-ordered"
+    _close(out.host(), numpy.einsum("ijabcde,abde->cij", rho, V), 1e-12)
+    _close(out2.host(), numpy.einsum("fpsr,ijpxsr->xfij", W, rho[0]), 1e-12)
