@@ -67,7 +67,8 @@ def config_of(workload):
         n_tri = len(list(itertools.combinations(range(w["n_frag"]), 3)))
         cfg["step"] = ("every H1 + every dimer H2 + one of the %d trimer H3 (round-robin): %d consecutive steps = one full build"
                        % (n_tri, max(1, n_tri)))
-        cfg["sharding"] = "dimers: bra-state slabs of fragment m1 + NCCL all-gather of H2; trimers: leading pair-index slabs, no collective"
+        cfg["sharding"] = ("dimers: bra-state slabs of fragment m1, H2 assembled on every rank by an all-gather over NVLink (copy-engine pulls "
+                           "from peer memory, or NCCL); trimers: leading pair-index slabs, no collective")
         cfg["cache"] = "inputs_larger_than_L2 (4 GB of densities read, 77 GB of H2 written per step at cfg4)"
     elif w["kind"] == "hermitian":
         cfg["step"] = "one get_xr_H call (every monomer and dimer diagram of the order, S2 inverse included), densities resident in HBM"
@@ -91,8 +92,9 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true", help="skip the dimer-phase / gather-overlap measurements after the timed region")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--sample", type=int, default=0, help="CPU sample elements per class (0 = default)")
-    ap.add_argument("--assemble", default="nccl", choices=["nccl", "ce"],
-                    help="N > 1: how the H2 slabs are assembled (NCCL all-gather, or copy-engine pulls over NVLink peer memory)")
+    ap.add_argument("--assemble", default="auto", choices=["auto", "nccl", "ce"],
+                    help="N > 1: how the H2 slabs are assembled (copy-engine pulls over NVLink peer memory; NCCL all-gather; auto = ce "
+                         "where symmetric memory can be set up, else nccl)")
     ap.add_argument("--scale", type=float, default=0.0, help="cfg5: fraction of the 1000 states per fragment (0 = as many as the GPUs present hold)")
     return ap.parse_args()
 
@@ -357,7 +359,7 @@ def run_general(args):
             extras["dimer_phase"].update({
                 "with_gather_ms": with_gather_ms, "gather_bytes_received_per_rank": recv,
                 "gather_gbs_per_rank": recv / max(with_gather_ms - compute_ms, 1e-6) / 1e6,
-                "nvlink_peak_gbs": 770.0, "nvlink_peak_source": "B200_PROFILING.md: measured peer copy per direction per GPU (900 nominal)", "limiting_collective": "NCCL all_gather_into_tensor of the H2 bra slabs (8 B/element in, 2K flop/element: gather-bound at n = 18)"})
+                "nvlink_peak_gbs": 770.0, "nvlink_peak_source": "B200_PROFILING.md: measured peer copy per direction per GPU (900 nominal)", "limiting_collective": "all-gather of the H2 bra slabs (8 B/element in over NVLink against 2K flop/element: gather-bound at n = 18); mode: " + build.assemble})
             one = lambda **kw: (lambda: step(**kw))
             def four(**kw):          # a whole round-robin cycle, so the three variants time the same trimers
                 return timed(one(**kw), len(trimers) or 1)
@@ -819,8 +821,8 @@ def run_cfg5(args):
 
 def main():
     args = parse_args()
-    if "NCCL_DEBUG" not in os.environ:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout unless the caller asks for more
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (rank 0 prints ONE JSON line); INFO etc. stay
     if args.impl == "reference":
         run_reference(args)
     else:

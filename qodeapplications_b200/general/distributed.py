@@ -10,12 +10,13 @@ Assemble step.  The H2 all-gather moves 8 B per element against 2K flop per elem
 ~20x the dimer compute of a rank, and it sits in front of a trimer phase that keeps every SM busy with a persistent
 FP64 kernel (all 64 K registers of each SM).  Two ways to run it, both off the launch stream:
 
-* "nccl" (default): one all_gather_into_tensor per dimer, issued asynchronously; NCCL's kernels need SMs, so they
-  interleave with the trimer kernels at kernel boundaries;
-* "ce": the H2 buffers live in symmetric memory (torch.distributed._symmetric_memory: every rank maps every peer's buffer
+* "nccl": one all_gather_into_tensor per dimer, issued asynchronously so that it overlaps the next dimer's kernels, joined
+  before the trimer phase (NCCL's kernels need SMs: side by side with the trimer stream they make the step longer);
+* "ce" (what "auto", the default, takes when it can): the H2 buffers live in symmetric memory (torch.distributed._symmetric_memory: every rank maps every peer's buffer
   over NVLink), and after a device-side barrier each rank PULLS the other ranks' slabs with plain device-to-device copies
   on a side stream -- the copy engines move the data through the NVSwitch while the SMs stream trimer tiles, so the
-  gather costs the step nothing.  Falls back to "nccl" when symmetric memory cannot be set up on the box.
+  gather costs the step nothing (N = 2: 5798 ms with it, 5796 ms without; 732 GB/s per rank when timed alone = 95 % of
+  the measured 770 GB/s peer copy).  Falls back to "nccl" when symmetric memory cannot be set up on the box.
 
 torch.distributed is plumbing here (NCCL on GPUs, gloo in the CPU tests); the arithmetic is in
 libxr_b200.so.
@@ -80,7 +81,7 @@ class _peer_gather(object):
 
 class sharded_build(object):
     """Holds the output buffers of a (possibly multi-rank) build and runs one build step."""
-    def __init__(self, engine, dimers, trimers, rank=0, world=1, group=None, assemble="nccl"):
+    def __init__(self, engine, dimers, trimers, rank=0, world=1, group=None, assemble="auto"):
         self.eng, self.dimers, self.trimers = engine, list(dimers), list(trimers)
         self.rank, self.world, self.group = rank, world, group
         self.dims = [engine._frag(m).dim for m in range(len(engine._supersystem))]
@@ -92,7 +93,7 @@ class sharded_build(object):
             # rows padded to world*per bra states so that all slabs have equal size; rows >= dim1*dim2 are unused
             shapes[(m1, m2)] = (per * world * self.dims[m2], self.dims[m1] * self.dims[m2])
         self.peer, self.assemble, self.assemble_note = None, "nccl", None
-        if assemble == "ce" and world > 1 and dev.torch_device.type == "cuda":
+        if assemble in ("ce", "auto") and world > 1 and dev.torch_device.type == "cuda":
             ok = torch.ones(1, device=dev.torch_device)
             try:
                 self.peer = _peer_gather(dev, shapes, rank, world, group)
@@ -152,10 +153,16 @@ class sharded_build(object):
                     pending.append(work)
         if after_dimers is not None:
             after_dimers()
+        # NCCL's all-gather kernels need SMs, and the trimer stream holds every SM with a persistent, statically partitioned
+        # kernel: run side by side, the trimer kernels wait for the SMs NCCL took and the step gets LONGER (measured at
+        # N = 2: 6364 ms overlapped vs 5864 ms one after the other, profiles/r02e).  So NCCL gathers only overlap the next
+        # dimers and are joined here; the copy-engine gathers use no SM and run under the whole trimer phase.
+        for work in [w for w in pending if w is not self.peer]:
+            work.wait()
         for ms in (self.trimers if trimers is None else trimers):
             self.H3_moments[ms] = eng.H3_moments_device(*ms, shard=(rank, world))
-        for work in pending:
-            (work.join if work is self.peer else work.wait)()        # the launch stream waits for the collective (no host block)
+        if self.peer in pending:
+            self.peer.join()       # the launch stream waits for the last pull and the closing barrier (no host block)
 
     def gather_bytes(self):
         """bytes this rank RECEIVES over NVLink per step for the dimer all-gathers (the other ranks' slabs)"""
