@@ -12,8 +12,8 @@ if [ "$N" = "2" ]; then
   run r02d_bench_cfg4_n2_ce 2 --steps 4 --warmup 3 --assemble ce --no-e2e
 fi
 if [ "$N" = "8" ]; then
-  run r02e_bench_cfg4_n8_nccl 8 --steps 8 --warmup 4
-  run r02e_bench_cfg4_n8_ce 8 --steps 8 --warmup 4 --assemble ce --no-e2e
-  run r02e_bench_cfg4_n4_nccl 4 --steps 4 --warmup 3 --no-e2e
-  run r02e_bench_cfg5_n8 8 --workload cfg5 --steps 2 --warmup 1
+  run r02f_bench_cfg4_n8 8 --steps 8 --warmup 4
+  run r02f_bench_cfg4_n4 4 --steps 4 --warmup 3 --no-e2e
+  run r02f_bench_cfg4_n8_nccl 8 --steps 4 --warmup 3 --assemble nccl --no-e2e
+  run r02f_bench_cfg5_n8 8 --workload cfg5 --steps 2 --warmup 1
 fi
