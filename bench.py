@@ -692,7 +692,7 @@ def run_hermitian(args):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config_of(args.workload), "build_time_s": ms_step * 1e-3,
         "algorithmic_flops_per_step": trace_flops, "flops_key": str(key),
-        "gpu_launches": build.launches * args.steps, "launches_per_call": build.launches, "cuda_graph": build.graph is not None,
+        "gpu_launches": build.launches * args.steps, "launches_per_call": build.launches, "cuda_graph": build.graph is not None, "graph_streams": build.n_streams,
         "clocks": clocks, "e2e": e2e,
         "roofline": {"bound": "hbm", "kernel": "whole call (one CUDA graph of %d xr launches); dominant kernels: the rho x integral "
                                                "precontractions (gemm_tma split-K) streaming every density block once" % build.launches,

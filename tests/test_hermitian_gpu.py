@@ -281,7 +281,9 @@ def test_plan_replays_get_xr_H_as_one_cuda_graph(dev, name, order, ops):
     ints = (system["symm"], system["bior"], system["nuc"])
     build = plan(ints, system["densities"][:2], order, [ch, ch], device=dev)
     assert build.graph is not None, getattr(build, "graph_error", None)
+    assert build.n_streams > 1, getattr(build, "streams_error", None)        # independent diagram GEMMs on several streams
     H1, H2 = build()
+    assert build.n_streams > 1, "the multi-stream graph did not reproduce the eager build"
     E1, E2 = get_xr_H(ints, system["densities"][:2], order, [ch, ch], device=dev)
     assert numpy.array_equal(H2, E2) and numpy.array_equal(H1[0], E1[0])
     other = synth.make_system(name, ops=ops, with_bior=True, seed=78)["densities"][:2]
@@ -292,6 +294,8 @@ def test_plan_replays_get_xr_H_as_one_cuda_graph(dev, name, order, ops):
     _close(R2, O2)
     _close(R1[0], O1[0])
     assert numpy.array_equal(build(other)[1], R2)
+    chain = plan(ints, other, order, [ch, ch], device=dev, streams=1)
+    assert chain.n_streams == 1 and numpy.array_equal(chain()[1], R2)
 
 
 def test_device_inverse_converges_and_falls_back(dev):

@@ -644,3 +644,41 @@ def test_hermitian_plan_replays_get_xr_H_on_new_densities(order, ops):
     assert numpy.abs(R2 - H2).max() > 1e-3 * numpy.abs(H2).max()
     again = build(other)[1]
     assert numpy.array_equal(again, R2)
+
+
+@pytest.mark.parametrize("order,ops", [(0, synth.OPS_ORDER0), (1, synth.OPS_ORDER1)])
+def test_hermitian_schedule_dependencies_allow_any_valid_order(order, ops):
+    """hermitian/schedule.py: the dependencies worked out from the recorded arguments are sufficient -- the recorded
+    get_xr_H re-issued in a very different order that respects them (always the LAST ready call first) gives bit-identical
+    matrices -- and they are not trivial (most calls do not depend on their predecessor)"""
+    from qodeapplications_b200.hermitian.plan import plan
+    from qodeapplications_b200.hermitian import schedule
+    system = synth.make_system("toy", ops=ops, with_bior=True)
+    ch = system["charges"]
+    dev = FakeDevice()
+    build = plan((system["symm"], system["bior"], system["nuc"]), system["densities"][:2], order, [ch, ch], device=dev, verify=False)
+    H1, H2 = build()
+    deps = schedule.dependencies(build.trace)
+    n = len(build.trace)
+    assert sum(1 for i, d in enumerate(deps) if i and (i - 1) not in d) > n // 3
+    users = [[] for _ in range(n)]
+    missing = [len(d) for d in deps]
+    for i, d in enumerate(deps):
+        for j in d:
+            users[j].append(i)
+    ready = [i for i in range(n) if missing[i] == 0]
+    issued = []
+    while ready:
+        i = ready.pop()                      # the most recently readied / highest index first: far from program order
+        issued.append(i)
+        call, args, kwargs = build.trace[i]
+        call(dev.ctx, *args, **kwargs)
+        for u in users[i]:
+            missing[u] -= 1
+            if missing[u] == 0:
+                ready.append(u)
+                ready.sort()
+    assert len(issued) == n and issued != sorted(issued)
+    assert numpy.array_equal(build.H2.host(), H2) and numpy.array_equal(build.H1[0].host(), H1[0])
+    stream_of, cross = schedule.assign_streams(deps, 6)
+    assert len(set(stream_of)) > 1 and all(stream_of[j] != stream_of[i] for i, c in enumerate(cross) for j in c)
