@@ -127,14 +127,6 @@ int xr_download(xr_ctx* ctx, void* dst_host, const void* src_device, size_t byte
  * over K with a fixed-order second pass.  Requirements: A, B, C device pointers to doubles.  Rows must
  * be 16-byte aligned (even lda/ldb, 16-byte-aligned bases) for the TMA path; anything else takes a
  * cp.async-staged kernel with 8-byte copies (same results). */
-enum xr_accumulate {
-    XR_OVERWRITE = 0,               /* C[...]  = result */
-    XR_ACCUMULATE = 1,              /* C[...] += result (read-modify-write; launches that touch the same elements must be ordered) */
-    XR_ACCUMULATE_INTO_ZEROS = 2    /* the caller guarantees the target elements are zero: same result as either of the above, and the
-                                     * kernel may give an output tile to two CTAs (half of K each) that add their halves atomically --
-                                     * 0 + a + b is the same double in either order, so the result stays bit-reproducible.  Chosen
-                                     * automatically when the tile count fills the last wave of resident CTAs badly. */
-};
 int xr_gemm_scatter(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha,
                     const double* A, int64_t lda, const double* B, int64_t ldb,
                     double* C, const int64_t* offM, int64_t ldc, const int64_t* offN, int accumulate);

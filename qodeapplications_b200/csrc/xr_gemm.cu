@@ -200,6 +200,5 @@ extern "C" int xr_gemm_scatter(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, dou
         int rc = xr_gemm_scatter_tma(ctx, M, N, K, alpha, A, lda, B, ldb, C, offM, ldc, offN, accumulate);
         if (rc != XR_ERR_UNSUPPORTED) return rc;
     }
-    if (p.accumulate == 2) p.accumulate = 0;        // zeroed target: a plain store is an accumulation
     return vec16 ? launch_gemm<64, 64, 16, 2, 2, 2, true>(ctx, p) : launch_gemm<64, 64, 16, 2, 2, 2, false>(ctx, p);
 }

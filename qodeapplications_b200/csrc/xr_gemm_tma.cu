@@ -28,7 +28,7 @@ struct GemmTmaParams {
     unsigned long long* tile_counter;      // persistent kernel, dynamic scheduling: next tile to hand out (zeroed per launch)
 };
 
-enum { MODE_SCATTER = 0, MODE_REDUCE = 1, MODE_SPLITK = 2, MODE_SPLIT_ATOMIC = 3 };
+enum { MODE_SCATTER = 0, MODE_REDUCE = 1, MODE_SPLITK = 2 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
@@ -82,7 +82,7 @@ gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
     const int64_t group_m = p.tiles_m - first_m < GROUP_M ? p.tiles_m - first_m : GROUP_M;
     const int64_t m0 = (first_m + (tile % per_group) % group_m) * TBM, n0 = ((tile % per_group) / group_m) * TBN;
     int KT = (int)((p.K + TBK - 1) / TBK), kt_begin = 0;
-    if (MODE == MODE_SPLITK || MODE == MODE_SPLIT_ATOMIC) {      // this CTA owns k-tiles [kt_begin, kt_begin + KT) of its output tile
+    if (MODE == MODE_SPLITK) {      // this CTA owns k-tiles [kt_begin, kt_begin + KT) of its output tile
         kt_begin = (int)blockIdx.y * p.kt_per_split;
         KT = KT - kt_begin < p.kt_per_split ? KT - kt_begin : p.kt_per_split;
     }
@@ -149,27 +149,6 @@ gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
                 const int64_t col = n0 + warp_n * 32 + j * 8 + 2 * t;
                 if (col < p.N) ws[row * p.N + col] = acc[i][j][0];
                 if (col + 1 < p.N) ws[row * p.N + col + 1] = acc[i][j][1];
-            }
-        }
-        return;
-    }
-
-    if (MODE == MODE_SPLIT_ATOMIC) {
-        // Two CTAs share an output tile (half of K each) and ADD their halves into a target the caller guarantees to be zero:
-        // 0 + a + b and 0 + b + a are the same double, so the result does not depend on which CTA arrives first.  Used when
-        // the tile count fills the last wave of resident CTAs badly (2380^2 outputs: 1444 tiles on 592 slots = 2.44 waves).
-#pragma unroll
-        for (int i = 0; i < MI; ++i) {
-            const int64_t row = m0 + warp_m * 32 + i * 8 + g;
-            if (row >= p.M) continue;
-            const int64_t om = p.offM ? p.offM[row] : row * p.ldc;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int64_t col = n0 + warp_n * 32 + j * 8 + 2 * t + e;
-                    if (col < p.N) atomicAdd(p.C + om + (p.offN ? p.offN[col] : col), p.alpha * acc[i][j][e]);
-                }
             }
         }
         return;
@@ -733,21 +712,6 @@ int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alp
         XR_CUDA(cudaGetLastError());
         ctx->launches += 2;
         return XR_OK;
-    }
-    if (accumulate == 2) {
-        // zeroed target (the caller's promise): plain stores, unless two half-K CTAs per tile fill the machine better
-        const double waves = (double)tiles / (4.0 * ctx->sm_count);
-        const double e1 = waves / (double)(int64_t)(waves + 0.999999), e2 = 2 * waves / (double)(int64_t)(2 * waves + 0.999999);
-        if (KT >= 8 && waves < 8.0 && e2 - e1 > 0.08) {
-            p.kt_per_split = (int)((KT + 1) / 2);
-            p.accumulate = 1;
-            XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel<MODE_SPLIT_ATOMIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
-            gemm_tma_scatter_kernel<MODE_SPLIT_ATOMIC><<<dim3((unsigned)tiles, 2), TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
-            XR_CUDA(cudaGetLastError());
-            ctx->launches++;
-            return XR_OK;
-        }
-        p.accumulate = 0;
     }
     if (XR_GEMM_VARIANT == 0 || KT > XR_GEMM_PERSISTENT_MAX_KT) {
         XR_CUDA(cudaFuncSetAttribute(gemm_tma_scatter_kernel<MODE_SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));

@@ -352,8 +352,7 @@ class build_matrix_elements(object):
             off1 = self._index(lambda: c1.offsets(f1, f2.dim * D, f2.dim, bra_base=lo), ("off1", m1, m2, d1, lo, hi))
             off2 = self._index(lambda: c2.offsets(f2, D, 1), ("off2", m1, m2, d1))
             with self._timed(self, "dimer_class_d%+d" % d1, 2.0 * c1.P * c2.P * K, 8.0 * (c1.P * c2.P + (c1.P + c2.P) * K)):
-                # `out` was zero-filled above and the classes partition the block: every element is written exactly once
-                ctx.gemm_scatter(c1.P, c2.P, K, 1.0, A, ld, B, ld, out, off1, 0, off2, _lib.ACCUMULATE_INTO_ZEROS)
+                ctx.gemm_scatter(c1.P, c2.P, K, 1.0, A, ld, B, ld, out, off1, 0, off2, False)
         return out
 
     def H2_moments_device(self, m1, m2, shard=(0, 1), group=None, inspect=None):

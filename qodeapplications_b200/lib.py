@@ -205,7 +205,7 @@ class Context(object):
     @_recorded
     def gemm_scatter(self, M, N, K, alpha, A, lda, B, ldb, C, offM=None, ldc=0, offN=None, accumulate=False):
         check(self.lib.xr_gemm_scatter(self.handle, M, N, K, float(alpha), _p(A), lda, _p(B), ldb, _p(C), _p(offM),
-                                       ldc, _p(offN), 2 if accumulate == ACCUMULATE_INTO_ZEROS else (1 if accumulate else 0)), "xr_gemm_scatter")
+                                       ldc, _p(offN), 1 if accumulate else 0), "xr_gemm_scatter")
 
     @_recorded
     def gemm_stream(self, E1, s1, E2, s2, EK1, sk1, EK2, N, alpha, A, B, ldb, C, offM=None, ldc=0, offN=None, accumulate=False):
@@ -280,6 +280,5 @@ class Context(object):
                                         len(abc_host), _p(abc_host), _p(out)), "xr_trimer_sample")
 
 
-ACCUMULATE_INTO_ZEROS = 2      # xr_gemm_scatter: the target elements are zero (lets the kernel split K over two CTAs per tile)
 TRIMER_REDUCE = 0
 TRIMER_MATERIALIZE = 1
