@@ -259,7 +259,8 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     }
     __syncthreads();
 
-    constexpr bool ROTATE = XR_GEMM_VARIANT == 2, DYNAMIC = XR_GEMM_VARIANT == 3;
+    constexpr bool ROTATE = XR_GEMM_VARIANT == 2;
+    const bool DYNAMIC = XR_GEMM_VARIANT == 3 && p.tile_counter != nullptr;     // (no counter: every CTA has exactly one tile)
     __shared__ int64_t tile_ring[4];       // DYNAMIC: tile ids in hand-out order (-1 = no more), written by the issuer
 
     // producer state: the next k-tile to issue in this CTA's sequence.  Kept by EVERY thread (it is a function of the
@@ -269,6 +270,8 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     int64_t pq = 0, ptile = blockIdx.x, pm0 = 0, pn0 = 0, pseq = 0;
     int pkt = 0;
     bool drained = false;                  // DYNAMIC: the counter ran past the last tile (issuer's knowledge)
+    int64_t upcoming = 0;                  // DYNAMIC: tile id fetched ahead of its use (thread 0)
+    if (DYNAMIC && tid == 0) upcoming = (int64_t)atomicAdd(p.tile_counter, 1ull);
     auto issue_next = [&]() {
         if (DYNAMIC ? drained : pq >= total_q) return;
         const bool elected = ROTATE ? tid == 32 * (int)(pq % (TTHREADS / 32)) : tid == 0;
@@ -276,7 +279,10 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         if (elected) {
             mbar_wait(&empty[s], (uint32_t)((pq / TSTAGES) & 1) ^ 1);       // passes at once on the first lap
             if (DYNAMIC && pkt == 0) {
-                ptile = (int64_t)atomicAdd(p.tile_counter, 1ull);
+                // the id for THIS tile was requested one tile ago; the request for the next one goes out now, so the
+                // round trip of the atomic (the issuing thread's long-scoreboard stall in profiles/r02c) is off the path
+                ptile = upcoming;
+                upcoming = (int64_t)atomicAdd(p.tile_counter, 1ull);
                 if (ptile >= n_tiles) ptile = -1;
                 tile_ring[pseq & 3] = ptile;                                // published by the barrier arrival below
             }
@@ -720,7 +726,7 @@ int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alp
         ctx->launches++;
         return XR_OK;
     }
-    if (XR_GEMM_VARIANT == 3) {
+    if (XR_GEMM_VARIANT == 3 && tiles > (int64_t)ctx->sm_count * 4) {      // more tiles than resident CTAs: hand them out dynamically
         if (!ctx->counters) XR_CUDA(cudaMalloc(&ctx->counters, 256));
         XR_CUDA(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
         p.tile_counter = static_cast<unsigned long long*>(ctx->counters);
