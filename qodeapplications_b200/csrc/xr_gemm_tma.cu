@@ -55,7 +55,15 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
 #define XR_GEMM_PERSISTENT_MAX_KT 4
 #endif
 
+// ... and the ring depth of the persistent kernel: deeper rings prefetch further across tile boundaries but fewer CTAs fit an SM
+#ifndef XR_GEMM_PERSISTENT_STAGES
+#define XR_GEMM_PERSISTENT_STAGES 3
+#endif
+
 constexpr int TBM = 64, TBN = 64, TBK = 16, TSTAGES = 3, TTHREADS = 128;
+constexpr int PSTAGES = XR_GEMM_PERSISTENT_STAGES;
+constexpr size_t PERSISTENT_SMEM = (size_t)PSTAGES * (TBM + TBN) * TBK * 8 + 1024;
+constexpr int PCTAS = (int)((227 * 1024) / (PERSISTENT_SMEM + 1024 + 128)) < 4 ? (int)((227 * 1024) / (PERSISTENT_SMEM + 1024 + 128)) : 4;
 constexpr int TILE_A_BYTES = TBM * TBK * 8, TILE_B_BYTES = TBN * TBK * 8;     // 8 KB each, 1024-byte aligned
 constexpr int GROUP_M = 16;
 constexpr size_t TMA_SMEM = (size_t)TSTAGES * (TILE_A_BYTES + TILE_B_BYTES) + 1024;
@@ -224,17 +232,17 @@ gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
 }
 
 // Persistent variant of the scatter mode.  A CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... and its TMA ring runs
-// ACROSS tile boundaries: thread 0 keeps TSTAGES-1 k-tiles in flight in the CTA's global k-tile sequence, so the first
+// ACROSS tile boundaries: thread 0 keeps PSTAGES-1 k-tiles in flight in the CTA's global k-tile sequence, so the first
 // operand tiles of tile i+1 are already landing while the warps scatter tile i, and a stage is recycled through an `empty`
 // mbarrier (one arrival per warp) instead of a block-wide barrier per k-tile.  For the short-K charge-transfer classes
 // (d = +-1: K = 2n = 36 = three k-tiles, the whole K resident in the ring) a one-tile CTA spent more time being launched,
 // fetching its tensor maps and filling its pipeline than on its 1.2 us of DMMAs.
-__global__ void __launch_bounds__(TTHREADS, 4)
+__global__ void __launch_bounds__(TTHREADS, PCTAS)
 gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmTmaParams p) {
     constexpr int MI = 4, NJ = 4;      // 2 x 2 warps, each 32 x 32
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t full[TSTAGES], empty[TSTAGES];
+    __shared__ uint64_t full[PSTAGES], empty[PSTAGES];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -251,7 +259,7 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     };
 
     if (tid == 0) {
-        for (int s = 0; s < TSTAGES; ++s) {
+        for (int s = 0; s < PSTAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], TTHREADS / 32);
         }
@@ -275,9 +283,9 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     auto issue_next = [&]() {
         if (DYNAMIC ? drained : pq >= total_q) return;
         const bool elected = ROTATE ? tid == 32 * (int)(pq % (TTHREADS / 32)) : tid == 0;
-        const int s = (int)(pq % TSTAGES);
+        const int s = (int)(pq % PSTAGES);
         if (elected) {
-            mbar_wait(&empty[s], (uint32_t)((pq / TSTAGES) & 1) ^ 1);       // passes at once on the first lap
+            mbar_wait(&empty[s], (uint32_t)((pq / PSTAGES) & 1) ^ 1);       // passes at once on the first lap
             if (DYNAMIC && pkt == 0) {
                 // the id for THIS tile was requested one tile ago; the request for the next one goes out now, so the
                 // round trip of the atomic (the issuing thread's long-scoreboard stall in profiles/r02c) is off the path
@@ -307,13 +315,13 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         }
     };
     if (ROTATE || tid == 0) {
-        for (int s = 0; s < TSTAGES - 1; ++s) issue_next();
+        for (int s = 0; s < PSTAGES - 1; ++s) issue_next();
     }
 
     int64_t q = 0;
     for (int64_t tile = blockIdx.x, seq = 0; DYNAMIC || tile < n_tiles; tile += gridDim.x, ++seq) {
         if (DYNAMIC) {      // the tile id travels with the first k-tile of the tile: wait for it, then read the ring
-            mbar_wait(&full[q % TSTAGES], (uint32_t)(q / TSTAGES) & 1);
+            mbar_wait(&full[q % PSTAGES], (uint32_t)(q / PSTAGES) & 1);
             tile = tile_ring[seq & 3];
             if (tile < 0) break;
         }
@@ -338,9 +346,9 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         }
 
         for (int kt = 0; kt < KT; ++kt, ++q) {
-            const int s = (int)(q % TSTAGES);
-            if (ROTATE || tid == 0) issue_next();                // k-tile q + TSTAGES - 1 into the stage k-tile q - 1 used
-            mbar_wait(&full[s], (uint32_t)(q / TSTAGES) & 1);
+            const int s = (int)(q % PSTAGES);
+            if (ROTATE || tid == 0) issue_next();                // k-tile q + PSTAGES - 1 into the stage k-tile q - 1 used
+            mbar_wait(&full[s], (uint32_t)(q / PSTAGES) & 1);
             const unsigned char* as = smem + (size_t)s * (TILE_A_BYTES + TILE_B_BYTES);
             const unsigned char* bs = as + TILE_A_BYTES;
             const int ksteps = kt == KT - 1 ? last_ksteps : TBK / 4;
@@ -726,15 +734,16 @@ int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alp
         ctx->launches++;
         return XR_OK;
     }
-    if (XR_GEMM_VARIANT == 3 && tiles > (int64_t)ctx->sm_count * 4) {      // more tiles than resident CTAs: hand them out dynamically
+    if (XR_GEMM_VARIANT == 3 && tiles > (int64_t)ctx->sm_count * PCTAS) {      // more tiles than resident CTAs: hand them out dynamically
         if (!ctx->counters) XR_CUDA(cudaMalloc(&ctx->counters, 256));
         XR_CUDA(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
         p.tile_counter = static_cast<unsigned long long*>(ctx->counters);
     }
-    // persistent CTAs, 4 per SM (48 KB of ring + <= 128 registers each): one launch-and-fill per CTA instead of per tile
-    const int64_t resident = (int64_t)ctx->sm_count * 4;
-    XR_CUDA(cudaFuncSetAttribute(gemm_tma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
-    gemm_tma_persistent_kernel<<<(unsigned)(tiles < resident ? tiles : resident), TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
+    // persistent CTAs, PCTAS per SM (48 KB of ring + <= 128 registers each at the default depth): one launch-and-fill per CTA
+    // instead of per tile
+    const int64_t resident = (int64_t)ctx->sm_count * PCTAS;
+    XR_CUDA(cudaFuncSetAttribute(gemm_tma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PERSISTENT_SMEM));
+    gemm_tma_persistent_kernel<<<(unsigned)(tiles < resident ? tiles : resident), TTHREADS, PERSISTENT_SMEM, ctx->stream>>>(mapA, mapB, p);
     XR_CUDA(cudaGetLastError());
     ctx->launches++;
     return XR_OK;

@@ -44,9 +44,10 @@ def precise_inverse(S2, dev, contractor=None):
     S = S2 if isinstance(S2, DeviceTensor) else DeviceTensor(dev.upload(numpy.ascontiguousarray(S2, dtype=numpy.float64)), dev)
     n = S.shape[0]
     diag = contractor._table([n], [n + 1])
-    X = dev.zeros((n, n))
-    dev.ctx.scatter_const(X, diag, n, 1.0, False)
-    for _ in range(NEWTON_SCHULZ_STEPS):
+    X = dev.empty((n, n))                                       # the first step from X = I is X = 2 I - S2: no product needed
+    dev.ctx.copy2d_scaled(X, n, S.buf, n, n, n, -1.0)
+    dev.ctx.scatter_const(X, diag, n, 2.0, True)
+    for _ in range(NEWTON_SCHULZ_STEPS - 1):
         R = dev.empty((n, n))
         dev.ctx.gemm_scatter(n, n, n, -1.0, S.buf, n, _transposed(X, dev, n), n, R, None, n, None, False)    # R = -S X
         dev.ctx.scatter_const(R, diag, n, 2.0, True)                                                    # R = 2 I - S X

@@ -14,12 +14,12 @@ from qodeapplications_b200 import build as xr_build
 
 OUT = os.path.join(ROOT, "tools", "variants")
 VARIANTS = {
+    "shipped": [],
     "one_tile": ["-DXR_GEMM_VARIANT=0"],
-    "persistent_t0": ["-DXR_GEMM_VARIANT=1"],
-    "persistent_rotate": ["-DXR_GEMM_VARIANT=2"],
-    "persistent_dynamic": ["-DXR_GEMM_VARIANT=3"],
-    "persistent_shortK_only": ["-DXR_GEMM_VARIANT=1", "-DXR_GEMM_PERSISTENT_MAX_KT=4"],
-    "dynamic_shortK_only": ["-DXR_GEMM_VARIANT=3", "-DXR_GEMM_PERSISTENT_MAX_KT=4"],
+    "dynamic_4stages_3ctas": ["-DXR_GEMM_PERSISTENT_STAGES=4"],
+    "dynamic_5stages_2ctas": ["-DXR_GEMM_PERSISTENT_STAGES=5"],
+    "dynamic_6stages_2ctas": ["-DXR_GEMM_PERSISTENT_STAGES=6"],
+    "dynamic_6stages_allK": ["-DXR_GEMM_PERSISTENT_STAGES=6", "-DXR_GEMM_PERSISTENT_MAX_KT=1000000"],
 }
 
 
