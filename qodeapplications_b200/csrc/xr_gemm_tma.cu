@@ -61,6 +61,12 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
 #endif
 
 constexpr int TBM = 64, TBN = 64, TBK = 16, TSTAGES = 3, TTHREADS = 128;
+// ... and its warp count: 2 x WARPS_N warps on the 64 x 64 tile (2: 32 x 32 warp tiles, 64 accumulator registers; 4: 32 x 16 warp
+// tiles, half the registers per thread, twice the resident warps)
+#ifndef XR_GEMM_PERSISTENT_WARPS_N
+#define XR_GEMM_PERSISTENT_WARPS_N 2
+#endif
+constexpr int PWN = XR_GEMM_PERSISTENT_WARPS_N, PTHREADS = 2 * PWN * 32;
 constexpr int PSTAGES = XR_GEMM_PERSISTENT_STAGES;
 constexpr size_t PERSISTENT_SMEM = (size_t)PSTAGES * (TBM + TBN) * TBK * 8 + 1024;
 constexpr int PCTAS = (int)((227 * 1024) / (PERSISTENT_SMEM + 1024 + 128)) < 4 ? (int)((227 * 1024) / (PERSISTENT_SMEM + 1024 + 128)) : 4;
@@ -237,9 +243,9 @@ gemm_tma_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
 // mbarrier (one arrival per warp) instead of a block-wide barrier per k-tile.  For the short-K charge-transfer classes
 // (d = +-1: K = 2n = 36 = three k-tiles, the whole K resident in the ring) a one-tile CTA spent more time being launched,
 // fetching its tensor maps and filling its pipeline than on its 1.2 us of DMMAs.
-__global__ void __launch_bounds__(TTHREADS, PCTAS)
+__global__ void __launch_bounds__(PTHREADS, PCTAS)
 gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmTmaParams p) {
-    constexpr int MI = 4, NJ = 4;      // 2 x 2 warps, each 32 x 32
+    constexpr int MI = 4, NJ = 8 / PWN, WCOLS = NJ * 8;      // 2 x PWN warps, each 32 x WCOLS
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t full[PSTAGES], empty[PSTAGES];
@@ -261,7 +267,7 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     if (tid == 0) {
         for (int s = 0; s < PSTAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], TTHREADS / 32);
+            mbar_init(&empty[s], PTHREADS / 32);
         }
         fence_barrier_init();
     }
@@ -282,7 +288,7 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     if (DYNAMIC && tid == 0) upcoming = (int64_t)atomicAdd(p.tile_counter, 1ull);
     auto issue_next = [&]() {
         if (DYNAMIC ? drained : pq >= total_q) return;
-        const bool elected = ROTATE ? tid == 32 * (int)(pq % (TTHREADS / 32)) : tid == 0;
+        const bool elected = ROTATE ? tid == 32 * (int)(pq % (PTHREADS / 32)) : tid == 0;
         const int s = (int)(pq % PSTAGES);
         if (elected) {
             mbar_wait(&empty[s], (uint32_t)((pq / PSTAGES) & 1) ^ 1);       // passes at once on the first lap
@@ -337,7 +343,7 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         // with three k-tiles per tile those loads were a quarter of all stall samples when first touched after the k loop
         // (profiles/r02c).  Prefetches, not register loads: the kernel has no registers to spare at 4 CTAs per SM.
         if (p.offN) {
-            const int64_t col = n0 + warp_n * 32 + 2 * t + 8 * (g & 3);       // the lane's columns are 8j + 2t: j <-> g & 3
+            const int64_t col = n0 + warp_n * WCOLS + 2 * t + 8 * (g % NJ);       // the lane's columns are 8j + 2t: j <-> g % NJ
             if (col < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.offN + col));
         }
         if (p.offM) {
@@ -359,7 +365,7 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
 #pragma unroll
                 for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const double*>(as + swz(warp_m * 32 + i * 8 + g, ks * 4 + t));
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double*>(bs + swz(warp_n * 32 + j * 8 + g, ks * 4 + t));
+                for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double*>(bs + swz(warp_n * WCOLS + j * 8 + g, ks * 4 + t));
 #pragma unroll
                 for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -373,7 +379,7 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         int64_t on[NJ][2];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            int64_t col = n0 + warp_n * 32 + j * 8 + 2 * t;
+            int64_t col = n0 + warp_n * WCOLS + j * 8 + 2 * t;
             on[j][0] = col < p.N ? (p.offN ? p.offN[col] : col) : -1;
             on[j][1] = col + 1 < p.N ? (p.offN ? p.offN[col + 1] : col + 1) : -1;
         }
@@ -743,7 +749,7 @@ int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alp
     // instead of per tile
     const int64_t resident = (int64_t)ctx->sm_count * PCTAS;
     XR_CUDA(cudaFuncSetAttribute(gemm_tma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PERSISTENT_SMEM));
-    gemm_tma_persistent_kernel<<<(unsigned)(tiles < resident ? tiles : resident), TTHREADS, PERSISTENT_SMEM, ctx->stream>>>(mapA, mapB, p);
+    gemm_tma_persistent_kernel<<<(unsigned)(tiles < resident ? tiles : resident), PTHREADS, PERSISTENT_SMEM, ctx->stream>>>(mapA, mapB, p);
     XR_CUDA(cudaGetLastError());
     ctx->launches++;
     return XR_OK;

@@ -1,5 +1,10 @@
 mkdir -p gpurun_out
-( time timeout 800 python3 bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02k_reference_n1.json 2> gpurun_out/r02k_reference_n1.err ) 2>&1 | tail -n 3; cut -c1-400 gpurun_out/r02k_reference_n1.json
-( time timeout 850 python3 bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02k_bench_n1.json 2> gpurun_out/r02k_bench_n1.err ) 2>&1 | tail -n 3; python -c "
-import json; d=json.loads([l for l in open('gpurun_out/r02k_bench_n1.json') if l.startswith('{')][-1]); print(d['value'], d['ms_per_step'], d['build_time_s'], d['e2e']['value'], d['roofline']['frac'], d['clocks'], d['gpu_launches'])"; tail -n 3 gpurun_out/r02k_bench_n1.err
-timeout 200 python3 bench.py --workload cfg3 --steps 5 --warmup 3 | cut -c1-700
+timeout 900 python tools/gemm_variants.py run > gpurun_out/r02l_gemm_variants.jsonl 2> gpurun_out/r02l_gemm_variants.err; echo variants rc=$?
+python - <<'PY'
+import json
+for line in open('gpurun_out/r02l_gemm_variants.jsonl'):
+    try: r=json.loads(line)
+    except Exception: print('BAD', line[:200]); continue
+    c=r['classes']
+    print(r['variant'], r['parity'][:80], {k:(round(v['tflops'],2)) for k,v in c.items()} if isinstance(c,dict) else c[-400:])
+PY

@@ -15,11 +15,8 @@ from qodeapplications_b200 import build as xr_build
 OUT = os.path.join(ROOT, "tools", "variants")
 VARIANTS = {
     "shipped": [],
-    "one_tile": ["-DXR_GEMM_VARIANT=0"],
-    "dynamic_4stages_3ctas": ["-DXR_GEMM_PERSISTENT_STAGES=4"],
-    "dynamic_5stages_2ctas": ["-DXR_GEMM_PERSISTENT_STAGES=5"],
-    "dynamic_6stages_2ctas": ["-DXR_GEMM_PERSISTENT_STAGES=6"],
-    "dynamic_6stages_allK": ["-DXR_GEMM_PERSISTENT_STAGES=6", "-DXR_GEMM_PERSISTENT_MAX_KT=1000000"],
+    "warps8_4ctas": ["-DXR_GEMM_PERSISTENT_WARPS_N=4"],
+    "warps8_3ctas_4stages": ["-DXR_GEMM_PERSISTENT_WARPS_N=4", "-DXR_GEMM_PERSISTENT_STAGES=4"],
 }
 
 
