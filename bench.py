@@ -95,6 +95,7 @@ def parse_args():
     ap.add_argument("--assemble", default="auto", choices=["auto", "nccl", "ce"],
                     help="N > 1: how the H2 slabs are assembled (copy-engine pulls over NVLink peer memory; NCCL all-gather; auto = ce "
                          "where symmetric memory can be set up, else nccl)")
+    ap.add_argument("--graph-streams", type=int, default=8, help="hermitian workloads: streams the recorded launch sequence is spread over")
     ap.add_argument("--scale", type=float, default=0.0, help="cfg5: fraction of the 1000 states per fragment (0 = as many as the GPUs present hold)")
     return ap.parse_args()
 
@@ -597,7 +598,7 @@ def run_hermitian(args):
                     blocks[sector] = torch.from_numpy(numpy.ascontiguousarray(blocks[sector])).pin_memory().numpy()
     dev = Device(local_rank)
     # N > 1: every rank holds a replica and runs the same build (this path does not shard below ~1e3 states; replicas only)
-    build = plan(ints, dens, xr_order, [ch, ch], device=dev)
+    build = plan(ints, dens, xr_order, [ch, ch], device=dev, streams=args.graph_streams)
     trace_flops = sum(2.0 * a[0] * a[1] * a[2] for call, a, k in build.trace if call.__name__ == "gemm_scatter")
     density_bytes = sum(slot.buf.numel() * 8 for slot in build.slots.values())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev.torch_device) if args.workload == "cfg2" else None
