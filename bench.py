@@ -95,7 +95,7 @@ def parse_args():
     ap.add_argument("--assemble", default="auto", choices=["auto", "nccl", "ce"],
                     help="N > 1: how the H2 slabs are assembled (copy-engine pulls over NVLink peer memory; NCCL all-gather; auto = ce "
                          "where symmetric memory can be set up, else nccl)")
-    ap.add_argument("--graph-streams", type=int, default=8, help="hermitian workloads: streams the recorded launch sequence is spread over")
+    ap.add_argument("--graph-streams", type=int, default=32, help="hermitian workloads: streams the recorded launch sequence is spread over")
     ap.add_argument("--scale", type=float, default=0.0, help="cfg5: fraction of the 1000 states per fragment (0 = as many as the GPUs present hold)")
     return ap.parse_args()
 

@@ -42,7 +42,7 @@ def _density_blocks(dens):
 
 
 class plan(object):
-    def __init__(self, ints, dens, xr_order, monomer_charges, device=None, graph=True, verify=True, streams=8):
+    def __init__(self, ints, dens, xr_order, monomer_charges, device=None, graph=True, verify=True, streams=32):
         """streams > 1: the recorded calls are placed on that many streams according to their real data dependencies
         (hermitian/schedule.py) before the graph is captured, so independent diagram GEMMs overlap on the GPU."""
         self.dev = dev = device or default_device()

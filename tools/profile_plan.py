@@ -49,12 +49,22 @@ for kind, args, e0, e1 in events:
     g["calls"] += 1
     g["ms"] += ms
     g["bytes"] += nbytes
+# the critical path of the recorded sequence under its real data dependencies (hermitian/schedule.py): what a perfect
+# multi-stream placement could reach, with these per-call times
+from qodeapplications_b200.hermitian import schedule
+deps = schedule.dependencies(build.trace)
+finish, longest = [], 0.0
+for i, (kind, args, e0, e1) in enumerate(events):
+    start = max([finish[j] for j in deps[i]] + [0.0])
+    finish.append(start + e0.elapsed_time(e1))
+    longest = max(longest, finish[-1])
 rows = sorted(groups.items(), key=lambda kv: -kv[1]["ms"])
 by_kind = {}
 for kind, args, e0, e1 in events:
     k = by_kind.setdefault(kind, {"calls": 0, "ms": 0.0})
     k["calls"] += 1
     k["ms"] += e0.elapsed_time(e1)
-print(json.dumps({"workload": name, "calls": len(events), "total_ms_between_events": total, "by_kind": by_kind,
+print(json.dumps({"workload": name, "calls": len(events), "total_ms_between_events": total, "critical_path_ms": longest,
+                  "dependency_edges": sum(len(d) for d in deps), "by_kind": by_kind,
                   "top": [dict(what=k, calls=v["calls"], ms=round(v["ms"], 3), gbs=round(v["bytes"] / v["ms"] / 1e6, 1) if v["ms"] else None)
                           for k, v in rows[:top]]}))
