@@ -52,6 +52,16 @@ def _worker(rank, world, port, out_dir, gpu=False):
     moments = build.reduced_moments()
     payload = {"H2_%d%d" % k: _np(build.full(*k)) for k in dimers}
     payload["moments"] = numpy.array(moments[(0, 1, 2)])
+    payload["assemble"] = numpy.array(build.assemble)
+    # both assemble modes, asked for by name, and steps repeated on the same buffers (the copy-engine gather's closing
+    # barrier is what keeps a rank from rewriting a slab a peer still reads); on CPU / gloo "ce" falls back to the collective
+    for mode in ("nccl", "ce"):
+        again = sharded_build(eng, dimers, [(0, 1, 2)], rank, world, assemble=mode)
+        for _ in range(3):
+            again.step(gather=True)
+        for k in dimers:
+            payload["H2_%d%d_%s" % (k + (mode,))] = _np(again.full(*k))
+        payload["assemble_" + mode] = numpy.array(again.assemble)
     # streamed dimer with the factor exchange (all-gather of the fragment-2 factor slabs)
     t = eng.H2_moments_device(0, 2, shard=(rank, world))
     dist.all_reduce(t)
@@ -94,6 +104,8 @@ def test_two_rank_sharded_build_matches_reference(tmp_path):
         for m1, m2 in itertools.combinations(range(3), 2):          # every rank holds the assembled H2
             ref = g["H2_%d%d" % (m1, m2)]
             assert numpy.abs(out["H2_%d%d" % (m1, m2)] - ref).max() <= 1e-10 * numpy.abs(ref).max()
+            for mode in ("nccl", "ce"):
+                assert numpy.array_equal(out["H2_%d%d_%s" % (m1, m2, mode)], out["H2_%d%d" % (m1, m2)])
         assert abs(out["moments"][1] - (ref3 ** 2).sum()) <= 1e-10 * (ref3 ** 2).sum()
         assert abs(out["moments"][0] - ref3.sum()) <= 1e-9 * numpy.abs(ref3).sum()
         ref2 = g["H2_02"]

@@ -26,6 +26,10 @@ def test_two_rank_sharded_build_over_nccl(tmp_path):
         for m1, m2 in itertools.combinations(range(3), 2):
             ref = g["H2_%d%d" % (m1, m2)]
             assert numpy.abs(out["H2_%d%d" % (m1, m2)] - ref).max() <= 1e-10 * numpy.abs(ref).max()
+            for mode in ("nccl", "ce"):       # both assemble modes by name, three steps each on the same buffers
+                assert numpy.array_equal(out["H2_%d%d_%s" % (m1, m2, mode)], out["H2_%d%d" % (m1, m2)])
+        assert str(out["assemble_nccl"]) == "nccl"
+        print("assemble modes used on this box:", str(out["assemble"]), str(out["assemble_ce"]))
         assert abs(out["moments"][1] - (ref3 ** 2).sum()) <= 1e-10 * (ref3 ** 2).sum()
         ref2 = g["H2_02"]
         assert abs(out["dimer_moments"][1] - (ref2 ** 2).sum()) <= 1e-11 * (ref2 ** 2).sum()
