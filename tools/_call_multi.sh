@@ -2,18 +2,6 @@
 N=$1
 mkdir -p gpurun_out
 export MASTER_ADDR=127.0.0.1
-run() { # name, nproc, extra args
-  timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --gpus $2 ${@:3} > gpurun_out/$1.json 2> gpurun_out/$1.err
-  echo "$1 rc=$?"; tail -c 1800 gpurun_out/$1.json; tail -n 4 gpurun_out/$1.err | cut -c1-400
-}
-if [ "$N" = "2" ]; then
-  timeout 900 python -m pytest tests/test_zz_distributed_gpu.py -m gpu -q -p no:cacheprovider > gpurun_out/r02d_pytest_nccl.log 2>&1; echo pytest nccl rc=$?; tail -n 8 gpurun_out/r02d_pytest_nccl.log
-  run r02d_bench_cfg4_n2_nccl 2 --steps 4 --warmup 3
-  run r02d_bench_cfg4_n2_ce 2 --steps 4 --warmup 3 --assemble ce --no-e2e
-fi
-if [ "$N" = "8" ]; then
-  run r02f_bench_cfg4_n8 8 --steps 8 --warmup 4
-  run r02f_bench_cfg4_n4 4 --steps 4 --warmup 3 --no-e2e
-  run r02f_bench_cfg4_n8_nccl 8 --steps 4 --warmup 3 --assemble nccl --no-e2e
-  run r02f_bench_cfg5_n8 8 --workload cfg5 --steps 2 --warmup 1
-fi
+timeout 900 python -m pytest tests/test_zz_distributed_gpu.py -m gpu -q -s -p no:cacheprovider > gpurun_out/r02o_pytest_nccl.log 2>&1; echo pytest nccl rc=$?; tail -n 12 gpurun_out/r02o_pytest_nccl.log | cut -c1-300
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --workload cfg1 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02o_bench_cfg1_n2.json 2> gpurun_out/r02o_bench_cfg1_n2.err; echo cfg1 n2 rc=$?; python -c "
+import json; d=json.loads([l for l in open('gpurun_out/r02o_bench_cfg1_n2.json') if l.startswith('{')][-1]); print(d['n_gpus'], d['ms_per_step'], d['value'], d['scaling'], d['e2e']['seconds_per_step'])"; tail -n 3 gpurun_out/r02o_bench_cfg1_n2.err | cut -c1-300
