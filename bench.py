@@ -822,8 +822,8 @@ def run_cfg5(args):
 
 def main():
     args = parse_args()
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (rank 0 prints ONE JSON line); INFO etc. stay
+    # NCCL_DEBUG is left exactly as the caller set it: unset, NCCL prints nothing and stdout is the ONE JSON line; VERSION / WARN /
+    # INFO (a driver checking the communicator) print NCCL's own lines first -- the JSON line is always the last one
     if args.impl == "reference":
         run_reference(args)
     else:
