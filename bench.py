@@ -822,8 +822,11 @@ def run_cfg5(args):
 
 def main():
     args = parse_args()
-    # NCCL_DEBUG is left exactly as the caller set it: unset, NCCL prints nothing and stdout is the ONE JSON line; VERSION / WARN /
-    # INFO (a driver checking the communicator) print NCCL's own lines first -- the JSON line is always the last one
+    # stdout carries ONE JSON line.  This image's NCCL configuration prints a version banner to stdout when NCCL_DEBUG is unset
+    # (and also at WARN); an unrecognised level ("NONE") is NCCL's way to say nothing.  A caller that sets NCCL_DEBUG itself (a
+    # driver checking the communicator with INFO) keeps it: NCCL's lines then come first, the JSON line is always the last one.
+    if "NCCL_DEBUG" not in os.environ:
+        os.environ["NCCL_DEBUG"] = "NONE"
     if args.impl == "reference":
         run_reference(args)
     else:
