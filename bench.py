@@ -822,11 +822,8 @@ def run_cfg5(args):
 
 def main():
     args = parse_args()
-    # stdout carries ONE JSON line.  This image's NCCL configuration prints a version banner to stdout when NCCL_DEBUG is unset
-    # (and also at WARN); an unrecognised level ("NONE") is NCCL's way to say nothing.  A caller that sets NCCL_DEBUG itself (a
-    # driver checking the communicator with INFO) keeps it: NCCL's lines then come first, the JSON line is always the last one.
-    if "NCCL_DEBUG" not in os.environ:
-        os.environ["NCCL_DEBUG"] = "NONE"
+    # NCCL_DEBUG is left as the caller set it (a driver checking the communicator sets INFO).  At N > 1 this image's NCCL prints a
+    # one-line version banner to stdout whatever the level; rank 0's JSON line is always the LAST line of stdout.
     if args.impl == "reference":
         run_reference(args)
     else:
