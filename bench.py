@@ -352,7 +352,8 @@ def run_general(args):
         def dimers_only(gather, overlap=True):
             return lambda: build.step(gather=gather, trimers=[], overlap=overlap)
         compute_ms = timed(dimers_only(False), 3)
-        extras["dimer_phase"] = {"compute_ms": compute_ms, "h2_bytes_written_all_ranks": sum(8.0 * (dims[a] * dims[b]) ** 2 for a, b in dimers),
+        extras["dimer_phase"] = {"compute_ms": compute_ms, "tflops_all_ranks": flops_dimers / (compute_ms * 1e-3) / 1e12,
+                                 "h2_bytes_written_all_ranks": sum(8.0 * (dims[a] * dims[b]) ** 2 for a, b in dimers),
                                  "note": "every H1 + all %d H2 of one build, this rank's bra slabs; zero fill of the dense blocks included" % len(dimers)}
         if world > 1:
             with_gather_ms = timed(dimers_only(True, overlap=False), 3)
