@@ -400,6 +400,8 @@ def run_general(args):
             eng.drop_caches(densities=True)
             dev.h2d_bytes = dev.d2h_bytes = 0
             copied[0] = 0
+            if world > 1:          # every density crosses PCIe on ONE rank and reaches the others over NVLink
+                eng.preload_distributed(rank, world)
             chosen = [trimers[cursor[0] % len(trimers)]] if trimers else []
             flops = step(gather=True, after_dimers=read_back_dimers)
             d2h = copied[0]
@@ -431,9 +433,9 @@ def run_general(args):
         e2e = {"value": e2e_flops / (float(tms.item()) * 1e-3) / 1e12, "unit": UNIT,
                "h2d_bytes_per_step": int(byt[0].item() / e2e_steps), "d2h_bytes_per_step": int(byt[1].item() / e2e_steps),
                "seconds_per_step": float(tms.item()) * 1e-3 / e2e_steps, "steps": e2e_steps,
-               "note": "host wall clock (max over ranks) around, every step: upload of every density from pinned host memory, the "
-                       "build, download of every H1, this rank's H2 slabs and the step's H3 moments; the H2 slabs are read back "
-                       "on a second stream while the trimer phase runs"}
+               "note": "host wall clock (max over ranks) around, every step: upload of every density from pinned host memory (N > 1: each "
+                       "block by one rank, broadcast to the others over NVLink), the build, download of every H1, this rank's H2 "
+                       "slabs and the step's H3 moments; the H2 slabs are read back on a second stream while the trimer phase runs"}
 
     if rank != 0:
         if world > 1:

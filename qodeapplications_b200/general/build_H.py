@@ -268,6 +268,45 @@ class build_matrix_elements(object):
                 for sector in rho[m].get(op, {}):
                     self._rho(m, op, sector)
 
+    def preload_distributed(self, rank, world, group=None, fragments=None, ops=("a", "c", "aa", "cc", "ca", "caa", "cca")):
+        """Multi-GPU variant of preload(): every density block is uploaded over PCIe by ONE rank (blocks dealt out so that
+        the ranks carry equal bytes) and reaches the others by a broadcast over NVLink -- N ranks that each need all the
+        densities then move them across the host links once instead of N times (cfg4 at N = 8: 4 GB instead of 25 GB).
+        Only for engines that hold full densities (no held= slabs)."""
+        import torch.distributed as dist
+        if world == 1:
+            return self.preload(fragments, ops)
+        if self._held:
+            raise ValueError("preload_distributed: this engine holds bra slabs (held=); every rank uploads its own")
+        rho = self.data[0]
+        keys = []
+        for m in (range(len(rho)) if fragments is None else fragments):
+            info = self._frag(m)
+            for op in ops:
+                for sector in sorted(rho[m].get(op, {})):
+                    block = rho[m][op][sector]
+                    if isinstance(block, torch.Tensor):
+                        continue                                    # already on the device
+                    rows = info.n_states[sector[0]] * info.n_states[sector[1]]
+                    keys.append((rows * info.n_orb ** len(op), m, op, sector, rows))
+        load, owner = [0] * world, {}
+        for size, m, op, sector, rows in sorted(keys, key=lambda k: (-k[0], k[1], k[2], k[3])):      # same deal on every rank
+            r = min(range(world), key=lambda x: (load[x], x))
+            owner[(m, op, sector)] = r
+            load[r] += size
+        pending = []
+        for size, m, op, sector, rows in keys:
+            key = (m, op, sector)
+            if key in self._rho_dev:
+                continue
+            if owner[key] == rank:
+                t = self._rho(m, op, sector)
+            else:
+                t = self._rho_dev[key] = self.dev.empty((rows, self._frag(m).n_orb ** len(op)))
+            pending.append(dist.broadcast(t, src=owner[key], group=group, async_op=True))
+        for work in pending:
+            work.wait()
+
     # ----- factor builders: fill columns [col0, col0+F) of a [P, ld] class buffer -------------
     def _fill_raw(self, out, ld, col0, m, op, cls, sign=None):
         ctx = self.dev.ctx

@@ -53,6 +53,13 @@ def _worker(rank, world, port, out_dir, gpu=False):
     payload = {"H2_%d%d" % k: _np(build.full(*k)) for k in dimers}
     payload["moments"] = numpy.array(moments[(0, 1, 2)])
     payload["assemble"] = numpy.array(build.assemble)
+    # inputs uploaded once and broadcast: an engine whose densities arrived that way builds the same blocks
+    eng_b = build_matrix_elements(system["fragments"], system["symm"], system["nuc"], device=make_device())
+    eng_b.preload_distributed(rank, world)
+    payload["h2d_broadcast"] = numpy.array(eng_b.dev.h2d_bytes)
+    payload["H2_01_broadcast_inputs"] = _np(eng_b.H2_device(0, 1))
+    payload["h2d_everything"] = numpy.array(sum(numpy.asarray(b).nbytes for f in system["fragments"] for op in ("a", "c", "aa", "cc", "ca", "caa", "cca")
+                                                for b in f.rho[op].values()))
     # both assemble modes, asked for by name, and steps repeated on the same buffers (the copy-engine gather's closing
     # barrier is what keeps a rank from rewriting a slab a peer still reads); on CPU / gloo "ce" falls back to the collective
     for mode in ("nccl", "ce"):
@@ -106,6 +113,9 @@ def test_two_rank_sharded_build_matches_reference(tmp_path):
             assert numpy.abs(out["H2_%d%d" % (m1, m2)] - ref).max() <= 1e-10 * numpy.abs(ref).max()
             for mode in ("nccl", "ce"):
                 assert numpy.array_equal(out["H2_%d%d_%s" % (m1, m2, mode)], out["H2_%d%d" % (m1, m2)])
+        ref = g["H2_01"]
+        assert numpy.abs(out["H2_01_broadcast_inputs"] - ref).max() <= 1e-10 * numpy.abs(ref).max()
+        assert 0 < int(out["h2d_broadcast"]) < 0.75 * int(out["h2d_everything"]) + 4096        # this rank uploaded about half
         assert abs(out["moments"][1] - (ref3 ** 2).sum()) <= 1e-10 * (ref3 ** 2).sum()
         assert abs(out["moments"][0] - ref3.sum()) <= 1e-9 * numpy.abs(ref3).sum()
         ref2 = g["H2_02"]

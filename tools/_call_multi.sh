@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-env | grep -i nccl; echo "--- env above"
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 2 --workload cfg3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02p_bench_cfg3_n2.json 2> gpurun_out/r02p_bench_cfg3_n2.err; echo rc=$?; wc -l gpurun_out/r02p_bench_cfg3_n2.json; head -c 150 gpurun_out/r02p_bench_cfg3_n2.json; echo; NCCL_DEBUG=INFO timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 2 --workload cfg3 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r02p_info.out 2> gpurun_out/r02p_info.err; grep -c "NCCL INFO" gpurun_out/r02p_info.out gpurun_out/r02p_info.err; grep -h "nranks" gpurun_out/r02p_info.out gpurun_out/r02p_info.err | head -3 | cut -c1-200; tail -n 1 gpurun_out/r02p_info.out | cut -c1-80; true
+export MASTER_ADDR=127.0.0.1
+timeout 600 python -m pytest tests/test_zz_distributed_gpu.py -m gpu -q -p no:cacheprovider > gpurun_out/r02q_pytest_nccl.log 2>&1; echo pytest nccl rc=$?; tail -n 4 gpurun_out/r02q_pytest_nccl.log | cut -c1-300
+timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 8 --warmup 4 > gpurun_out/r02q_bench_cfg4_n8.json 2> gpurun_out/r02q_bench_cfg4_n8.err; echo n8 rc=$?; python -c "
+import json; d=json.loads([l for l in open('gpurun_out/r02q_bench_cfg4_n8.json') if l.startswith('{')][-1]); print(d['value'], d['ms_per_step'], d['build_time_s']); print({k:v for k,v in d['e2e'].items() if k!='note'}); print(d['step_ms_by_assemble_mode'], d['assemble'], d['dimer_phase'])"; tail -n 3 gpurun_out/r02q_bench_cfg4_n8.err | cut -c1-300
