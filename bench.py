@@ -374,6 +374,33 @@ def run_general(args):
             build.step(gather=False, trimers=[ms_])
     moments = build.reduced_moments()
 
+    # ---- the other consumers of the same tile stream on one full-size trimer (N = 1): the screened COO build and the
+    #      caller-given elements -- outputs a solver can use, where the moment reducer only certifies that every element was formed
+    if not args.no_extras and world == 1 and trimers:
+        ms_ = trimers[0]
+        n_elements = sum(v for k, v in counts.items() if k[0] == "trimer") / len(trimers)
+        rms = (moments[ms_][1] / n_elements) ** 0.5
+        tau = 6.0 * rms
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        idx, val = eng.H3_sparse(*ms_, tau)
+        took = time.perf_counter() - t0
+        rng = numpy.random.default_rng(0)
+        st = [f.state_indices for f in system["fragments"]]
+        pick = lambda: tuple(st[m][int(rng.integers(len(st[m])))] for m in ms_)
+        I, J = [pick() for _ in range(2000)], [pick() for _ in range(2000)]
+        t0 = time.perf_counter()
+        elements = eng.H3_elements(*ms_, I, J)
+        took_s = time.perf_counter() - t0
+        extras["trimer_consumers"] = {
+            "trimer": "".join(map(str, ms_)),
+            "threshold": {"tau": tau, "tau_over_rms": 6.0, "kept": int(len(idx)), "of_elements": n_elements, "seconds": took,
+                          "tflops": flops_trimer[ms_] / took / 1e12, "max_abs_kept": float(numpy.abs(val).max()) if len(val) else None,
+                          "note": "xr_trimer_threshold over all 12 classes of one trimer: every |H3| > tau as a sorted COO list (host wall clock, "
+                                  "list download and sort included)"},
+            "sample": {"requested": len(I), "non_zero": int(numpy.count_nonzero(elements)), "seconds": took_s,
+                       "note": "xr_trimer_sample: 2000 random <I|H3|J> picked out of the streamed tiles (factor build of the 12 classes included)"}}
+
     # ---- end-to-end: pinned host inputs -> upload -> build -> results read back to pinned host
     e2e = None
     if not args.no_e2e:
