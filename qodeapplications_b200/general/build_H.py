@@ -680,10 +680,13 @@ class build_matrix_elements(object):
             out[mine] = self.dev.download(vals)
         return out
 
-    def H3_sparse(self, m1, m2, m3, tau, capacity=1 << 22, shard=(0, 1)):
+    def H3_sparse(self, m1, m2, m3, tau, capacity=1 << 22, shard=(0, 1), classes=None, count_only=False, max_elements=1 << 28):
         """Screened H3[m1][m2][m3]: (flat indices into the dense [D, D] block in test_H.py:113-126 ordering, values) of every
         element with |H3| > tau, sorted by index (host ndarrays) -- the compaction consumer of the tile stream
-        (xr_trimer_threshold).  shard=(rank, world) restricts to this rank's slab of each class's leading pair index."""
+        (xr_trimer_threshold).  shard=(rank, world) restricts to this rank's slab of each class's leading pair index;
+        classes (indices into the 12 charge-transfer classes) restricts to those; count_only=True returns the number of
+        elements above tau per class ({class index: count}) without storing anything.  A list longer than max_elements raises
+        MemoryError (with the exact count) instead of trying to allocate it."""
         ms = (m1, m2, m3)
         f = [self._frag(m) for m in ms]
         D = f[0].dim * f[1].dim * f[2].dim
@@ -691,8 +694,10 @@ class build_matrix_elements(object):
         rank, world = shard
         ctx = self.dev.ctx
         count = self.dev.zeros((1,), dtype=torch.int64)
-        idx_parts, val_parts = [], []
-        for cl in self._trimer_classes(ms):
+        idx_parts, val_parts, counted = [], [], {}
+        for which, cl in enumerate(self._trimer_classes(ms)):
+            if classes is not None and which not in classes:
+                continue
             fac = self._trimer_factors(ms, cl)
             if fac is None:
                 continue
@@ -700,6 +705,12 @@ class build_matrix_elements(object):
                     for role, cls in ((cl["k"], fac["ck"]), (cl["b"], fac["cb"]), (cl["c"], fac["cc"]))]
             Pa = fac["ck"].P
             a_lo, a_hi = Pa * rank // world, Pa * (rank + 1) // world
+            if count_only:
+                ctx.trimer_threshold(fac["n"], Pa, fac["cb"].P, fac["cc"].P, fac["alpha"], fac["W"], fac["ldw"], fac["beta"],
+                                     fac["beta"].shape[1], fac["gamma"], fac["gamma"].shape[1], a_lo, a_hi, tau, offs[0], offs[1],
+                                     offs[2], 0, None, None, count)
+                counted[which] = int(self.dev.download(count)[0])
+                continue
             cap = int(capacity)
             while True:
                 idx = self.dev.empty((cap,), dtype=torch.int64)
@@ -710,9 +721,15 @@ class build_matrix_elements(object):
                 kept = int(self.dev.download(count)[0])
                 if kept <= cap:
                     break
+                if kept > max_elements:
+                    raise MemoryError("H3_sparse: %d elements of class %d are above tau = %g (max_elements = %d): raise tau"
+                                      % (kept, which, tau, max_elements))
+                del idx, val
                 cap = kept          # the list overflowed: the count is exact, run the class again with room for all of it
             idx_parts.append(self.dev.download(idx[:kept]))
             val_parts.append(self.dev.download(val[:kept]))
+        if count_only:
+            return counted
         if not idx_parts:
             return numpy.zeros(0, dtype=numpy.int64), numpy.zeros(0)
         idx, val = numpy.concatenate(idx_parts), numpy.concatenate(val_parts)

@@ -65,6 +65,12 @@ def test_general_trimer_consumers_host_logic(name):
     _close(val, dense.reshape(-1)[keep], 1e-13)
     parts = [eng.H3_sparse(0, 1, 2, tau, shard=(r, 2)) for r in range(2)]
     assert numpy.array_equal(numpy.sort(numpy.concatenate([q[0] for q in parts])), keep)
+    counts = eng.H3_sparse(0, 1, 2, tau, count_only=True)
+    assert sum(counts.values()) == len(keep)
+    some = sorted(counts)[:5]
+    assert len(eng.H3_sparse(0, 1, 2, tau, classes=some)[0]) == sum(counts[c] for c in some)
+    with pytest.raises(MemoryError):
+        eng.H3_sparse(0, 1, 2, 0.0, capacity=1, max_elements=3)
 
 
 def test_general_bra_slabs_host_logic():
