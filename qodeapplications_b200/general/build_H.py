@@ -358,11 +358,14 @@ class build_matrix_elements(object):
             ca, first = self._rho_rows(m, "ca", ci, cj, i_lo, i_hi)
             ctx.gemm_scatter(rows, 1, n * n, 1.0, ca.data_ptr() + 8 * first, n * n, h, n * n, H, off.data_ptr() + 8 * row0, 0, None, False)
             h_lo, h_hi = self._held_range(m, ci)
-            scal = rho[m]["ccaa"][(ci, cj)]
-            if isinstance(scal, torch.Tensor):      # device-resident (general.build_density_tensors(device_result=True))
-                scal = scal.reshape((h_hi - h_lo) * N, 1)
-            else:
-                scal = self.dev.upload(numpy.asarray(scal, dtype=numpy.float64).reshape((h_hi - h_lo) * N, 1))
+            scal = self._rho_dev.get((m, "ccaa", (ci, cj)))
+            if scal is None:
+                scal = rho[m]["ccaa"][(ci, cj)]
+                if isinstance(scal, torch.Tensor):      # device-resident (general.build_density_tensors(device_result=True))
+                    scal = scal.reshape((h_hi - h_lo) * N, 1)
+                else:
+                    scal = self.dev.upload(numpy.asarray(scal, dtype=numpy.float64).reshape((h_hi - h_lo) * N, 1))
+                self._rho_dev[(m, "ccaa", (ci, cj))] = scal      # an input like every other density (drop_caches clears it)
             ctx.gemm_scatter(rows, 1, 1, 1.0, scal.data_ptr() + 8 * (i_lo - h_lo) * N, 1, one, 2, H, off.data_ptr() + 8 * row0, 0, None, True)
             held_pos.append(info.pos[ci][i_lo:i_hi])
         held_pos = numpy.concatenate(held_pos)
@@ -386,7 +389,7 @@ class build_matrix_elements(object):
             out = self.dev.zeros(((hi - lo) * f2.dim, D))
         else:
             assert out.shape == ((hi - lo) * f2.dim, D)
-            out.zero_()
+            ctx.memset_zero(out, out.numel() * 8)        # (a library call, so that a recorded build contains it)
         for d1, c1, c2, A, B, K, ld in self._dimer_class_factors(m1, m2, (lo, hi) if bra_range is not None else None):
             off1 = self._index(lambda: c1.offsets(f1, f2.dim * D, f2.dim, bra_base=lo), ("off1", m1, m2, d1, lo, hi))
             off2 = self._index(lambda: c2.offsets(f2, D, 1), ("off2", m1, m2, d1))

@@ -21,6 +21,7 @@ FP64 kernel (all 64 K registers of each SM).  Two ways to run it, both off the l
 torch.distributed is plumbing here (NCCL on GPUs, gloo in the CPU tests); the arithmetic is in
 libxr_b200.so.
 """
+import numpy
 import torch
 import torch.distributed as dist
 
@@ -164,6 +165,12 @@ class sharded_build(object):
         if self.peer in pending:
             self.peer.join()       # the launch stream waits for the last pull and the closing barrier (no host block)
 
+    def recorded(self, streams=16, graph=True, **step_arguments):
+        """This build's step() recorded once and replayed as ONE CUDA graph (single rank): for the small systems the
+        reference loops over (Be2 / Be3 shapes: a step is a few hundred launches whose Python planning costs ten times the
+        GPU work).  Returns a recorded_step; its outputs are this object's H1 / H2 / H3_moments buffers."""
+        return recorded_step(self, streams, graph, step_arguments)
+
     def gather_bytes(self):
         """bytes this rank RECEIVES over NVLink per step for the dimer all-gathers (the other ranks' slabs)"""
         total = 0
@@ -181,3 +188,42 @@ class sharded_build(object):
                 dist.all_reduce(t, group=self.group)
             out[ms] = [float(x) for x in self.eng.dev.download(t).sum(axis=0)]
         return out
+
+
+class recorded_step(object):
+    """sharded_build.step() as a recorded launch sequence (recording.launch_graph).  Inputs are the engine's device copies
+    of the densities (build_matrix_elements._rho_dev): update(fragments) copies new values into them, run() launches the
+    graph, and the results are in build.H1 / build.full(m1, m2) / build.H3_moments afterwards."""
+    def __init__(self, build, streams=16, graph=True, step_arguments=None):
+        from ..recording import launch_graph
+        if build.world != 1:
+            raise NotImplementedError("recorded_step: one rank (the assemble collectives are not recorded)")
+        self.build, self.arguments = build, dict(step_arguments or {})
+        eng, dev = build.eng, build.eng.dev
+        eng.preload()
+        build.step(**self.arguments)                          # eager: sizes the context scratch, fills the table caches
+        dev.begin_trace()
+        try:
+            build.step(**self.arguments)
+        finally:
+            self.trace, self._alive = dev.end_trace()
+        self.launches = len(self.trace)
+        known = [t for t in self._alive if t.dtype == torch.int64] + [t for t in eng._idx_dev.values()]
+        self._launcher = launch_graph(dev, self.trace, streams=streams, graph=graph, known=known)
+        self.graph, self.n_streams = self._launcher.graph, self._launcher.n_streams
+
+    def update(self, fragments):
+        """new density values (same shapes) for the recorded build: fragments[m].rho[op][(ci, cj)] as for build_matrix_elements"""
+        eng = self.build.eng
+        for (m, op, sector), slot in eng._rho_dev.items():
+            block = fragments[m].rho[op][sector]
+            if isinstance(block, torch.Tensor):
+                if block.data_ptr() != slot.data_ptr():
+                    slot.copy_(block.reshape(slot.shape))
+                continue
+            host = torch.from_numpy(numpy.ascontiguousarray(numpy.asarray(block, dtype=numpy.float64)).reshape(tuple(slot.shape)))
+            slot.copy_(host, non_blocking=host.is_pinned())
+
+    def run(self):
+        self._launcher.run()
+        return self.build

@@ -23,6 +23,7 @@ Not planned (they go through get_xr_H directly): bra_det / ket_det, row sharding
 import numpy
 import torch
 
+from ..recording import launch_graph
 from .get_xr_result import get_xr_H, INVERSE_RESIDUAL_TOL
 from .tensor import DeviceTensor, FactoredTensor, as_host, default_device
 
@@ -71,72 +72,24 @@ class plan(object):
         finally:
             self.trace, self._alive = dev.end_trace()
         self.launches = len(self.trace)
-        # 3. the same sequence as one CUDA graph
-        self.graph, self.n_streams = None, 1
-        if graph and dev.torch_device.type == "cuda":
-            if streams > 1:
-                self._capture_streams(streams)
-            if self.graph is None:
-                self._capture()
+        # 3. the same sequence as one CUDA graph (recording.launch_graph: placed on `streams` streams by its data dependencies)
+        self._launcher = launch_graph(dev, self.trace, streams=streams, graph=graph)
 
-    def _capture(self):
-        dev = self.dev
-        try:
-            stream = torch.cuda.Stream(device=dev.torch_device)
-            stream.wait_stream(torch.cuda.current_stream(dev.torch_device))
-            g = torch.cuda.CUDAGraph()
-            with dev.use_stream(stream):
-                with torch.cuda.graph(g, stream=stream):
-                    dev.ctx.replay(self.trace)
-            torch.cuda.current_stream(dev.torch_device).wait_stream(stream)
-            self.graph = g
-        except Exception as exc:          # the recorded calls can still be re-issued one by one
-            self.graph, self.graph_error = None, repr(exc)
+    @property
+    def graph(self):
+        return self._launcher.graph
 
-    def _issue_on_streams(self, streams, contexts, stream_of, cross):
-        """the recorded calls, each on its stream (through a context of its own: no shared scratch), with an event wait for
-        every dependency that crosses streams; the first stream forks the others and joins them at the end"""
-        needed = set(j for c in cross for j in c)
-        start = torch.cuda.Event()
-        start.record(streams[0])
-        for s in streams[1:]:
-            s.wait_event(start)
-        events = {}
-        for i, (call, args, kwargs) in enumerate(self.trace):
-            s = streams[stream_of[i]]
-            for j in cross[i]:
-                s.wait_event(events[j])
-            call(contexts[stream_of[i]], *args, **kwargs)
-            if i in needed:
-                events[i] = torch.cuda.Event()
-                events[i].record(s)
-        for s in streams[1:]:
-            done = torch.cuda.Event()
-            done.record(s)
-            streams[0].wait_event(done)
+    @property
+    def n_streams(self):
+        return self._launcher.n_streams
 
-    def _capture_streams(self, n_streams):
-        from .. import lib as _lib
-        from . import schedule
-        dev = self.dev
-        try:
-            deps = schedule.dependencies(self.trace)
-            stream_of, cross = schedule.assign_streams(deps, n_streams)
-            streams = [torch.cuda.Stream(device=dev.torch_device) for _ in range(n_streams)]
-            contexts = [_lib.Context(dev.index, s.cuda_stream) for s in streams]
-            current = torch.cuda.current_stream(dev.torch_device)
-            streams[0].wait_stream(current)
-            self._issue_on_streams(streams, contexts, stream_of, cross)      # sizes every context's scratch before the capture
-            current.wait_stream(streams[0])
-            torch.cuda.synchronize(dev.index)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=streams[0]):
-                self._issue_on_streams(streams, contexts, stream_of, cross)
-            self.graph, self.n_streams = g, n_streams
-            self._stream_contexts = contexts                                   # their scratch buffers belong to the graph
-            self.cross_stream_dependencies = sum(len(c) for c in cross)
-        except Exception as exc:
-            self.graph, self.streams_error = None, repr(exc)
+    @property
+    def graph_error(self):
+        return self._launcher.graph_error
+
+    @property
+    def streams_error(self):
+        return self._launcher.streams_error
 
     def update(self, dens):
         """copy new density values into the input slots (host blocks: H2D; device blocks: D2D unless they ARE the slot)"""
@@ -158,10 +111,7 @@ class plan(object):
 
     def run(self):
         """launch the recorded build; results stay on the device in self.H1 / self.H2"""
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self.dev.ctx.replay(self.trace)
+        self._launcher.run()
         self.replays += 1
 
     def __call__(self, dens=None):
@@ -178,8 +128,7 @@ class plan(object):
                 return E1, E2
             if not (numpy.array_equal(E2, H2) and all(numpy.array_equal(a, b) for a, b in zip(E1, H1))):
                 if self.n_streams > 1:      # a dependency the analysis missed would show here: back to the single-stream chain
-                    self.graph, self.n_streams = None, 1
-                    self._capture()
+                    self._launcher.single_stream()
                     return self.__call__()
                 raise RuntimeError("plan: the replayed launch sequence does not reproduce get_xr_H on new densities "
                                    "(max diff %.3e); some input of the build was not recorded as a slot" % numpy.abs(E2 - H2).max())

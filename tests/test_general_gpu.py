@@ -604,3 +604,30 @@ def test_zero_size_arguments_are_no_ops(dev):
     c.trimer_stream(4, 3, 2, 5, 1.0, None, 16, None, 4, None, 4, 2, 2, xr.TRIMER_REDUCE, None)
     c.embed_add(None, None, 1, 0, 0, 1, None, None)
     assert c.launch_count() == before
+
+
+@pytest.mark.parametrize("name", ["toy3", "cfg3"])
+def test_recorded_step_is_one_cuda_graph(dev, name):
+    """general/distributed.recorded_step on the GPU: the recorded build step as a CUDA graph (single- and multi-stream) gives
+    the eager step's blocks bit for bit, and follows new densities"""
+    from qodeapplications_b200.general.build_H import build_matrix_elements
+    from qodeapplications_b200.general.distributed import sharded_build
+    system = synth.make_system(name)
+    eng = _engine(system, dev)
+    dimers = list(itertools.combinations(range(3), 2))
+    build = sharded_build(eng, dimers, [(0, 1, 2)])
+    build.step()
+    want = [build.full(*k).clone() for k in dimers] + [build.H3_moments[(0, 1, 2)].clone(), build.H1[0].clone()]
+    for streams in (1, 16):
+        rec = build.recorded(streams=streams)
+        assert rec.graph is not None and rec.n_streams == streams, (rec._launcher.graph_error, rec._launcher.streams_error)
+        for _ in range(2):
+            rec.run()
+        got = [build.full(*k) for k in dimers] + [build.H3_moments[(0, 1, 2)], build.H1[0]]
+        assert all(torch.equal(a, b) for a, b in zip(got, want)), streams
+    other = synth.make_system(name, seed=99)
+    rec.update(other["fragments"])
+    rec.run()
+    fresh = build_matrix_elements(other["fragments"], system["symm"], system["nuc"], device=dev)
+    assert numpy.array_equal(dev.download(build.full(0, 2)), fresh.H2(0, 2))
+    assert numpy.array_equal(dev.download(build.H3_moments[(0, 1, 2)]), fresh.H3_moments(0, 1, 2, per_class=True))
