@@ -358,6 +358,9 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
             const unsigned char* as = smem + (size_t)s * (TILE_A_BYTES + TILE_B_BYTES);
             const unsigned char* bs = as + TILE_A_BYTES;
             const int ksteps = kt == KT - 1 ? last_ksteps : TBK / 4;
+#if defined(XR_GEMM_DIAG_NO_DMMA)         // timing-only diagnostic (wrong results): the ring and the epilogue without the tensor work
+            if (kt >= 0) { __syncwarp(); if (lane == 0) mbar_arrive_cta(&empty[s]); continue; }
+#endif
 #pragma unroll
             for (int ks = 0; ks < TBK / 4; ++ks) {
                 if (ks >= ksteps) break;
@@ -375,6 +378,17 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
             if (lane == 0) mbar_arrive_cta(&empty[s]);           // this warp no longer reads the stage
         }
 
+#if defined(XR_GEMM_DIAG_NO_STORE)        // timing-only diagnostic (wrong results): the tile is formed and thrown away
+        {
+            double sink = 0.0;
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) sink += acc[i][j][0] + acc[i][j][1];
+            if (sink == 1.2345e301) p.C[0] = sink;
+            continue;
+        }
+#endif
         // epilogue: lane holds C[8i+g][8j+2t], C[8i+g][8j+2t+1]
         int64_t on[NJ][2];
 #pragma unroll

@@ -15,8 +15,8 @@ from qodeapplications_b200 import build as xr_build
 OUT = os.path.join(ROOT, "tools", "variants")
 VARIANTS = {
     "shipped": [],
-    "warps8_4ctas": ["-DXR_GEMM_PERSISTENT_WARPS_N=4"],
-    "warps8_3ctas_4stages": ["-DXR_GEMM_PERSISTENT_WARPS_N=4", "-DXR_GEMM_PERSISTENT_STAGES=4"],
+    "diag_no_store": ["-DXR_GEMM_DIAG_NO_STORE"],          # timing only: tiles formed, never written
+    "diag_no_dmma": ["-DXR_GEMM_DIAG_NO_DMMA"],            # timing only: ring + epilogue stores, no tensor work
 }
 
 
