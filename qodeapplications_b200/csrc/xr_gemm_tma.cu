@@ -55,6 +55,10 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
 #define XR_GEMM_PERSISTENT_MAX_KT 4
 #endif
 
+// ... whether K <= 48 goes to the whole-K kernel (one stage per tile) instead:
+#ifndef XR_GEMM_WHOLEK
+#define XR_GEMM_WHOLEK 1
+#endif
 // ... and the ring depth of the persistent kernel: deeper rings prefetch further across tile boundaries but fewer CTAs fit an SM
 #ifndef XR_GEMM_PERSISTENT_STAGES
 #define XR_GEMM_PERSISTENT_STAGES 3
@@ -427,6 +431,143 @@ gemm_tma_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     }
 }
 
+// Whole-K variant for K <= 48 (the d = +-1 dimer classes: K = 2n = 36; the K = n diagram products of hermitian-XRCC): the
+// three k-tiles of an output tile are ONE stage with ONE barrier pair, so a warp runs its nine k-steps without a barrier or
+// a dependent shared-memory round trip in between (the timing diagnostics of profiles/r02u put the ring + DMMAs of the
+// per-k-tile kernel at 0.283 ms where the DMMA work is 0.193 ms).  The 48 KB stage is refilled for the CTA's next tile as soon
+// as every warp has read it -- thread 0 issues that before its own epilogue -- so the loads fly under the stores; four
+// CTAs per SM cover what is left of the latency.  Tiles are handed out by the atomic counter, fetched a tile ahead.
+__global__ void __launch_bounds__(TTHREADS, 4)
+gemm_tma_wholek_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmTmaParams p) {
+    constexpr int MI = 4, NJ = 4;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full, empty;
+    __shared__ int64_t next_tile[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int warp_m = warp & 1, warp_n = warp >> 1;
+    const int KT = (int)((p.K + TBK - 1) / TBK);                                   // 1..3
+    const int last_ksteps = (int)((p.K - (int64_t)(KT - 1) * TBK + 3) / 4);
+    const int64_t n_tiles = p.tiles_m * p.tiles_n;
+    const int64_t per_group = GROUP_M * p.tiles_n;
+    auto tile_origin = [&](int64_t tile, int64_t& m0, int64_t& n0) {
+        const int64_t first_m = (tile / per_group) * GROUP_M;
+        const int64_t group_m = p.tiles_m - first_m < GROUP_M ? p.tiles_m - first_m : GROUP_M;
+        m0 = (first_m + (tile % per_group) % group_m) * TBM;
+        n0 = ((tile % per_group) / group_m) * TBN;
+    };
+    if (tid == 0) {
+        mbar_init(&full, 1);
+        mbar_init(&empty, TTHREADS / 32);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // thread 0: hand-out state.  `upcoming` was requested one tile ago (static striding when there is no counter)
+    const bool dynamic = p.tile_counter != nullptr;
+    int64_t upcoming = blockIdx.x, issued = 0;
+    if (tid == 0 && dynamic) upcoming = (int64_t)atomicAdd(p.tile_counter, 1ull);
+    auto issue_tile = [&]() {      // thread 0: publish the next tile id and start its loads (or publish -1)
+        int64_t tile = upcoming;
+        upcoming = dynamic ? (int64_t)atomicAdd(p.tile_counter, 1ull) : upcoming + gridDim.x;
+        if (tile >= n_tiles) tile = -1;
+        if (issued > 0) mbar_wait(&empty, (uint32_t)((issued - 1) & 1));       // every warp has read the previous tile's stage
+        next_tile[issued & 1] = tile;
+        if (tile < 0) {
+            mbar_arrive_cta(&full);
+        } else {
+            int64_t m0, n0;
+            tile_origin(tile, m0, n0);
+            mbar_expect_tx(&full, (uint32_t)KT * (TILE_A_BYTES + TILE_B_BYTES));
+            for (int kt = 0; kt < KT; ++kt) {
+                unsigned char* a = smem + (size_t)kt * (TILE_A_BYTES + TILE_B_BYTES);
+                tma_load_2d(a, &mapA, kt * TBK, (int)m0, &full);
+                tma_load_2d(a + TILE_A_BYTES, &mapB, kt * TBK, (int)n0, &full);
+            }
+        }
+        ++issued;
+    };
+    if (tid == 0) issue_tile();
+
+    for (int64_t seq = 0;; ++seq) {
+        mbar_wait(&full, (uint32_t)(seq & 1));
+        const int64_t tile = next_tile[seq & 1];
+        if (tile < 0) break;
+        int64_t m0, n0;
+        tile_origin(tile, m0, n0);
+        if (p.offN) {
+            const int64_t col = n0 + warp_n * 32 + 2 * t + 8 * (g & 3);
+            if (col < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.offN + col));
+        }
+        if (p.offM) {
+            const int64_t row = m0 + warp_m * 32 + lane;
+            if (row < p.M) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.offM + row));
+        }
+        double acc[MI][NJ][2];
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kt = 0; kt < KT; ++kt) {
+            const unsigned char* as = smem + (size_t)kt * (TILE_A_BYTES + TILE_B_BYTES);
+            const unsigned char* bs = as + TILE_A_BYTES;
+            const int ksteps = kt == KT - 1 ? last_ksteps : TBK / 4;
+#pragma unroll
+            for (int ks = 0; ks < TBK / 4; ++ks) {
+                if (ks >= ksteps) break;
+                double a[MI], b[NJ];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const double*>(as + swz(warp_m * 32 + i * 8 + g, ks * 4 + t));
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double*>(bs + swz(warp_n * 32 + j * 8 + g, ks * 4 + t));
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(&empty);
+        if (tid == 0) issue_tile();           // next tile's loads go out now and land under the stores below
+
+        int64_t on[NJ][2];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            int64_t col = n0 + warp_n * 32 + j * 8 + 2 * t;
+            on[j][0] = col < p.N ? (p.offN ? p.offN[col] : col) : -1;
+            on[j][1] = col + 1 < p.N ? (p.offN ? p.offN[col + 1] : col + 1) : -1;
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            int64_t row = m0 + warp_m * 32 + i * 8 + g;
+            if (row >= p.M) continue;
+            int64_t om = p.offM ? p.offM[row] : row * p.ldc;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                double* dst0 = p.C + om + on[j][0];
+                if (on[j][0] >= 0 && on[j][1] == on[j][0] + 1 && (reinterpret_cast<uintptr_t>(dst0) & 15) == 0) {
+                    double2 v = make_double2(p.alpha * acc[i][j][0], p.alpha * acc[i][j][1]);
+                    if (p.accumulate) {
+                        const double2 old = *reinterpret_cast<double2*>(dst0);
+                        v.x += old.x;
+                        v.y += old.y;
+                    }
+                    *reinterpret_cast<double2*>(dst0) = v;
+                    continue;
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (on[j][e] < 0) continue;
+                    double* dst = p.C + om + on[j][e];
+                    double v = p.alpha * acc[i][j][e];
+                    *dst = p.accumulate ? *dst + v : v;
+                }
+            }
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -745,6 +886,19 @@ int xr_gemm_scatter_tma(xr_ctx* ctx, int64_t M, int64_t N, int64_t K, double alp
         splitk_finish_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p.ws, (int)splits, p);
         XR_CUDA(cudaGetLastError());
         ctx->launches += 2;
+        return XR_OK;
+    }
+    if (XR_GEMM_WHOLEK && KT <= 3) {
+        const int64_t resident = (int64_t)ctx->sm_count * 4;
+        if (tiles > resident) {
+            if (!ctx->counters) XR_CUDA(cudaMalloc(&ctx->counters, 256));
+            XR_CUDA(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+            p.tile_counter = static_cast<unsigned long long*>(ctx->counters);
+        }
+        XR_CUDA(cudaFuncSetAttribute(gemm_tma_wholek_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+        gemm_tma_wholek_kernel<<<(unsigned)(tiles < resident ? tiles : resident), TTHREADS, TMA_SMEM, ctx->stream>>>(mapA, mapB, p);
+        XR_CUDA(cudaGetLastError());
+        ctx->launches++;
         return XR_OK;
     }
     if (XR_GEMM_VARIANT == 0 || KT > XR_GEMM_PERSISTENT_MAX_KT) {

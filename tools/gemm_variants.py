@@ -14,9 +14,8 @@ from qodeapplications_b200 import build as xr_build
 
 OUT = os.path.join(ROOT, "tools", "variants")
 VARIANTS = {
-    "shipped": [],
-    "diag_no_store": ["-DXR_GEMM_DIAG_NO_STORE"],          # timing only: tiles formed, never written
-    "diag_no_dmma": ["-DXR_GEMM_DIAG_NO_DMMA"],            # timing only: ring + epilogue stores, no tensor work
+    "wholek": ["-DXR_GEMM_WHOLEK=1"],
+    "per_ktile_ring": ["-DXR_GEMM_WHOLEK=0"],
 }
 
 
