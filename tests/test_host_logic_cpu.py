@@ -738,3 +738,32 @@ def test_general_recorded_step_replays_and_follows_new_densities():
                 ready.sort()
     assert issued == n
     assert numpy.array_equal(build.full(0, 2).numpy(), before[0]) and numpy.array_equal(build.H3_moments[(0, 1, 2)].numpy(), before[1])
+
+
+def test_schedule_treats_unknown_calls_and_unsized_operands_as_barriers():
+    """schedule.py is conservative by construction: a call it has no footprint for, or an offset table it cannot read,
+    depends on everything before it and everything after depends on it"""
+    from qodeapplications_b200 import schedule
+    dev = FakeDevice()
+    a, b, c, d = (dev.zeros((4, 4)) for _ in range(4))
+
+    def named(name):
+        def call(ctx, *args, **kwargs):
+            return None
+        call.__name__ = name
+        return call
+    trace = [(named("copy2d_scaled"), (b, 4, a, 4, 4, 4, 1.0), {}),                  # b <- a
+             (named("copy2d_scaled"), (d, 4, c, 4, 4, 4, 1.0), {}),                  # d <- c: independent of call 0
+             (named("something_new"), (a,), {}),                                     # unknown: a barrier
+             (named("copy2d_scaled"), (c, 4, d, 4, 4, 4, 1.0), {}),                  # after the barrier
+             (named("gemm_scatter"), (4, 4, 4, 1.0, a, 4, b, 4, c, 12345, 0, None, False), {}),   # raw-pointer table nobody knows
+             (named("copy2d_scaled"), (b, 4, a, 4, 4, 4, 1.0), {})]
+    deps = schedule.dependencies(trace)
+    assert deps[0] == [] and deps[1] == []
+    assert deps[2] == [0, 1]
+    assert deps[3] == [2]
+    assert deps[4] == [3]                  # (the barrier 2 is implied through 3)
+    assert deps[5] == [4]
+    stream_of, cross = schedule.assign_streams(deps, 3)
+    assert stream_of[0] != stream_of[1]
+    assert all(stream_of[j] != stream_of[i] for i, cs in enumerate(cross) for j in cs)
