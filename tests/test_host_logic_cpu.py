@@ -767,3 +767,38 @@ def test_schedule_treats_unknown_calls_and_unsized_operands_as_barriers():
     stream_of, cross = schedule.assign_streams(deps, 3)
     assert stream_of[0] != stream_of[1]
     assert all(stream_of[j] != stream_of[i] for i, cs in enumerate(cross) for j in cs)
+
+
+def test_hermitian_plan_with_device_resident_densities_updated_in_place():
+    """densities already on the device (DeviceTensor blocks, what a density builder on the GPU hands over) ARE the input
+    slots of the plan: the caller rewrites them in place and calls build() with no arguments"""
+    from qodeapplications_b200.hermitian.get_xr_result import get_xr_H
+    from qodeapplications_b200.hermitian.plan import plan
+    from qodeapplications_b200.hermitian.tensor import DeviceTensor
+    system = synth.make_system("toy", ops=synth.OPS_ORDER1, with_bior=True)
+    other = synth.make_system("toy", ops=synth.OPS_ORDER1, with_bior=True, seed=5)["densities"][:2]
+    ch = system["charges"]
+    ints = (system["symm"], system["bior"], system["nuc"])
+    dev = FakeDevice()
+    resident = []
+    for rho in system["densities"][:2]:
+        resident.append({key: ({sector: DeviceTensor(dev.upload(block), dev) for sector, block in value.items()}
+                               if isinstance(value, dict) and key not in ("n_elec", "n_states", "n_states_bra") else value)
+                         for key, value in rho.items()})
+    build = plan(ints, resident, 1, [ch, ch], device=dev)
+    H1, H2 = build()
+    E1, E2 = get_xr_H(ints, system["densities"][:2], 1, [ch, ch], device=FakeDevice())
+    _close(H2, E2, 1e-12)
+    for m, rho in enumerate(other):                       # new values written into the caller's own device buffers
+        for key, value in rho.items():
+            if isinstance(value, dict) and key not in ("n_elec", "n_states", "n_states_bra"):
+                for sector, block in value.items():
+                    resident[m][key][sector].buf.copy_(torch.from_numpy(numpy.ascontiguousarray(block)))
+    R1, R2 = build()
+    F1, F2 = get_xr_H(ints, other, 1, [ch, ch], device=FakeDevice())
+    _close(R2, F2, 1e-12)
+    _close(R1[0], F1[0], 1e-12)
+    with pytest.raises(ValueError):                       # a block of another shape is not this plan's input
+        bad = [dict(rho) for rho in other]
+        bad[0]["ca"] = {sector: numpy.zeros((1,) + block.shape) for sector, block in other[0]["ca"].items()}
+        build(bad)
