@@ -530,6 +530,15 @@ gemm_tma_wholek_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive_cta(&empty);
         if (tid == 0) issue_tile();           // next tile's loads go out now and land under the stores below
+        if (p.alpha != 1.0) {                 // (uniform) the class products have alpha = 1: 32 DMULs per lane less on the pipe the DMMAs use
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    acc[i][j][0] *= p.alpha;
+                    acc[i][j][1] *= p.alpha;
+                }
+        }
 
         int64_t on[NJ][2];
 #pragma unroll
@@ -547,7 +556,7 @@ gemm_tma_wholek_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             for (int j = 0; j < NJ; ++j) {
                 double* dst0 = p.C + om + on[j][0];
                 if (on[j][0] >= 0 && on[j][1] == on[j][0] + 1 && (reinterpret_cast<uintptr_t>(dst0) & 15) == 0) {
-                    double2 v = make_double2(p.alpha * acc[i][j][0], p.alpha * acc[i][j][1]);
+                    double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
                     if (p.accumulate) {
                         const double2 old = *reinterpret_cast<double2*>(dst0);
                         v.x += old.x;
@@ -560,7 +569,7 @@ gemm_tma_wholek_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                 for (int e = 0; e < 2; ++e) {
                     if (on[j][e] < 0) continue;
                     double* dst = p.C + om + on[j][e];
-                    double v = p.alpha * acc[i][j][e];
+                    double v = acc[i][j][e];
                     *dst = p.accumulate ? *dst + v : v;
                 }
             }
